@@ -1,0 +1,40 @@
+# Builds the B200 tensor-verification engine in-tree.
+#   make            -> qsyn_b200/lib/libqsx.so   (C ABI of include/qsx.h; CUDA sm_100a)
+#   make oracle     -> oracle/_build/*           (CPU checker, test infrastructure only)
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CXX       ?= g++
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := -O3 -std=c++20 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wextra -Xptxas -v
+CXXFLAGS  := -O2 -std=c++20 -fPIC -Wall -Wextra -Werror
+
+CSRC      := qsyn_b200/csrc
+LIBDIR    := qsyn_b200/lib
+OBJDIR    := build/obj
+
+LIBQSX    := $(LIBDIR)/libqsx.so
+OBJS      := $(OBJDIR)/kernels.o $(OBJDIR)/runtime.o $(OBJDIR)/planner.o
+
+all: $(LIBQSX)
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.hpp) include/qsx.h $(wildcard qsyn_b200/host/util/*.hpp)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; false)
+
+$(OBJDIR)/%.o: $(CSRC)/%.cpp $(wildcard $(CSRC)/*.hpp) include/qsx.h
+	@mkdir -p $(OBJDIR)
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+$(LIBQSX): $(OBJS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
+
+oracle: oracle/_build/liboracle_c.so
+
+oracle/_build/liboracle_c.so: oracle/oracle_c.c
+	@mkdir -p oracle/_build
+	gcc -O3 -march=native -std=c11 -fPIC -shared -Wall -Wextra -o $@ $< -lm
+
+clean:
+	rm -rf build $(LIBDIR) oracle/_build
+
+.PHONY: all clean oracle

@@ -1,0 +1,173 @@
+/* qsx.h -- C ABI of the B200 tensor-verification engine (libqsx.so).
+ *
+ * This is the drop-in boundary for qsyn's `convert qcir tensor` / `tensor equiv`
+ * hot path.  The reference (DVLab-NTU/qsyn v0.8.1) has no FFI on this path: its
+ * seam is the header trio src/tensor/{tensor_util,tensor,qtensor}.hpp plus
+ * src/convert/qcir_to_tensor.{hpp,cpp}, the only files that name an xtensor
+ * type.  Each entry point below cites the reference interface it replaces
+ * (paths relative to the reference root).  Plain C types only: no torch, no
+ * C++ types, no CUDA types in any signature.
+ *
+ * Conventions
+ *   - A `qsx_unitary` is ONE column shard of the 2^n x 2^n matrix U[out,in]
+ *     that `qc2ts` stores (conversion_cmd.cpp:89): rows = all 2^n output basis
+ *     states, columns = [col0, col0+ncols) of the input basis states, row-major,
+ *     complex128 (re,im doubles), resident in the HBM of one device.
+ *     Qubit 0 is the most significant bit of both indices
+ *     (qcir_to_tensor.cpp:201-208, tensor.hpp:266-274).
+ *   - Every function returns a qsx_status; qsx_last_error() gives the text
+ *     (thread-local).  There is NO CPU fallback: compute entry points return
+ *     QSX_ERR_CUDA when no device is usable.
+ *   - Work is enqueued on one library-owned stream per device
+ *     (qsx_device_stream) and, unless stated otherwise, completed before return.
+ */
+#ifndef QSX_H_
+#define QSX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QSX_ABI_VERSION 1
+#define QSX_MAX_GATE_QUBITS 16
+
+typedef enum qsx_status {
+    QSX_OK              = 0,
+    QSX_ERR_BAD_ARG     = 1,
+    QSX_ERR_OOM         = 2, /* -> "Memory allocation failed!!" (qcir_to_tensor.cpp:211-214) */
+    QSX_ERR_INTERRUPTED = 3, /* -> "Conversion interrupted."    (qcir_to_tensor.cpp:159-162,174-177,196-199) */
+    QSX_ERR_CUDA        = 4,
+    QSX_ERR_NCCL        = 5,
+    QSX_ERR_SHAPE       = 6, /* -> std::invalid_argument / "Shape Mismatch" (tensor.hpp:395, tensor_cmd.cpp:171) */
+    QSX_ERR_UNSUPPORTED = 7  /* -> "Conversion of Gate ... is not supported yet!!" (qcir_to_tensor.cpp:180-183) */
+} qsx_status;
+
+typedef struct qsx_unitary qsx_unitary; /* opaque: one column shard on one device */
+typedef struct qsx_plan    qsx_plan;    /* opaque: a scheduled gate stream        */
+
+/* ---- runtime -------------------------------------------------------------- */
+int         qsx_abi_version(void);
+const char* qsx_last_error(void);
+/* number of usable CUDA devices (0 on a CPU-only host; never an error) */
+int qsx_device_count(int* count);
+/* the cudaStream_t (as void*) all work for `device` is enqueued on */
+int qsx_device_stream(int device, void** stream);
+int qsx_device_synchronize(int device);
+
+/* ---- storage: replaces xt::xarray<complex<double>> inside Tensor<DT> (tensor.hpp:38,144) -------- */
+typedef struct qsx_unitary_info {
+    int32_t  n_qubits;
+    int32_t  device;
+    uint64_t col0;   /* first column of this shard          */
+    uint64_t ncols;  /* number of columns (a power of two)  */
+    uint64_t nrows;  /* 2^n_qubits                          */
+    uint64_t bytes;  /* nrows * ncols * 16                  */
+    void*    data;   /* device pointer, row-major c128      */
+} qsx_unitary_info;
+
+/* uninitialised shard */
+int qsx_unitary_create(int device, int n_qubits, uint64_t col0, uint64_t ncols, qsx_unitary** out);
+/* identity: replaces the n-fold tensordot(tensor, identity(1)) of qcir_to_tensor.cpp:154-164
+ * and QTensor::identity (qtensor.hpp:121-131): one write pass, U[r, r] = 1. */
+int qsx_unitary_set_identity(qsx_unitary* u);
+/* deep copy on the same device: Tensor copy-ctor used by TensorMgr (data_structure_manager.hpp:138-150) */
+int qsx_unitary_clone(const qsx_unitary* u, qsx_unitary** out);
+int qsx_unitary_destroy(qsx_unitary* u);
+int qsx_unitary_get_info(const qsx_unitary* u, qsx_unitary_info* info);
+/* host <-> device; host layout = rows [row0,row0+nrows) x ncols, row-major c128.
+ * Replaces element access / xt::adapt (tensor.hpp:156-175,380) for whole blocks. */
+int qsx_unitary_upload(qsx_unitary* u, uint64_t row0, uint64_t nrows, const double* host);
+int qsx_unitary_download(const qsx_unitary* u, uint64_t row0, uint64_t nrows, double* host);
+
+/* ---- construction: replaces the per-gate tensordot loop (qcir_to_tensor.cpp:173-194 -> tensor.hpp:413-432) */
+typedef struct qsx_gate {
+    int32_t n_ctrls;   /* the first n_ctrls entries of qubits[] are controls (ControlGate, basic_gate_type.hpp:233-256) */
+    int32_t n_targets; /* then n_targets targets; matrix is 2^t x 2^t, first target = MSB                              */
+    int32_t qubits[QSX_MAX_GATE_QUBITS]; /* reference qubit ids: 0 = MSB of the row index                             */
+    const double* matrix; /* host, row-major complex128 (re,im), built with the reference formulas (qtensor.hpp:142-277) */
+} qsx_gate;
+
+typedef struct qsx_plan_options {
+    int32_t struct_size;   /* = sizeof(qsx_plan_options); 0-initialise the rest for defaults                    */
+    int32_t fuse;          /* 0: one sweep per gate (no scheduling); 1 (default): blocked multi-gate sweeps     */
+    double  snap_tol;      /* matrix entries within snap_tol of 0 / +-1 / +-i are snapped (default 1e-15);
+                              < 0 disables snapping: the host-built matrices are applied as given               */
+    int32_t reg_qubits;    /* qubits held in registers per thread (1..4, default 4)                             */
+    int32_t tile_qubits;   /* max row bits staged per shared-memory tile (default 10)                           */
+    int32_t log2_tile_cols;/* log2 of tile width in columns (default 3 -> 128 B contiguous per row)             */
+    int32_t max_ops_per_sweep; /* cap on ops per sweep (default 48)                                             */
+    int32_t lookahead;     /* scheduler scan window in gates (default 4096)                                     */
+    int32_t dense_block;   /* 0 (default): never; k>=3: fold runs of gates on <=k qubits into dense k-blocks    */
+    int32_t reserved[8];
+} qsx_plan_options;
+
+typedef struct qsx_plan_stats {
+    uint64_t n_gates;
+    uint64_t n_ops;        /* lowered ops (identity gates dropped)                */
+    uint64_t n_sweeps;     /* kernel launches per run                             */
+    uint64_t n_stages;     /* register-blocking stages over all sweeps            */
+    uint64_t n_dense_blocks;
+    double   alg_bytes_per_run;   /* sum over sweeps of 32 B x elements touched (this shard geometry) */
+    double   gate_bytes_per_run;  /* sum over GATES of f*32*rows*ncols, f per SURVEY 8(d)              */
+    double   plan_host_ms; /* time spent scheduling on the host                  */
+} qsx_plan_stats;
+
+/* Schedules a gate stream for shards of 2^n_qubits rows x ncols columns.  Pure host work
+ * (runs without a GPU).  Gates are applied left to right: U <- G_k ... G_1 G_0 U. */
+int qsx_plan_create(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gates,
+                    const qsx_plan_options* opt, qsx_plan** out);
+int qsx_plan_destroy(qsx_plan* plan);
+int qsx_plan_get_stats(const qsx_plan* plan, qsx_plan_stats* stats);
+/* Human/machine readable dump of the schedule (JSON) into buf (NUL-terminated);
+ * *needed receives the size required including the NUL. */
+int qsx_plan_dump(const qsx_plan* plan, char* buf, size_t buf_size, size_t* needed);
+
+typedef int (*qsx_stop_fn)(void* arg); /* mirrors `extern bool stop_requested()` (qcir_to_tensor.cpp:20) */
+
+#define QSX_RUN_ASYNC 1u /* do not synchronise at the end (for event timing on qsx_device_stream) */
+
+typedef struct qsx_run_stats {
+    uint64_t launches;   /* kernels launched by this call        */
+    double   device_ms;  /* CUDA-event time of the launches (0 when QSX_RUN_ASYNC) */
+} qsx_run_stats;
+
+/* U <- plan(U) in place.  should_stop (nullable) is polled between sweeps; when it
+ * returns non-zero the call drains the stream and returns QSX_ERR_INTERRUPTED. */
+int qsx_plan_run(const qsx_plan* plan, qsx_unitary* u, qsx_stop_fn should_stop, void* stop_arg,
+                 uint32_t flags, qsx_run_stats* stats);
+/* convenience: plan_create + plan_run + plan_destroy */
+int qsx_apply_gates(qsx_unitary* u, const qsx_gate* gates, size_t n_gates, const qsx_plan_options* opt,
+                    qsx_stop_fn should_stop, void* stop_arg, qsx_run_stats* stats);
+
+/* ---- verification: replaces inner_product / cosine_similarity (tensor.hpp:393-403) and
+ *      global_scalar_factor / global_norm / global_phase / is_equivalent (qtensor.hpp:383-417) ---- */
+/* sums[8] = { Re,Im sum conj(a)*b ; sum |a|^2 ; sum |b|^2 ; Re,Im sum a ; Re,Im sum b } over THIS shard pair,
+ * one fused read-only pass with compensated summation.  a and b must have identical geometry and device
+ * (QSX_ERR_SHAPE otherwise).  Shards of one unitary are combined by adding the 8 doubles
+ * (ncclAllReduce / torch.distributed.all_reduce, SUM). */
+int qsx_equiv_partial(const qsx_unitary* a, const qsx_unitary* b, double sums[8]);
+
+typedef struct qsx_equiv_result {
+    int32_t equivalent;      /* verdict incl. --strict rule (tensor_cmd.cpp:152-160)                      */
+    int32_t phase_defined;   /* 0 when sum(a) == 0 (reference: NaN -> UB, SURVEY Appendix C trap 2)       */
+    double  cosine;          /* |<a,b>| / sqrt(<a,a><b,b>)              (tensor.hpp:401-403)              */
+    double  norm;            /* |sum b / sum a|                         (qtensor.hpp:396-398)             */
+    double  phase_rad;       /* arg(sum b / sum a)                      (qtensor.hpp:409-411)             */
+    int32_t phase_num;       /* dvlab::Phase(phase_rad): rational multiple of pi, Stern-Brocot eps 1e-4   */
+    int32_t phase_den;       /*                                         (phase.hpp:38-40, rational.hpp:97-128) */
+} qsx_equiv_result;
+
+/* host finish from the (all-reduced) sums with the reference formulas */
+int qsx_equiv_finish(const double sums[8], double eps, int strict, qsx_equiv_result* out);
+
+/* ---- whole-tensor ops on one shard ----------------------------------------------- */
+/* conjugate transpose in place; only valid for a full (unsharded) unitary: replaces Tensor::adjoint_inplace (tensor.hpp:303-306) */
+int qsx_unitary_adjoint_inplace(qsx_unitary* u);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QSX_H_ */

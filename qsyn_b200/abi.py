@@ -1,0 +1,274 @@
+"""ctypes binding of include/qsx.h.  No arithmetic here: every call goes to libqsx.so."""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from typing import Iterable, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+QSX_MAX_GATE_QUBITS = 16
+QSX_RUN_ASYNC = 1
+
+STATUS = {
+    0: "QSX_OK", 1: "QSX_ERR_BAD_ARG", 2: "QSX_ERR_OOM", 3: "QSX_ERR_INTERRUPTED", 4: "QSX_ERR_CUDA",
+    5: "QSX_ERR_NCCL", 6: "QSX_ERR_SHAPE", 7: "QSX_ERR_UNSUPPORTED",
+}
+
+
+class QsxError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{STATUS.get(code, code)}: {msg}")
+        self.code = code
+        self.status = STATUS.get(code, str(code))
+
+
+def lib_path() -> str:
+    return os.environ.get("QSX_LIB", os.path.join(_HERE, "lib", "libqsx.so"))
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Loads libqsx.so; fails loudly when the extension has not been built."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise ImportError(f"{path} is missing: build it with `make` (or __graft_entry__.build()); "
+                              "there is no Python or CPU fallback for this path")
+        _lib = C.CDLL(path)
+        _declare(_lib)
+    return _lib
+
+
+class GateStruct(C.Structure):
+    _fields_ = [("n_ctrls", C.c_int32), ("n_targets", C.c_int32), ("qubits", C.c_int32 * QSX_MAX_GATE_QUBITS),
+                ("matrix", C.POINTER(C.c_double))]
+
+
+class PlanOptions(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("fuse", C.c_int32), ("snap_tol", C.c_double), ("reg_qubits", C.c_int32),
+                ("tile_qubits", C.c_int32), ("log2_tile_cols", C.c_int32), ("max_ops_per_sweep", C.c_int32),
+                ("lookahead", C.c_int32), ("dense_block", C.c_int32), ("reserved", C.c_int32 * 8)]
+
+    def __init__(self, fuse: int = 1, **kw):
+        super().__init__()
+        self.struct_size = C.sizeof(PlanOptions)
+        self.fuse = fuse
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise TypeError(k)
+            setattr(self, k, v)
+
+
+class PlanStats(C.Structure):
+    _fields_ = [("n_gates", C.c_uint64), ("n_ops", C.c_uint64), ("n_sweeps", C.c_uint64), ("n_stages", C.c_uint64),
+                ("n_dense_blocks", C.c_uint64), ("alg_bytes_per_run", C.c_double), ("gate_bytes_per_run", C.c_double),
+                ("plan_host_ms", C.c_double)]
+
+
+class RunStats(C.Structure):
+    _fields_ = [("launches", C.c_uint64), ("device_ms", C.c_double)]
+
+
+class UnitaryInfo(C.Structure):
+    _fields_ = [("n_qubits", C.c_int32), ("device", C.c_int32), ("col0", C.c_uint64), ("ncols", C.c_uint64),
+                ("nrows", C.c_uint64), ("bytes", C.c_uint64), ("data", C.c_void_p)]
+
+
+class EquivResult(C.Structure):
+    _fields_ = [("equivalent", C.c_int32), ("phase_defined", C.c_int32), ("cosine", C.c_double), ("norm", C.c_double),
+                ("phase_rad", C.c_double), ("phase_num", C.c_int32), ("phase_den", C.c_int32)]
+
+
+STOP_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
+
+
+def _declare(L: C.CDLL) -> None:
+    vp, i32, u64, dp = C.c_void_p, C.c_int, C.c_uint64, C.POINTER(C.c_double)
+    L.qsx_abi_version.restype = C.c_int
+    L.qsx_last_error.restype = C.c_char_p
+    sig = {
+        "qsx_device_count": [C.POINTER(C.c_int)],
+        "qsx_device_stream": [i32, C.POINTER(vp)],
+        "qsx_device_synchronize": [i32],
+        "qsx_unitary_create": [i32, i32, u64, u64, C.POINTER(vp)],
+        "qsx_unitary_set_identity": [vp],
+        "qsx_unitary_clone": [vp, C.POINTER(vp)],
+        "qsx_unitary_destroy": [vp],
+        "qsx_unitary_get_info": [vp, C.POINTER(UnitaryInfo)],
+        "qsx_unitary_upload": [vp, u64, u64, dp],
+        "qsx_unitary_download": [vp, u64, u64, dp],
+        "qsx_plan_create": [i32, u64, C.POINTER(GateStruct), C.c_size_t, C.POINTER(PlanOptions), C.POINTER(vp)],
+        "qsx_plan_destroy": [vp],
+        "qsx_plan_get_stats": [vp, C.POINTER(PlanStats)],
+        "qsx_plan_dump": [vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)],
+        "qsx_plan_run": [vp, vp, STOP_FN, vp, C.c_uint32, C.POINTER(RunStats)],
+        "qsx_apply_gates": [vp, C.POINTER(GateStruct), C.c_size_t, C.POINTER(PlanOptions), STOP_FN, vp,
+                            C.POINTER(RunStats)],
+        "qsx_equiv_partial": [vp, vp, dp],
+        "qsx_equiv_finish": [dp, C.c_double, i32, C.POINTER(EquivResult)],
+        "qsx_unitary_adjoint_inplace": [vp],
+    }
+    for name, args in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise QsxError(rc, lib().qsx_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    _check(lib().qsx_device_count(C.byref(n)))
+    return n.value
+
+
+def pack_gates(gates: Iterable[tuple]):
+    """gates: iterable of (n_ctrls, qubits[controls first], target_matrix 2^t x 2^t complex128).
+    Returns (ctypes array, keepalive list)."""
+    gates = list(gates)
+    arr = (GateStruct * max(len(gates), 1))()
+    keep = []
+    for i, (n_ctrls, qubits, mat) in enumerate(gates):
+        m = np.ascontiguousarray(np.asarray(mat, dtype=np.complex128))
+        nt = len(qubits) - n_ctrls
+        assert m.shape == (2**nt, 2**nt), (m.shape, nt)
+        keep.append(m)
+        arr[i].n_ctrls = n_ctrls
+        arr[i].n_targets = nt
+        for k, q in enumerate(qubits):
+            arr[i].qubits[k] = int(q)
+        arr[i].matrix = m.ctypes.data_as(C.POINTER(C.c_double))
+    return arr, keep, len(gates)
+
+
+class Plan:
+    def __init__(self, n_qubits: int, ncols: int, gates: Iterable[tuple], options: PlanOptions | None = None):
+        arr, keep, n = pack_gates(gates)
+        self._h = C.c_void_p()
+        _check(lib().qsx_plan_create(n_qubits, ncols, arr, n, C.byref(options) if options is not None else None,
+                                     C.byref(self._h)))
+        self.n_qubits, self.ncols = n_qubits, ncols
+
+    def stats(self) -> PlanStats:
+        s = PlanStats()
+        _check(lib().qsx_plan_get_stats(self._h, C.byref(s)))
+        return s
+
+    def dump(self) -> dict:
+        need = C.c_size_t(0)
+        _check(lib().qsx_plan_dump(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        _check(lib().qsx_plan_dump(self._h, buf, need.value, None))
+        return json.loads(buf.value.decode())
+
+    def run(self, u: "Unitary", should_stop=None, flags: int = 0) -> RunStats:
+        st = RunStats()
+        cb = STOP_FN(lambda _arg: int(bool(should_stop()))) if should_stop is not None else C.cast(None, STOP_FN)
+        _check(lib().qsx_plan_run(self._h, u._h, cb, None, flags, C.byref(st)))
+        return st
+
+    def close(self):
+        if self._h:
+            lib().qsx_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Unitary:
+    """One column shard of U[out,in] on one device."""
+
+    def __init__(self, n_qubits: int, device: int = 0, col0: int = 0, ncols: int | None = None, identity: bool = True,
+                 _handle=None):
+        if _handle is not None:
+            self._h = _handle
+        else:
+            ncols = 2**n_qubits if ncols is None else ncols
+            self._h = C.c_void_p()
+            _check(lib().qsx_unitary_create(device, n_qubits, col0, ncols, C.byref(self._h)))
+            if identity:
+                _check(lib().qsx_unitary_set_identity(self._h))
+
+    @property
+    def info(self) -> UnitaryInfo:
+        i = UnitaryInfo()
+        _check(lib().qsx_unitary_get_info(self._h, C.byref(i)))
+        return i
+
+    def set_identity(self):
+        _check(lib().qsx_unitary_set_identity(self._h))
+
+    def clone(self) -> "Unitary":
+        h = C.c_void_p()
+        _check(lib().qsx_unitary_clone(self._h, C.byref(h)))
+        return Unitary(0, _handle=h)
+
+    def download(self, row0: int = 0, nrows: int | None = None) -> np.ndarray:
+        i = self.info
+        nrows = i.nrows - row0 if nrows is None else nrows
+        out = np.empty((nrows, i.ncols), dtype=np.complex128)
+        _check(lib().qsx_unitary_download(self._h, row0, nrows, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def upload(self, host: np.ndarray, row0: int = 0):
+        i = self.info
+        h = np.ascontiguousarray(host, dtype=np.complex128)
+        assert h.ndim == 2 and h.shape[1] == i.ncols
+        _check(lib().qsx_unitary_upload(self._h, row0, h.shape[0], h.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def apply(self, gates: Iterable[tuple], options: PlanOptions | None = None, should_stop=None) -> RunStats:
+        arr, keep, n = pack_gates(gates)
+        st = RunStats()
+        cb = STOP_FN(lambda _arg: int(bool(should_stop()))) if should_stop is not None else C.cast(None, STOP_FN)
+        _check(lib().qsx_apply_gates(self._h, arr, n, C.byref(options) if options is not None else None, cb, None,
+                                     C.byref(st)))
+        return st
+
+    def equiv_partial(self, other: "Unitary") -> np.ndarray:
+        out = np.zeros(8, dtype=np.float64)
+        _check(lib().qsx_equiv_partial(self._h, other._h, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def adjoint_inplace(self):
+        _check(lib().qsx_unitary_adjoint_inplace(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().qsx_unitary_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def equiv_finish(sums: Sequence[float], eps: float = 1e-6, strict: bool = False) -> EquivResult:
+    s = np.ascontiguousarray(np.asarray(sums, dtype=np.float64))
+    r = EquivResult()
+    _check(lib().qsx_equiv_finish(s.ctypes.data_as(C.POINTER(C.c_double)), eps, int(strict), C.byref(r)))
+    return r
+
+
+def device_stream(device: int = 0) -> int:
+    p = C.c_void_p()
+    _check(lib().qsx_device_stream(device, C.byref(p)))
+    return p.value
+
+
+def device_synchronize(device: int = 0) -> None:
+    _check(lib().qsx_device_synchronize(device))

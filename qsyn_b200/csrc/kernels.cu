@@ -1,0 +1,548 @@
+// kernels.cu -- hand-written sm_100a kernels of the tensor-verification hot path.
+//
+//   sweep_kernel<R>   K1: in-place strided gate-apply.  One launch = one read+write pass over
+//                     the shard.  A CTA owns a tile of 2^m rows x W columns; each thread holds
+//                     2^R rows x 1 column in registers and interprets the sweep's op list on
+//                     them; between stages the tile is transposed through shared memory so a
+//                     different set of R row bits becomes register-resident.  Every global and
+//                     shared access is a 128-bit (one complex128) access, and adjacent lanes
+//                     take adjacent columns, so accesses are coalesced for ANY row bit
+//                     (replaces xt::linalg::tensordot, tensor.hpp:418).
+//   set_identity      K2: one write pass (replaces qcir_to_tensor.cpp:154-164).
+//   equiv_*           K4: fused 8-sum reduction with compensated accumulation
+//                     (replaces the lazy xt::sum loops of tensor.hpp:393-403, qtensor.hpp:383-385).
+//   adjoint_inplace   K5: tiled conjugate transpose (tensor.hpp:303-306).
+#include <cstdint>
+#include <type_traits>
+
+#include "kernels.hpp"
+
+namespace qsx {
+
+namespace {
+
+
+// ---------------------------------------------------------------------------------------
+// complex helpers (explicit FMA forms so the arithmetic does not depend on contraction flags)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
+}
+// a*b + c
+__device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 c) {
+    return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
+}
+
+template <int N, int I = 0, class Fn>
+__device__ __forceinline__ void static_switch(int v, Fn&& fn) {
+    if constexpr (I < N) {
+        if (v == I)
+            fn(std::integral_constant<int, I>{});
+        else
+            static_switch<N, I + 1>(v, fn);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// register-level ops.  E = 2^R elements; `creg` is a required-one mask over the register
+// index (uniform across the grid, so every test below is a uniform branch).
+// ---------------------------------------------------------------------------------------
+template <int R, int J>
+__device__ __forceinline__ void op_u1(double2 (&e)[1 << R], const double* __restrict__ c, uint32_t creg) {
+    double2 const m00 = make_double2(__ldg(c + 0), __ldg(c + 1)), m01 = make_double2(__ldg(c + 2), __ldg(c + 3));
+    double2 const m10 = make_double2(__ldg(c + 4), __ldg(c + 5)), m11 = make_double2(__ldg(c + 6), __ldg(c + 7));
+#pragma unroll
+    for (int i = 0; i < (1 << R); ++i) {
+        if ((i >> J) & 1) continue;
+        if ((i & creg) != creg) continue;
+        double2 const a = e[i], b = e[i | (1 << J)];
+        e[i]            = cfma(m01, b, cmul(m00, a));
+        e[i | (1 << J)] = cfma(m11, b, cmul(m10, a));
+    }
+}
+
+template <int R, int J>
+__device__ __forceinline__ void op_h(double2 (&e)[1 << R], double s, uint32_t creg) {
+#pragma unroll
+    for (int i = 0; i < (1 << R); ++i) {
+        if ((i >> J) & 1) continue;
+        if ((i & creg) != creg) continue;
+        double2 const a = e[i], b = e[i | (1 << J)];
+        e[i]            = make_double2(s * (a.x + b.x), s * (a.y + b.y));
+        e[i | (1 << J)] = make_double2(s * (a.x - b.x), s * (a.y - b.y));
+    }
+}
+
+template <int R, int J>
+__device__ __forceinline__ void op_x(double2 (&e)[1 << R], uint32_t creg) {
+#pragma unroll
+    for (int i = 0; i < (1 << R); ++i) {
+        if ((i >> J) & 1) continue;
+        if ((i & creg) != creg) continue;
+        double2 const a = e[i];
+        e[i]            = e[i | (1 << J)];
+        e[i | (1 << J)] = a;
+    }
+}
+
+template <int R, int J>
+__device__ __forceinline__ void op_ad(double2 (&e)[1 << R], const double* __restrict__ c, uint32_t creg) {
+    double2 const m01 = make_double2(__ldg(c + 0), __ldg(c + 1)), m10 = make_double2(__ldg(c + 2), __ldg(c + 3));
+#pragma unroll
+    for (int i = 0; i < (1 << R); ++i) {
+        if ((i >> J) & 1) continue;
+        if ((i & creg) != creg) continue;
+        double2 const a = e[i], b = e[i | (1 << J)];
+        e[i]            = cmul(m01, b);
+        e[i | (1 << J)] = cmul(m10, a);
+    }
+}
+
+template <int R, int JA, int JB>
+__device__ __forceinline__ void op_swap(double2 (&e)[1 << R], uint32_t creg) {
+#pragma unroll
+    for (int i = 0; i < (1 << R); ++i) {
+        if (!((i >> JA) & 1) || ((i >> JB) & 1)) continue;
+        if ((i & creg) != creg) continue;  // controls never include the swapped bits
+        constexpr int flip = (1 << JA) | (1 << JB);
+        double2 const a    = e[i];
+        e[i]               = e[i ^ flip];
+        e[i ^ flip]        = a;
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void op_u2(double2 (&e)[1 << R], const double* __restrict__ m, uint32_t creg) {
+    if constexpr (R >= 2) {
+#pragma unroll
+        for (int g = 0; g < (1 << R); g += 4) {
+            if ((g & creg) != creg) continue;
+            double2 v[4], w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = e[g + k];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    double2 const mk = make_double2(__ldg(m + 2 * (4 * r + k)), __ldg(m + 2 * (4 * r + k) + 1));
+                    acc              = cfma(mk, v[k], acc);
+                }
+                w[r] = acc;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) e[g + k] = w[k];
+        }
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void apply_op(double2 (&e)[1 << R], const DevOp* __restrict__ op, uint32_t grow,
+                                         const double* __restrict__ pool) {
+    int4 const hdr        = __ldg(reinterpret_cast<const int4*>(op));       // kind, j0, j1, creg
+    int4 const hdr2       = __ldg(reinterpret_cast<const int4*>(op) + 1);   // cother, pool, pad0, pad1
+    uint32_t const creg   = (uint32_t)hdr.w;
+    uint32_t const cother = (uint32_t)hdr2.x;
+    if ((grow & cother) != cother) return;
+    const double* c = op->c;
+    switch (hdr.x) {
+        case OP_U1:
+            static_switch<R>(hdr.y, [&](auto J) { op_u1<R, decltype(J)::value>(e, c, creg); });
+            break;
+        case OP_H: {
+            double const s = __ldg(c);
+            static_switch<R>(hdr.y, [&](auto J) { op_h<R, decltype(J)::value>(e, s, creg); });
+            break;
+        }
+        case OP_X:
+            static_switch<R>(hdr.y, [&](auto J) { op_x<R, decltype(J)::value>(e, creg); });
+            break;
+        case OP_AD:
+            static_switch<R>(hdr.y, [&](auto J) { op_ad<R, decltype(J)::value>(e, c, creg); });
+            break;
+        case OP_PHASE: {
+            double2 const w = make_double2(__ldg(c), __ldg(c + 1));
+#pragma unroll
+            for (int i = 0; i < (1 << R); ++i)
+                if ((i & creg) == creg) e[i] = cmul(e[i], w);
+            break;
+        }
+        case OP_NEG:
+#pragma unroll
+            for (int i = 0; i < (1 << R); ++i)
+                if ((i & creg) == creg) e[i] = make_double2(-e[i].x, -e[i].y);
+            break;
+        case OP_MULI: {
+            double const s = __ldg(c);  // +1: multiply by +i ; -1: by -i
+#pragma unroll
+            for (int i = 0; i < (1 << R); ++i)
+                if ((i & creg) == creg) e[i] = make_double2(-s * e[i].y, s * e[i].x);
+            break;
+        }
+        case OP_DIAG: {
+            double2 const d0 = make_double2(__ldg(c), __ldg(c + 1)), d1 = make_double2(__ldg(c + 2), __ldg(c + 3));
+            int const j0 = hdr.y;
+            if (j0 >= 0) {
+#pragma unroll
+                for (int i = 0; i < (1 << R); ++i)
+                    if ((i & creg) == creg) e[i] = cmul(e[i], ((i >> j0) & 1) ? d1 : d0);
+            } else {
+                double2 const d = ((grow >> hdr2.z) & 1u) ? d1 : d0;
+#pragma unroll
+                for (int i = 0; i < (1 << R); ++i)
+                    if ((i & creg) == creg) e[i] = cmul(e[i], d);
+            }
+            break;
+        }
+        case OP_SWAP: {
+            int const ja = hdr.y > hdr.z ? hdr.y : hdr.z, jb = hdr.y > hdr.z ? hdr.z : hdr.y;
+            static_switch<R>(ja, [&](auto JA) {
+                static_switch<decltype(JA)::value>(jb, [&](auto JB) {
+                    op_swap<R, decltype(JA)::value, decltype(JB)::value>(e, creg);
+                });
+            });
+            break;
+        }
+        case OP_U2:
+            op_u2<R>(e, pool + hdr2.y, creg);
+            break;
+        default:
+            break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// the sweep interpreter
+// ---------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(1 << max_threads_log2(R), 1)
+    sweep_kernel(double2* __restrict__ u, const unsigned char* __restrict__ prog, uint64_t ncols, int log2_ncb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* const tile = reinterpret_cast<double2*>(smem_raw);
+
+    const DevSweep* const sw     = reinterpret_cast<const DevSweep*>(prog);
+    const DevStage* const stages = reinterpret_cast<const DevStage*>(prog + sizeof(DevSweep));
+    int const n_stages           = sw->n_stages;
+    const DevOp* const ops       = reinterpret_cast<const DevOp*>(stages + n_stages);
+    const double* const pool     = reinterpret_cast<const double*>(ops + sw->n_ops);
+
+    int const log2w      = sw->log2w;
+    uint32_t const tid   = threadIdx.x;
+    uint32_t const cw    = tid & ((1u << log2w) - 1u);
+    uint32_t const trow  = tid >> log2w;
+    uint64_t const tid64 = blockIdx.x;
+    uint64_t const cb    = tid64 & ((1ull << log2_ncb) - 1ull);
+    uint32_t const rc    = (uint32_t)(tid64 >> log2_ncb);
+
+    // row bits fixed by the tile id
+    uint32_t row_outer = sw->fixed_one;
+    {
+        int const n_outer = sw->n_outer;
+        for (int k = 0; k < n_outer; ++k) row_outer |= ((rc >> k) & 1u) << sw->outer[k];
+    }
+    uint64_t const col = (cb << log2w) + cw;
+
+    double2 e[1 << R];
+
+    for (int s = 0; s < n_stages; ++s) {
+        const DevStage* const st = stages + s;
+        // this thread's rows: tile-local index (register bits = 0) and the global row it maps to
+        uint32_t lbase = 0, grow = row_outer;
+        {
+            int const n_t = st->n_t;
+            for (int k = 0; k < n_t; ++k) {
+                int const l      = st->tl[k];
+                uint32_t const b = (trow >> k) & 1u;
+                lbase |= b << l;
+                grow |= b << sw->sp[l];
+            }
+        }
+        int rl[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) rl[j] = st->rl[j];
+
+        if (s == 0) {
+            size_t gs[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j) gs[j] = ((size_t)1 << sw->sp[rl[j]]) * ncols;
+            const double2* const gp = u + (size_t)grow * ncols + col;
+#pragma unroll
+            for (int i = 0; i < (1 << R); ++i) {
+                size_t off = 0;
+#pragma unroll
+                for (int j = 0; j < R; ++j)
+                    if ((i >> j) & 1) off += gs[j];
+                e[i] = gp[off];
+            }
+        } else {
+            uint32_t ss[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j) ss[j] = (1u << rl[j]) << log2w;
+            const double2* const sp_ = tile + ((lbase << log2w) + cw);
+#pragma unroll
+            for (int i = 0; i < (1 << R); ++i) {
+                uint32_t off = 0;
+#pragma unroll
+                for (int j = 0; j < R; ++j)
+                    if ((i >> j) & 1) off += ss[j];
+                e[i] = sp_[off];
+            }
+            __syncthreads();  // all reads of the previous layout done before anyone overwrites it
+        }
+
+        {
+            int const ob = st->op_begin, oe = st->op_end;
+            for (int o = ob; o < oe; ++o) apply_op<R>(e, ops + o, grow, pool);
+        }
+
+        if (s == n_stages - 1) {
+            size_t gs[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j) gs[j] = ((size_t)1 << sw->sp[rl[j]]) * ncols;
+            double2* const gp = u + (size_t)grow * ncols + col;
+#pragma unroll
+            for (int i = 0; i < (1 << R); ++i) {
+                size_t off = 0;
+#pragma unroll
+                for (int j = 0; j < R; ++j)
+                    if ((i >> j) & 1) off += gs[j];
+                gp[off] = e[i];
+            }
+        } else {
+            uint32_t ss[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j) ss[j] = (1u << rl[j]) << log2w;
+            double2* const sp_ = tile + ((lbase << log2w) + cw);
+#pragma unroll
+            for (int i = 0; i < (1 << R); ++i) {
+                uint32_t off = 0;
+#pragma unroll
+                for (int j = 0; j < R; ++j)
+                    if ((i >> j) & 1) off += ss[j];
+                sp_[off] = e[i];
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <int R>
+cudaError_t launch_sweep_r(double2* u, int n, uint64_t ncols, const DevSweep& hs, const unsigned char* prog,
+                           cudaStream_t s) {
+    (void)n;
+    int const m        = hs.m;
+    int const threads  = 1 << (m - R + hs.log2w);
+    size_t const smem  = hs.n_stages > 1 ? ((size_t)16 << (m + hs.log2w)) : 0;
+    int log2_ncols     = 0;
+    while ((1ull << log2_ncols) < ncols) ++log2_ncols;
+    int const log2_ncb = log2_ncols - hs.log2w;
+    uint64_t const nblocks = 1ull << (log2_ncb + hs.n_outer);
+    if (threads < 1 || threads > (1 << max_threads_log2(R)) || nblocks > 0x7fffffffull)
+        return cudaErrorInvalidConfiguration;
+    static bool attr_set[64] = {};  // per template instantiation, per device
+    int dev                  = 0;
+    if (cudaError_t const rc = cudaGetDevice(&dev); rc != cudaSuccess) return rc;
+    if (dev < 64 && !attr_set[dev]) {
+        cudaError_t const rc =
+            cudaFuncSetAttribute(sweep_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (rc != cudaSuccess) return rc;
+        attr_set[dev] = true;
+    }
+    sweep_kernel<R><<<(unsigned)nblocks, threads, smem, s>>>(u, prog, ncols, log2_ncb);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// identity
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) set_identity_kernel(double2* __restrict__ u, uint64_t n_elems, uint64_t col0,
+                                                           int log2_ncols) {
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t const cmask  = (1ull << log2_ncols) - 1ull;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += stride) {
+        uint64_t const r = i >> log2_ncols, c = i & cmask;
+        u[i]             = make_double2(r == col0 + c ? 1.0 : 0.0, 0.0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// equivalence reduction
+// ---------------------------------------------------------------------------------------
+constexpr int kEqThreads = 256;
+constexpr int kEqBlocks  = 148 * 4;
+constexpr int kEqUnroll  = 4;
+
+struct Kahan {
+    double s = 0.0, c = 0.0;
+    __device__ __forceinline__ void add(double x) {
+        // Neumaier variant: exact for |x| > |s| as well
+        double const t = s + x;
+        c += (fabs(s) >= fabs(x)) ? ((s - t) + x) : ((x - t) + s);
+        s = t;
+    }
+    __device__ __forceinline__ double value() const { return s + c; }
+};
+
+__device__ __forceinline__ void accumulate8(Kahan (&acc)[8], const double2 (&a)[kEqUnroll], const double2 (&b)[kEqUnroll]) {
+    double p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < kEqUnroll; ++k) {
+        p[0] += fma(a[k].x, b[k].x, a[k].y * b[k].y);     // Re conj(a) b
+        p[1] += fma(a[k].x, b[k].y, -(a[k].y * b[k].x));  // Im conj(a) b
+        p[2] += fma(a[k].x, a[k].x, a[k].y * a[k].y);
+        p[3] += fma(b[k].x, b[k].x, b[k].y * b[k].y);
+        p[4] += a[k].x;
+        p[5] += a[k].y;
+        p[6] += b[k].x;
+        p[7] += b[k].y;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q].add(p[q]);
+}
+
+// two-sum merge of (s,c) pairs through the block: warp shuffle then shared memory
+__device__ __forceinline__ void kahan_merge(Kahan& x, double s2, double c2) {
+    x.add(s2);
+    x.c += c2;
+}
+
+__global__ void __launch_bounds__(kEqThreads) equiv_partial_kernel(const double2* __restrict__ a,
+                                                                   const double2* __restrict__ b, uint64_t n_elems,
+                                                                   double* __restrict__ partials) {
+    Kahan acc[8];
+    uint64_t const stride = (uint64_t)gridDim.x * kEqThreads;
+    uint64_t i            = (uint64_t)blockIdx.x * kEqThreads + threadIdx.x;
+    // main loop: kEqUnroll independent 128-bit loads per operand in flight
+    for (; i + (kEqUnroll - 1) * stride < n_elems; i += kEqUnroll * stride) {
+        double2 va[kEqUnroll], vb[kEqUnroll];
+#pragma unroll
+        for (int k = 0; k < kEqUnroll; ++k) {
+            va[k] = __ldcs(a + i + k * stride);
+            vb[k] = __ldcs(b + i + k * stride);
+        }
+        accumulate8(acc, va, vb);
+    }
+    for (; i < n_elems; i += stride) {
+        double2 va[kEqUnroll], vb[kEqUnroll];
+#pragma unroll
+        for (int k = 0; k < kEqUnroll; ++k) va[k] = vb[k] = make_double2(0.0, 0.0);
+        va[0] = a[i];
+        vb[0] = b[i];
+        accumulate8(acc, va, vb);
+    }
+    // warp level
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            double const s2 = __shfl_down_sync(0xffffffffu, acc[q].s, off);
+            double const c2 = __shfl_down_sync(0xffffffffu, acc[q].c, off);
+            kahan_merge(acc[q], s2, c2);
+        }
+    }
+    __shared__ double sh[kEqThreads / 32][16];
+    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            sh[warp][2 * q]     = acc[q].s;
+            sh[warp][2 * q + 1] = acc[q].c;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        int const q = threadIdx.x;
+        Kahan t;
+        for (int w = 0; w < kEqThreads / 32; ++w) kahan_merge(t, sh[w][2 * q], sh[w][2 * q + 1]);
+        partials[(size_t)blockIdx.x * 16 + 2 * q]     = t.s;
+        partials[(size_t)blockIdx.x * 16 + 2 * q + 1] = t.c;
+    }
+}
+
+// deterministic finish: one block, fixed order
+__global__ void __launch_bounds__(32) equiv_finish_kernel(const double* __restrict__ partials, int n_blocks,
+                                                          double* __restrict__ out8) {
+    if (threadIdx.x < 8) {
+        int const q = threadIdx.x;
+        Kahan t;
+        for (int blk = 0; blk < n_blocks; ++blk)
+            kahan_merge(t, partials[(size_t)blk * 16 + 2 * q], partials[(size_t)blk * 16 + 2 * q + 1]);
+        out8[q] = t.value();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// in-place conjugate transpose (full square matrix), 32x32 tiles, pairs of tiles swapped
+// ---------------------------------------------------------------------------------------
+constexpr int kTr = 32;
+__global__ void __launch_bounds__(kTr * 8) adjoint_inplace_kernel(double2* __restrict__ u, uint64_t dim) {
+    __shared__ double2 ta[kTr][kTr + 1];
+    __shared__ double2 tb[kTr][kTr + 1];
+    uint32_t const bx = blockIdx.x, by = blockIdx.y;
+    if (bx > by) return;  // upper triangle of tile pairs (incl. diagonal)
+    uint64_t const r0 = (uint64_t)by * kTr, c0 = (uint64_t)bx * kTr;
+    int const tx = threadIdx.x & (kTr - 1), ty = threadIdx.x / kTr;  // 8 row groups
+    for (int r = ty; r < kTr; r += 8) {
+        if (r0 + r < dim && c0 + tx < dim) ta[r][tx] = u[(r0 + r) * dim + c0 + tx];
+        if (c0 + r < dim && r0 + tx < dim) tb[r][tx] = u[(c0 + r) * dim + r0 + tx];
+    }
+    __syncthreads();
+    for (int r = ty; r < kTr; r += 8) {
+        // block (by,bx) <- conj(transpose(block (bx,by)))
+        if (r0 + r < dim && c0 + tx < dim) {
+            double2 const v           = tb[tx][r];
+            u[(r0 + r) * dim + c0 + tx] = make_double2(v.x, -v.y);
+        }
+        if (bx != by && c0 + r < dim && r0 + tx < dim) {
+            double2 const v           = ta[tx][r];
+            u[(c0 + r) * dim + r0 + tx] = make_double2(v.x, -v.y);
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_set_identity(double2* u, int n, uint64_t col0, uint64_t ncols, cudaStream_t s) {
+    int log2_ncols = 0;
+    while ((1ull << log2_ncols) < ncols) ++log2_ncols;
+    uint64_t const n_elems = (1ull << n) * ncols;
+    uint64_t blocks        = (n_elems + 255) / 256;
+    if (blocks > 148ull * 16) blocks = 148ull * 16;
+    set_identity_kernel<<<(unsigned)blocks, 256, 0, s>>>(u, n_elems, col0, log2_ncols);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, int R, const DevSweep& hs, const unsigned char* prog,
+                         cudaStream_t s) {
+    switch (R) {
+        case 1: return launch_sweep_r<1>(u, n, ncols, hs, prog, s);
+        case 2: return launch_sweep_r<2>(u, n, ncols, hs, prog, s);
+        case 3: return launch_sweep_r<3>(u, n, ncols, hs, prog, s);
+        case 4: return launch_sweep_r<4>(u, n, ncols, hs, prog, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+size_t equiv_partials_doubles() { return (size_t)kEqBlocks * 16; }
+
+cudaError_t launch_equiv(const double2* a, const double2* b, uint64_t n_elems, double* partials, double* out8,
+                         cudaStream_t s) {
+    uint64_t blocks = (n_elems + kEqThreads - 1) / kEqThreads;
+    if (blocks > (uint64_t)kEqBlocks) blocks = kEqBlocks;
+    if (blocks == 0) blocks = 1;
+    equiv_partial_kernel<<<(unsigned)blocks, kEqThreads, 0, s>>>(a, b, n_elems, partials);
+    cudaError_t rc = cudaGetLastError();
+    if (rc != cudaSuccess) return rc;
+    equiv_finish_kernel<<<1, 32, 0, s>>>(partials, (int)blocks, out8);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_adjoint_inplace(double2* u, int n, cudaStream_t s) {
+    uint64_t const dim = 1ull << n;
+    unsigned const nb  = (unsigned)((dim + kTr - 1) / kTr);
+    dim3 grid(nb, nb);
+    adjoint_inplace_kernel<<<grid, kTr * 8, 0, s>>>(u, dim);
+    return cudaGetLastError();
+}
+
+}  // namespace qsx

@@ -1,0 +1,27 @@
+// kernels.hpp -- launchers of the sm_100a kernels (kernels.cu).  Internal.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "program.hpp"
+
+namespace qsx {
+
+// U[r, c] = (r == col0 + c) ? 1 : 0 over a 2^n x ncols shard (K2 of SURVEY 2.2)
+cudaError_t launch_set_identity(double2* u, int n, uint64_t col0, uint64_t ncols, cudaStream_t s);
+
+// one sweep (K1 a-e): `prog` is the device copy of a serialized DevSweep blob, `hs` its host copy
+cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, int R, const DevSweep& hs, const unsigned char* prog,
+                         cudaStream_t s);
+
+// fused equivalence reduction (K4): 8 compensated sums of a shard pair.
+// `partials` must hold equiv_partials_doubles() doubles of device scratch; out8 is device memory.
+size_t equiv_partials_doubles();
+cudaError_t launch_equiv(const double2* a, const double2* b, uint64_t n_elems, double* partials, double* out8,
+                         cudaStream_t s);
+
+// in-place conjugate transpose of a full 2^n x 2^n matrix (K5)
+cudaError_t launch_adjoint_inplace(double2* u, int n, cudaStream_t s);
+
+}  // namespace qsx

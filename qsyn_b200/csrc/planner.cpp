@@ -1,0 +1,463 @@
+// planner.cpp -- lowers a reference-style gate stream to register-level ops and schedules
+// them into blocked multi-gate sweeps.
+//
+// Replaces, on the host side, the per-gate `tensordot(gate, main)` dispatch of
+// qcir_to_tensor.cpp:173-194: instead of one full-tensor contraction per gate, runs of
+// gates are grouped so that ONE pass over the shard in HBM applies all of them.
+//
+// Scheduling rule (correctness): gate A may be moved before an earlier gate B iff
+// they commute.  We use the sufficient condition "on every shared qubit both act
+// diagonally" -- controls and diagonal gates are diagonal on that qubit.  With
+//   T(g) = row bits g acts on non-diagonally,  D(g) = row bits g only tests,
+// A and B commute when T(A) & (T(B)|D(B)) == 0 and T(B) & (T(A)|D(A)) == 0.
+//
+// Locality rule (performance): only the bits in T(g) have to be inside the shared-memory
+// tile (and, for the stage that applies g, in registers); tested bits can be any row bit.
+#include "planner.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <sstream>
+
+namespace qsx {
+
+namespace {
+
+inline int popc(uint32_t x) { return __builtin_popcount(x); }
+
+struct C2 {
+    double re, im;
+};
+
+double snap1(double x, double tol) {
+    if (tol < 0) return x;
+    if (std::fabs(x) <= tol) return 0.0;
+    if (std::fabs(x - 1.0) <= tol) return 1.0;
+    if (std::fabs(x + 1.0) <= tol) return -1.0;
+    return x;
+}
+
+bool is_zero(C2 z) { return z.re == 0.0 && z.im == 0.0; }
+bool is_one(C2 z) { return z.re == 1.0 && z.im == 0.0; }
+
+int ilog2_exact(uint64_t x) {
+    if (x == 0 || (x & (x - 1))) return -1;
+    int l = 0;
+    while ((x >> l) != 1) ++l;
+    return l;
+}
+
+// ---- lowering ---------------------------------------------------------------------------
+
+int lower_gate(int n, const qsx_gate& g, int gate_index, double tol, std::vector<LoweredOp>& out, std::string& msg) {
+    int const nc = g.n_ctrls, nt = g.n_targets;
+    if (nc < 0 || nt < 1 || nc + nt > QSX_MAX_GATE_QUBITS || g.matrix == nullptr) {
+        msg = "gate " + std::to_string(gate_index) + ": bad arity or null matrix";
+        return QSX_ERR_BAD_ARG;
+    }
+    uint32_t seen = 0, req = 0;
+    for (int i = 0; i < nc + nt; ++i) {
+        int const q = g.qubits[i];
+        if (q < 0 || q >= n) {
+            msg = "gate " + std::to_string(gate_index) + ": qubit id out of range";
+            return QSX_ERR_BAD_ARG;
+        }
+        uint32_t const b = 1u << (n - 1 - q);
+        if (seen & b) {
+            msg = "gate " + std::to_string(gate_index) + ": duplicate qubit id";
+            return QSX_ERR_BAD_ARG;
+        }
+        seen |= b;
+        if (i < nc) req |= b;
+    }
+    double const cfrac = std::ldexp(1.0, -nc);
+    if (nt == 1) {
+        int const tb = n - 1 - g.qubits[nc];
+        C2 m[4];
+        for (int i = 0; i < 4; ++i) m[i] = {snap1(g.matrix[2 * i], tol), snap1(g.matrix[2 * i + 1], tol)};
+        LoweredOp op;
+        op.src_gate = gate_index;
+        op.req      = req;
+        if (is_zero(m[1]) && is_zero(m[2])) {  // diagonal
+            if (is_one(m[0]) && is_one(m[3])) return QSX_OK;  // identity: nothing to do
+            if (is_one(m[0])) {
+                op.req |= 1u << tb;
+                op.frac = cfrac * 0.5;
+                if (m[3].re == -1.0 && m[3].im == 0.0) {
+                    op.kind = OP_NEG;
+                } else if (m[3].re == 0.0 && (m[3].im == 1.0 || m[3].im == -1.0)) {
+                    op.kind = OP_MULI;
+                    op.c[0] = m[3].im;
+                } else {
+                    op.kind = OP_PHASE;
+                    op.c[0] = m[3].re;
+                    op.c[1] = m[3].im;
+                }
+            } else {
+                op.kind = OP_DIAG;
+                op.dbit = tb;
+                op.frac = cfrac;
+                op.c[0] = m[0].re, op.c[1] = m[0].im, op.c[2] = m[3].re, op.c[3] = m[3].im;
+            }
+        } else {
+            op.t0   = tb;
+            op.frac = cfrac;
+            if (is_zero(m[0]) && is_zero(m[3])) {
+                if (is_one(m[1]) && is_one(m[2])) {
+                    op.kind = OP_X;
+                } else {
+                    op.kind = OP_AD;
+                    op.c[0] = m[1].re, op.c[1] = m[1].im, op.c[2] = m[2].re, op.c[3] = m[2].im;
+                }
+            } else if (m[0].im == 0 && m[1].im == 0 && m[2].im == 0 && m[3].im == 0 && m[0].re == m[1].re &&
+                       m[0].re == m[2].re && m[0].re == -m[3].re) {
+                op.kind = OP_H;
+                op.c[0] = m[0].re;
+            } else {
+                op.kind = OP_U1;
+                for (int i = 0; i < 4; ++i) op.c[2 * i] = m[i].re, op.c[2 * i + 1] = m[i].im;
+            }
+        }
+        out.push_back(std::move(op));
+        return QSX_OK;
+    }
+    if (nt == 2) {
+        int const b1 = n - 1 - g.qubits[nc], b0 = n - 1 - g.qubits[nc + 1];
+        std::vector<double> m(32);
+        for (int i = 0; i < 32; ++i) m[i] = snap1(g.matrix[i], tol);
+        static double const kSwap[16] = {1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1};
+        bool is_swap = true, is_id = true;
+        for (int i = 0; i < 16; ++i) {
+            if (m[2 * i] != kSwap[i] || m[2 * i + 1] != 0.0) is_swap = false;
+            if (m[2 * i] != ((i % 5 == 0) ? 1.0 : 0.0) || m[2 * i + 1] != 0.0) is_id = false;
+        }
+        if (is_id) return QSX_OK;
+        LoweredOp op;
+        op.src_gate = gate_index;
+        op.req      = req;
+        op.t0       = b1;
+        op.t1       = b0;
+        if (is_swap) {
+            op.kind = OP_SWAP;
+            op.frac = cfrac * 0.5;
+        } else {
+            op.kind = OP_U2;
+            op.frac = cfrac;
+            op.mat  = std::move(m);
+        }
+        out.push_back(std::move(op));
+        return QSX_OK;
+    }
+    msg = "gate " + std::to_string(gate_index) + ": " + std::to_string(nt) +
+          "-target dense gates are not supported (flatten nested circuits on the host)";
+    return QSX_ERR_UNSUPPORTED;
+}
+
+// ---- scheduling -------------------------------------------------------------------------
+
+struct Picker {
+    uint32_t blockedT = 0, blockedA = 0;
+    bool passes(LoweredOp const& op) const {
+        uint32_t const T = op.tmask(), A = T | op.dmask();
+        return (T & blockedA) == 0 && (A & blockedT) == 0;
+    }
+    void block(LoweredOp const& op) {
+        blockedT |= op.tmask();
+        blockedA |= op.tmask() | op.dmask();
+    }
+};
+
+void build_stages(Plan& plan, std::vector<int> chosen, PlannedSweep& sw) {
+    int const R = plan.cfg.R;
+    uint32_t tile_mask = 0;
+    for (int b : sw.tile_bits) tile_mask |= 1u << b;
+    while (!chosen.empty()) {
+        PlannedStage st;
+        uint32_t rm = 0;
+        int u2_t0 = -1, u2_t1 = -1;
+        Picker pk;
+        std::vector<int> rest;
+        for (int idx : chosen) {
+            LoweredOp const& op = plan.ops[idx];
+            bool ok = pk.passes(op) && popc(rm | op.tmask()) <= R;
+            if (ok && op.kind == OP_U2 && u2_t0 >= 0 && (u2_t0 != op.t0 || u2_t1 != op.t1)) ok = false;
+            if (ok) {
+                if (op.kind == OP_U2) u2_t0 = op.t0, u2_t1 = op.t1;
+                rm |= op.tmask();
+                st.ops.push_back(idx);
+            } else {
+                pk.block(op);
+                rest.push_back(idx);
+            }
+        }
+        // register-bit assignment: a U2 pair must sit on register bits (1,0)
+        std::vector<int> rb;
+        if (u2_t0 >= 0) {
+            rb.push_back(u2_t1);
+            rb.push_back(u2_t0);
+        }
+        for (int b = 0; b < kMaxRowBits; ++b)
+            if ((rm >> b) & 1u)
+                if (std::find(rb.begin(), rb.end(), b) == rb.end()) rb.push_back(b);
+        for (int b : sw.tile_bits) {
+            if ((int)rb.size() >= R) break;
+            if (std::find(rb.begin(), rb.end(), b) == rb.end()) rb.push_back(b);
+        }
+        st.reg_bits = rb;
+        sw.stages.push_back(std::move(st));
+        chosen.swap(rest);
+    }
+}
+
+void finish_sweep(Plan& plan, std::vector<int> const& chosen, uint32_t S) {
+    PlanConfig const& cfg = plan.cfg;
+    PlannedSweep sw;
+    // pad the tile: at least R bits; one-stage sweeps get enough rows for a full CTA
+    int const m_target = std::min(cfg.n, std::min(cfg.m_cap, cfg.R + 8 - cfg.log2w));
+    int m              = std::max(popc(S), m_target);
+    m                  = std::max(m, std::min(cfg.n, cfg.R));
+    for (int b = 0; b < cfg.n && popc(S) < m; ++b) S |= 1u << b;
+    for (int b = 0; b < cfg.n; ++b)
+        if ((S >> b) & 1u) sw.tile_bits.push_back(b);
+    // tiles whose outer bits fail a control shared by every op are never touched
+    uint32_t common = ~0u;
+    for (int idx : chosen) common &= plan.ops[idx].req;
+    sw.fixed_one = chosen.empty() ? 0u : (common & ~S);
+    build_stages(plan, chosen, sw);
+    sw.alg_bytes = 32.0 * std::ldexp(1.0, cfg.n - popc(sw.fixed_one)) * (double)cfg.ncols;
+    plan.stats.n_stages += sw.stages.size();
+    plan.stats.alg_bytes_per_run += sw.alg_bytes;
+    plan.sweeps.push_back(std::move(sw));
+}
+
+void schedule(Plan& plan) {
+    PlanConfig const& cfg = plan.cfg;
+    size_t const N        = plan.ops.size();
+    if (!cfg.fuse) {
+        for (size_t i = 0; i < N; ++i) finish_sweep(plan, {(int)i}, plan.ops[i].tmask());
+        return;
+    }
+    std::vector<char> done(N, 0);
+    size_t first = 0;
+    while (true) {
+        while (first < N && done[first]) ++first;
+        if (first >= N) break;
+        uint32_t S = 0;
+        std::vector<int> chosen;
+        Picker pk;
+        int scanned = 0;
+        for (size_t i = first; i < N && scanned < cfg.lookahead; ++i) {
+            if (done[i]) continue;
+            ++scanned;
+            LoweredOp const& op = plan.ops[i];
+            if (pk.passes(op) && popc(S | op.tmask()) <= cfg.m_cap) {
+                S |= op.tmask();
+                chosen.push_back((int)i);
+                done[i] = 1;
+                if ((int)chosen.size() >= cfg.max_ops) break;
+            } else {
+                pk.block(op);
+                if (popc(pk.blockedT) >= cfg.n) break;
+            }
+        }
+        finish_sweep(plan, chosen, S);
+    }
+}
+
+// ---- serialization ----------------------------------------------------------------------
+
+void serialize(Plan& plan) {
+    PlanConfig const& cfg = plan.cfg;
+    for (PlannedSweep const& sw : plan.sweeps) {
+        DevSweep hs;
+        std::memset(&hs, 0, sizeof(hs));
+        int const m   = (int)sw.tile_bits.size();
+        hs.n_stages   = (int)sw.stages.size();
+        hs.m          = m;
+        hs.log2w      = cfg.log2w;
+        hs.fixed_one  = sw.fixed_one;
+        uint32_t S    = 0;
+        int local_of[kMaxRowBits];
+        for (int b = 0; b < kMaxRowBits; ++b) local_of[b] = -1;
+        for (int l = 0; l < m; ++l) {
+            hs.sp[l]                   = sw.tile_bits[l];
+            local_of[sw.tile_bits[l]] = l;
+            S |= 1u << sw.tile_bits[l];
+        }
+        int no = 0;
+        for (int b = 0; b < cfg.n; ++b)
+            if (!((S >> b) & 1u) && !((sw.fixed_one >> b) & 1u)) hs.outer[no++] = b;
+        hs.n_outer = no;
+        std::vector<DevStage> stages;
+        std::vector<DevOp> ops;
+        std::vector<double> pool;
+        for (PlannedStage const& st : sw.stages) {
+            DevStage ds;
+            std::memset(&ds, 0, sizeof(ds));
+            ds.op_begin = (int)ops.size();
+            ds.r        = (int)st.reg_bits.size();
+            uint32_t regmask_local = 0, regmask_global = 0;
+            int regidx_of[kMaxRowBits];
+            for (int b = 0; b < kMaxRowBits; ++b) regidx_of[b] = -1;
+            for (int j = 0; j < ds.r; ++j) {
+                ds.rl[j]                    = local_of[st.reg_bits[j]];
+                regidx_of[st.reg_bits[j]] = j;
+                regmask_local |= 1u << ds.rl[j];
+                regmask_global |= 1u << st.reg_bits[j];
+            }
+            int nt = 0;
+            for (int l = 0; l < m; ++l)
+                if (!((regmask_local >> l) & 1u)) ds.tl[nt++] = l;
+            ds.n_t = nt;
+            for (int idx : st.ops) {
+                LoweredOp const& lo = plan.ops[idx];
+                DevOp d;
+                std::memset(&d, 0, sizeof(d));
+                d.kind = lo.kind;
+                d.j0   = lo.t0 >= 0 ? regidx_of[lo.t0] : -1;
+                d.j1   = lo.t1 >= 0 ? regidx_of[lo.t1] : -1;
+                d.pool = -1;
+                d.pad0 = -1;
+                for (int b = 0; b < cfg.n; ++b)
+                    if ((lo.req >> b) & 1u) {
+                        if (regidx_of[b] >= 0)
+                            d.creg |= 1u << regidx_of[b];
+                        else
+                            d.cother |= 1u << b;
+                    }
+                if (lo.kind == OP_DIAG) {
+                    // the selecting bit is either a register bit (j0) or any other row bit (pad0)
+                    if (regidx_of[lo.dbit] >= 0)
+                        d.j0 = regidx_of[lo.dbit];
+                    else
+                        d.pad0 = lo.dbit;
+                }
+                std::memcpy(d.c, lo.c, sizeof(d.c));
+                if (lo.kind == OP_U2) {
+                    d.pool = (int)pool.size();
+                    pool.insert(pool.end(), lo.mat.begin(), lo.mat.end());
+                }
+                ops.push_back(d);
+            }
+            ds.op_end = (int)ops.size();
+            stages.push_back(ds);
+        }
+        hs.n_ops        = (int)ops.size();
+        hs.pool_doubles = (int)pool.size();
+        size_t const off = (plan.blob.size() + 255) / 256 * 256;
+        size_t const sz  = sizeof(DevSweep) + stages.size() * sizeof(DevStage) + ops.size() * sizeof(DevOp) +
+                          pool.size() * sizeof(double);
+        plan.blob.resize(off + sz, 0);
+        unsigned char* p = plan.blob.data() + off;
+        std::memcpy(p, &hs, sizeof(hs));
+        p += sizeof(hs);
+        if (!stages.empty()) std::memcpy(p, stages.data(), stages.size() * sizeof(DevStage));
+        p += stages.size() * sizeof(DevStage);
+        if (!ops.empty()) std::memcpy(p, ops.data(), ops.size() * sizeof(DevOp));
+        p += ops.size() * sizeof(DevOp);
+        if (!pool.empty()) std::memcpy(p, pool.data(), pool.size() * sizeof(double));
+        plan.sweep_offset.push_back(off);
+        plan.sweep_size.push_back(sz);
+    }
+}
+
+}  // namespace
+
+int build_plan(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gates, const qsx_plan_options* opt,
+               Plan& plan, std::string& msg) {
+    auto const t_begin = std::chrono::steady_clock::now();
+    if (n_qubits < 1 || n_qubits > kMaxRowBits) {
+        msg = "n_qubits must be in [1, " + std::to_string(kMaxRowBits) + "]";
+        return QSX_ERR_BAD_ARG;
+    }
+    int const lc = ilog2_exact(ncols);
+    if (lc < 0 || lc > n_qubits) {
+        msg = "ncols must be a power of two <= 2^n_qubits";
+        return QSX_ERR_BAD_ARG;
+    }
+    if (n_gates > 0 && gates == nullptr) {
+        msg = "null gate array";
+        return QSX_ERR_BAD_ARG;
+    }
+    qsx_plan_options o;
+    std::memset(&o, 0, sizeof(o));
+    o.fuse = 1;
+    if (opt != nullptr) {
+        if (opt->struct_size != (int32_t)sizeof(qsx_plan_options)) {
+            msg = "qsx_plan_options.struct_size mismatch";
+            return QSX_ERR_BAD_ARG;
+        }
+        o = *opt;
+    } else {
+        o.snap_tol = 1e-15;
+    }
+    PlanConfig& cfg = plan.cfg;
+    cfg.n           = n_qubits;
+    cfg.ncols       = ncols;
+    cfg.fuse        = o.fuse != 0;
+    cfg.snap_tol    = (opt != nullptr && o.snap_tol == 0.0) ? 1e-15 : o.snap_tol;
+    cfg.R           = std::min(n_qubits, o.reg_qubits > 0 ? std::min((int)o.reg_qubits, kMaxRegBits) : 4);
+    cfg.log2w       = std::min(lc, o.log2_tile_cols > 0 ? std::min((int)o.log2_tile_cols, 5) : 3);
+    if (o.log2_tile_cols < 0) cfg.log2w = 0;
+    cfg.m_cap       = o.tile_qubits > 0 ? (int)o.tile_qubits : 10;
+    cfg.m_cap       = std::min(cfg.m_cap, kMaxTileBits);
+    cfg.m_cap       = std::min(cfg.m_cap, 13 - cfg.log2w);            // 2^m * W * 16 B <= 128 KiB
+    cfg.m_cap       = std::min(cfg.m_cap, max_threads_log2(cfg.R) - cfg.log2w + cfg.R);  // CTA size limit
+    cfg.m_cap       = std::max(std::min(cfg.m_cap, n_qubits), cfg.R);
+    cfg.max_ops     = o.max_ops_per_sweep > 0 ? (int)o.max_ops_per_sweep : 48;
+    cfg.lookahead   = o.lookahead > 0 ? (int)o.lookahead : 4096;
+
+    plan.stats          = qsx_plan_stats{};
+    plan.stats.n_gates  = n_gates;
+    double const shard_elems = std::ldexp(1.0, n_qubits) * (double)ncols;
+    for (size_t i = 0; i < n_gates; ++i) {
+        size_t const before = plan.ops.size();
+        int const rc        = lower_gate(n_qubits, gates[i], (int)i, cfg.snap_tol, plan.ops, msg);
+        if (rc != QSX_OK) return rc;
+        for (size_t k = before; k < plan.ops.size(); ++k) plan.stats.gate_bytes_per_run += 32.0 * shard_elems * plan.ops[k].frac;
+    }
+    plan.stats.n_ops = plan.ops.size();
+    schedule(plan);
+    plan.stats.n_sweeps = plan.sweeps.size();
+    serialize(plan);
+    plan.stats.plan_host_ms =
+        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    return QSX_OK;
+}
+
+std::string dump_plan_json(const Plan& plan) {
+    static char const* const kNames[] = {"U1", "H", "X", "AD", "PHASE", "DIAG", "SWAP", "U2", "NEG", "MULI"};
+    std::ostringstream os;
+    os.precision(17);
+    os << "{\"n\":" << plan.cfg.n << ",\"ncols\":" << plan.cfg.ncols << ",\"R\":" << plan.cfg.R
+       << ",\"log2w\":" << plan.cfg.log2w << ",\"m_cap\":" << plan.cfg.m_cap << ",\"sweeps\":[";
+    for (size_t s = 0; s < plan.sweeps.size(); ++s) {
+        PlannedSweep const& sw = plan.sweeps[s];
+        os << (s ? "," : "") << "{\"tile_bits\":[";
+        for (size_t i = 0; i < sw.tile_bits.size(); ++i) os << (i ? "," : "") << sw.tile_bits[i];
+        os << "],\"fixed_one\":" << sw.fixed_one << ",\"stages\":[";
+        for (size_t t = 0; t < sw.stages.size(); ++t) {
+            PlannedStage const& st = sw.stages[t];
+            os << (t ? "," : "") << "{\"reg_bits\":[";
+            for (size_t i = 0; i < st.reg_bits.size(); ++i) os << (i ? "," : "") << st.reg_bits[i];
+            os << "],\"ops\":[";
+            for (size_t i = 0; i < st.ops.size(); ++i) {
+                LoweredOp const& op = plan.ops[st.ops[i]];
+                os << (i ? "," : "") << "{\"kind\":\"" << kNames[op.kind] << "\",\"t0\":" << op.t0 << ",\"t1\":" << op.t1
+                   << ",\"dbit\":" << op.dbit << ",\"req\":" << op.req << ",\"gate\":" << op.src_gate << ",\"c\":[";
+                for (int k = 0; k < 8; ++k) os << (k ? "," : "") << op.c[k];
+                os << "],\"mat\":[";
+                for (size_t k = 0; k < op.mat.size(); ++k) os << (k ? "," : "") << op.mat[k];
+                os << "]}";
+            }
+            os << "]}";
+        }
+        os << "]}";
+    }
+    os << "]}";
+    return os.str();
+}
+
+}  // namespace qsx

@@ -1,0 +1,68 @@
+// planner.hpp -- host-side lowering + scheduling of a gate stream into sweeps.
+// Pure C++ (no CUDA); see planner.cpp.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/qsx.h"
+#include "program.hpp"
+
+namespace qsx {
+
+struct LoweredOp {
+    int32_t  kind  = OP_U1;
+    int      t0    = -1;  // non-diagonal target row bits (global positions)
+    int      t1    = -1;
+    int      dbit  = -1;  // OP_DIAG: row bit selecting d0/d1 (needs no locality)
+    uint32_t req   = 0;   // required-one mask over global row bits (controls; phase-type: incl. the phase bit)
+    double   c[8]  = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<double> mat;  // OP_U2: 4x4 complex, row-major
+    int      src_gate = -1;
+    double   frac     = 1.0;  // touched fraction f of SURVEY 8(d)
+
+    uint32_t tmask() const { return (t0 >= 0 ? 1u << t0 : 0u) | (t1 >= 0 ? 1u << t1 : 0u); }
+    uint32_t dmask() const { return req | (dbit >= 0 ? 1u << dbit : 0u); }
+};
+
+struct PlannedStage {
+    std::vector<int> reg_bits;  // global row bit of register bit j (size R)
+    std::vector<int> ops;       // indices into Plan::ops
+};
+
+struct PlannedSweep {
+    std::vector<int> tile_bits;  // global row bits in the tile, ascending (size m)
+    uint32_t fixed_one = 0;
+    std::vector<PlannedStage> stages;
+    double alg_bytes = 0;
+};
+
+struct PlanConfig {
+    int  n = 0;
+    uint64_t ncols = 0;
+    int  R = 4;          // register bits (kernel template parameter)
+    int  log2w = 3;
+    int  m_cap = 10;
+    int  max_ops = 48;
+    int  lookahead = 4096;
+    bool fuse = true;
+    double snap_tol = 1e-15;
+};
+
+struct Plan {
+    PlanConfig cfg;
+    std::vector<LoweredOp> ops;
+    std::vector<PlannedSweep> sweeps;
+    qsx_plan_stats stats{};
+    // serialized device programs: one blob per sweep, concatenated; offsets are 256-B aligned
+    std::vector<unsigned char> blob;
+    std::vector<size_t> sweep_offset;
+    std::vector<size_t> sweep_size;
+};
+
+// returns QSX_OK or an error code; msg receives the reason
+int build_plan(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gates,
+               const qsx_plan_options* opt, Plan& plan, std::string& msg);
+std::string dump_plan_json(const Plan& plan);
+
+}  // namespace qsx

@@ -1,0 +1,399 @@
+// runtime.cu -- the C ABI of include/qsx.h: device contexts, shard storage, plan execution,
+// equivalence reduction.  CUDA lives only behind this file and kernels.cu.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/qsx.h"
+#include "../host/util/phase.hpp"
+#include "kernels.hpp"
+#include "planner.hpp"
+
+struct qsx_unitary {
+    int      device   = 0;
+    int      n        = 0;
+    uint64_t col0     = 0;
+    uint64_t ncols    = 0;
+    double2* data     = nullptr;
+    uint64_t elems() const { return (1ull << n) * ncols; }
+    uint64_t bytes() const { return elems() * 16ull; }
+};
+
+struct qsx_plan {
+    qsx::Plan plan;
+    std::mutex mu;
+    std::map<int, unsigned char*> device_blob;  // device id -> uploaded program
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, std::string msg) {
+    g_err = std::move(msg);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, char const* what) {
+    cudaGetLastError();  // clear sticky-less error state
+    std::string msg = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    if (e == cudaErrorMemoryAllocation) return fail(QSX_ERR_OOM, msg);
+    return fail(QSX_ERR_CUDA, msg);
+}
+
+#define QSX_CUDA(call)                                          \
+    do {                                                        \
+        cudaError_t const e__ = (call);                         \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);   \
+    } while (0)
+
+struct DeviceCtx {
+    cudaStream_t stream   = nullptr;
+    double*      scratch  = nullptr;  // equiv partials + 8 outputs
+    double*      host8    = nullptr;  // pinned
+    cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+};
+
+std::mutex g_mu;
+std::map<int, DeviceCtx> g_ctx;
+
+int device_count_nothrow() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int get_ctx(int device, DeviceCtx** out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_ctx.find(device);
+    if (it != g_ctx.end()) {
+        *out = &it->second;
+        QSX_CUDA(cudaSetDevice(device));
+        return QSX_OK;
+    }
+    int const n = device_count_nothrow();
+    if (n == 0) return fail(QSX_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(QSX_ERR_BAD_ARG, "device index out of range");
+    QSX_CUDA(cudaSetDevice(device));
+    DeviceCtx c;
+    QSX_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    QSX_CUDA(cudaMalloc(&c.scratch, (qsx::equiv_partials_doubles() + 8) * sizeof(double)));
+    QSX_CUDA(cudaMallocHost(&c.host8, 8 * sizeof(double)));
+    QSX_CUDA(cudaEventCreate(&c.ev0));
+    QSX_CUDA(cudaEventCreate(&c.ev1));
+    auto ins = g_ctx.emplace(device, c);
+    *out     = &ins.first->second;
+    return QSX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qsx_abi_version(void) { return QSX_ABI_VERSION; }
+
+const char* qsx_last_error(void) { return g_err.c_str(); }
+
+int qsx_device_count(int* count) {
+    if (count == nullptr) return fail(QSX_ERR_BAD_ARG, "null count");
+    *count = device_count_nothrow();
+    return QSX_OK;
+}
+
+int qsx_device_stream(int device, void** stream) {
+    if (stream == nullptr) return fail(QSX_ERR_BAD_ARG, "null stream out-pointer");
+    DeviceCtx* c = nullptr;
+    if (int rc = get_ctx(device, &c)) return rc;
+    *stream = (void*)c->stream;
+    return QSX_OK;
+}
+
+int qsx_device_synchronize(int device) {
+    DeviceCtx* c = nullptr;
+    if (int rc = get_ctx(device, &c)) return rc;
+    QSX_CUDA(cudaStreamSynchronize(c->stream));
+    return QSX_OK;
+}
+
+// ---- storage ----------------------------------------------------------------------------
+
+int qsx_unitary_create(int device, int n_qubits, uint64_t col0, uint64_t ncols, qsx_unitary** out) {
+    if (out == nullptr) return fail(QSX_ERR_BAD_ARG, "null out-pointer");
+    *out = nullptr;
+    if (n_qubits < 1 || n_qubits > qsx::kMaxRowBits) return fail(QSX_ERR_BAD_ARG, "n_qubits out of range");
+    uint64_t const dim = 1ull << n_qubits;
+    if (ncols == 0 || (ncols & (ncols - 1)) != 0 || ncols > dim || col0 % ncols != 0 || col0 + ncols > dim)
+        return fail(QSX_ERR_BAD_ARG, "column shard must be a power-of-two block aligned to its size");
+    DeviceCtx* c = nullptr;
+    if (int rc = get_ctx(device, &c)) return rc;
+    auto* u = new (std::nothrow) qsx_unitary;
+    if (u == nullptr) return fail(QSX_ERR_OOM, "host allocation failed");
+    u->device = device, u->n = n_qubits, u->col0 = col0, u->ncols = ncols;
+    cudaError_t const e = cudaMalloc(&u->data, u->bytes());
+    if (e != cudaSuccess) {
+        delete u;
+        return cuda_fail(e, "cudaMalloc(unitary shard)");
+    }
+    *out = u;
+    return QSX_OK;
+}
+
+int qsx_unitary_set_identity(qsx_unitary* u) {
+    if (u == nullptr) return fail(QSX_ERR_BAD_ARG, "null unitary");
+    DeviceCtx* c = nullptr;
+    if (int rc = get_ctx(u->device, &c)) return rc;
+    QSX_CUDA(qsx::launch_set_identity(u->data, u->n, u->col0, u->ncols, c->stream));
+    QSX_CUDA(cudaStreamSynchronize(c->stream));
+    return QSX_OK;
+}
+
+int qsx_unitary_clone(const qsx_unitary* u, qsx_unitary** out) {
+    if (u == nullptr || out == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    if (int rc = qsx_unitary_create(u->device, u->n, u->col0, u->ncols, out)) return rc;
+    DeviceCtx* c = nullptr;
+    if (int rc = get_ctx(u->device, &c)) return rc;
+    QSX_CUDA(cudaMemcpyAsync((*out)->data, u->data, u->bytes(), cudaMemcpyDeviceToDevice, c->stream));
+    QSX_CUDA(cudaStreamSynchronize(c->stream));
+    return QSX_OK;
+}
+
+int qsx_unitary_destroy(qsx_unitary* u) {
+    if (u == nullptr) return QSX_OK;
+    if (u->data != nullptr) {
+        DeviceCtx* c = nullptr;
+        if (get_ctx(u->device, &c) == QSX_OK) {
+            cudaStreamSynchronize(c->stream);
+            cudaFree(u->data);
+        }
+    }
+    delete u;
+    return QSX_OK;
+}
+
+int qsx_unitary_get_info(const qsx_unitary* u, qsx_unitary_info* info) {
+    if (u == nullptr || info == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    info->n_qubits = u->n;
+    info->device   = u->device;
+    info->col0     = u->col0;
+    info->ncols    = u->ncols;
+    info->nrows    = 1ull << u->n;
+    info->bytes    = u->bytes();
+    info->data     = u->data;
+    return QSX_OK;
+}
+
+int qsx_unitary_upload(qsx_unitary* u, uint64_t row0, uint64_t nrows, const double* host) {
+    if (u == nullptr || host == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    if (row0 + nrows > (1ull << u->n)) return fail(QSX_ERR_BAD_ARG, "row range out of bounds");
+    DeviceCtx* c = nullptr;
+    if (int rc = get_ctx(u->device, &c)) return rc;
+    QSX_CUDA(cudaMemcpyAsync(u->data + row0 * u->ncols, host, nrows * u->ncols * 16ull, cudaMemcpyHostToDevice, c->stream));
+    QSX_CUDA(cudaStreamSynchronize(c->stream));
+    return QSX_OK;
+}
+
+int qsx_unitary_download(const qsx_unitary* u, uint64_t row0, uint64_t nrows, double* host) {
+    if (u == nullptr || host == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    if (row0 + nrows > (1ull << u->n)) return fail(QSX_ERR_BAD_ARG, "row range out of bounds");
+    DeviceCtx* c = nullptr;
+    if (int rc = get_ctx(u->device, &c)) return rc;
+    QSX_CUDA(cudaMemcpyAsync(host, u->data + row0 * u->ncols, nrows * u->ncols * 16ull, cudaMemcpyDeviceToHost, c->stream));
+    QSX_CUDA(cudaStreamSynchronize(c->stream));
+    return QSX_OK;
+}
+
+// ---- construction -----------------------------------------------------------------------
+
+int qsx_plan_create(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gates, const qsx_plan_options* opt,
+                    qsx_plan** out) {
+    if (out == nullptr) return fail(QSX_ERR_BAD_ARG, "null out-pointer");
+    *out    = nullptr;
+    auto* p = new (std::nothrow) qsx_plan;
+    if (p == nullptr) return fail(QSX_ERR_OOM, "host allocation failed");
+    std::string msg;
+    int rc;
+    try {
+        rc = qsx::build_plan(n_qubits, ncols, gates, n_gates, opt, p->plan, msg);
+    } catch (std::bad_alloc const&) {
+        rc  = QSX_ERR_OOM;
+        msg = "host allocation failed while planning";
+    }
+    if (rc != QSX_OK) {
+        delete p;
+        return fail(rc, msg);
+    }
+    *out = p;
+    return QSX_OK;
+}
+
+int qsx_plan_destroy(qsx_plan* plan) {
+    if (plan == nullptr) return QSX_OK;
+    for (auto& kv : plan->device_blob) {
+        if (cudaSetDevice(kv.first) == cudaSuccess) cudaFree(kv.second);
+    }
+    delete plan;
+    return QSX_OK;
+}
+
+int qsx_plan_get_stats(const qsx_plan* plan, qsx_plan_stats* stats) {
+    if (plan == nullptr || stats == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    *stats = plan->plan.stats;
+    return QSX_OK;
+}
+
+int qsx_plan_dump(const qsx_plan* plan, char* buf, size_t buf_size, size_t* needed) {
+    if (plan == nullptr) return fail(QSX_ERR_BAD_ARG, "null plan");
+    std::string const s = qsx::dump_plan_json(plan->plan);
+    if (needed != nullptr) *needed = s.size() + 1;
+    if (buf != nullptr && buf_size > 0) {
+        size_t const k = std::min(buf_size - 1, s.size());
+        std::memcpy(buf, s.data(), k);
+        buf[k] = '\0';
+    }
+    return QSX_OK;
+}
+
+int qsx_plan_run(const qsx_plan* cplan, qsx_unitary* u, qsx_stop_fn should_stop, void* stop_arg, uint32_t flags,
+                 qsx_run_stats* stats) {
+    if (cplan == nullptr || u == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    auto* plan           = const_cast<qsx_plan*>(cplan);
+    qsx::Plan const& pl  = plan->plan;
+    if (pl.cfg.n != u->n || pl.cfg.ncols != u->ncols)
+        return fail(QSX_ERR_SHAPE, "plan was built for a different shard geometry");
+    if (stats != nullptr) *stats = qsx_run_stats{};
+    DeviceCtx* c = nullptr;
+    if (int rc = get_ctx(u->device, &c)) return rc;
+    if (pl.sweeps.empty()) return QSX_OK;
+    unsigned char* dblob = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(plan->mu);
+        auto it = plan->device_blob.find(u->device);
+        if (it == plan->device_blob.end()) {
+            QSX_CUDA(cudaMalloc(&dblob, pl.blob.size()));
+            QSX_CUDA(cudaMemcpyAsync(dblob, pl.blob.data(), pl.blob.size(), cudaMemcpyHostToDevice, c->stream));
+            QSX_CUDA(cudaStreamSynchronize(c->stream));  // pl.blob is pageable
+            plan->device_blob.emplace(u->device, dblob);
+        } else {
+            dblob = it->second;
+        }
+    }
+    bool const async = (flags & QSX_RUN_ASYNC) != 0;
+    if (!async) QSX_CUDA(cudaEventRecord(c->ev0, c->stream));
+    uint64_t launches = 0;
+    // with a stop callback, drain the stream every few sweeps so SIGINT is honoured promptly
+    // (the reference polls stop_requested() once per gate, qcir_to_tensor.cpp:174-177)
+    double pending_bytes = 0.0;
+    for (size_t s = 0; s < pl.sweeps.size(); ++s) {
+        if (should_stop != nullptr) {
+            if (pending_bytes > 64e9) {  // ~10 ms of HBM traffic
+                QSX_CUDA(cudaStreamSynchronize(c->stream));
+                pending_bytes = 0.0;
+            }
+            if (should_stop(stop_arg)) {
+                cudaStreamSynchronize(c->stream);
+                if (stats != nullptr) stats->launches = launches;
+                return fail(QSX_ERR_INTERRUPTED, "interrupted by the stop callback");
+            }
+        }
+        qsx::DevSweep const& hs = *reinterpret_cast<qsx::DevSweep const*>(pl.blob.data() + pl.sweep_offset[s]);
+        QSX_CUDA(qsx::launch_sweep(u->data, u->n, u->ncols, pl.cfg.R, hs, dblob + pl.sweep_offset[s], c->stream));
+        pending_bytes += pl.sweeps[s].alg_bytes;
+        ++launches;
+    }
+    if (stats != nullptr) stats->launches = launches;
+    if (!async) {
+        QSX_CUDA(cudaEventRecord(c->ev1, c->stream));
+        QSX_CUDA(cudaStreamSynchronize(c->stream));
+        float ms = 0.f;
+        QSX_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        if (stats != nullptr) stats->device_ms = ms;
+    }
+    return QSX_OK;
+}
+
+int qsx_apply_gates(qsx_unitary* u, const qsx_gate* gates, size_t n_gates, const qsx_plan_options* opt,
+                    qsx_stop_fn should_stop, void* stop_arg, qsx_run_stats* stats) {
+    if (u == nullptr) return fail(QSX_ERR_BAD_ARG, "null unitary");
+    qsx_plan* plan = nullptr;
+    if (int rc = qsx_plan_create(u->n, u->ncols, gates, n_gates, opt, &plan)) return rc;
+    int const rc = qsx_plan_run(plan, u, should_stop, stop_arg, 0, stats);
+    std::string const keep = g_err;
+    qsx_plan_destroy(plan);
+    g_err = keep;
+    return rc;
+}
+
+// ---- verification -----------------------------------------------------------------------
+
+int qsx_equiv_partial(const qsx_unitary* a, const qsx_unitary* b, double sums[8]) {
+    if (a == nullptr || b == nullptr || sums == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    if (a->n != b->n || a->ncols != b->ncols || a->col0 != b->col0)
+        return fail(QSX_ERR_SHAPE, "the two tensors should have the same shape");
+    if (a->device != b->device) return fail(QSX_ERR_SHAPE, "both shards must live on the same device");
+    DeviceCtx* c = nullptr;
+    if (int rc = get_ctx(a->device, &c)) return rc;
+    double* const out8 = c->scratch + qsx::equiv_partials_doubles();
+    QSX_CUDA(qsx::launch_equiv(a->data, b->data, a->elems(), c->scratch, out8, c->stream));
+    QSX_CUDA(cudaMemcpyAsync(c->host8, out8, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    QSX_CUDA(cudaStreamSynchronize(c->stream));
+    std::memcpy(sums, c->host8, 8 * sizeof(double));
+    return QSX_OK;
+}
+
+int qsx_equiv_finish(const double sums[8], double eps, int strict, qsx_equiv_result* out) {
+    if (sums == nullptr || out == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    std::memset(out, 0, sizeof(*out));
+    // inner_product = |sum conj(a) b| ; cosine = ip(a,b) / sqrt(ip(a,a) ip(b,b))   (tensor.hpp:393-403)
+    double const ip_ab = std::abs(std::complex<double>(sums[0], sums[1]));
+    out->cosine        = ip_ab / std::sqrt(std::abs(sums[2]) * std::abs(sums[3]));
+    bool equiv         = out->cosine >= (1 - eps);  // qtensor.hpp:414-417
+    std::complex<double> const sa(sums[4], sums[5]), sb(sums[6], sums[7]);
+    dvlab::Phase phase;
+    if (sa == std::complex<double>(0.0, 0.0)) {
+        // sum(t1) == 0: the reference divides by zero and feeds NaN to Phase (UB / endless loop,
+        // SURVEY Appendix C trap 2).  Defined behaviour here: norm = inf/nan, phase undefined.
+        out->norm          = (sb == std::complex<double>(0.0, 0.0)) ? std::nan("") : INFINITY;
+        out->phase_rad     = std::nan("");
+        out->phase_defined = 0;
+    } else {
+        std::complex<double> const s = sb / sa;  // global_scalar_factor, qtensor.hpp:383-385
+        out->norm                    = std::abs(s);
+        out->phase_rad               = std::arg(s);
+        if (std::isfinite(out->phase_rad)) {
+            phase              = dvlab::Phase(out->phase_rad);  // eps 1e-4 rad, phase.hpp:38-40
+            out->phase_defined = 1;
+        }
+    }
+    out->phase_num = phase.numerator();
+    out->phase_den = phase.denominator();
+    if (strict) {  // tensor_cmd.cpp:156-160
+        if (out->norm > 1 + eps || out->norm < 1 - eps || !out->phase_defined || phase != dvlab::Phase(0)) equiv = false;
+    }
+    out->equivalent = equiv ? 1 : 0;
+    return QSX_OK;
+}
+
+int qsx_unitary_adjoint_inplace(qsx_unitary* u) {
+    if (u == nullptr) return fail(QSX_ERR_BAD_ARG, "null unitary");
+    if (u->col0 != 0 || u->ncols != (1ull << u->n))
+        return fail(QSX_ERR_UNSUPPORTED, "adjoint of a column-sharded unitary needs an all-to-all (not built yet)");
+    DeviceCtx* c = nullptr;
+    if (int rc = get_ctx(u->device, &c)) return rc;
+    QSX_CUDA(qsx::launch_adjoint_inplace(u->data, u->n, c->stream));
+    QSX_CUDA(cudaStreamSynchronize(c->stream));
+    return QSX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+"""Test helper: executes a dumped qsx plan (qsx_plan_dump JSON) in numpy, op by op, in the
+scheduled order.  Used on CPU to prove that lowering + scheduling preserve the circuit's
+unitary, and to check the structural invariants the kernel relies on."""
+import numpy as np
+
+
+def _rows_with(n, mask):
+    r = np.arange(2**n)
+    return (r & mask) == mask
+
+
+def apply_op(u, n, op):
+    """u: (2^n, C) complex128, modified in place. Bit p = bit p of the row index."""
+    kind, req = op["kind"], op["req"]
+    rows = np.arange(2**n)
+    sel = (rows & req) == req
+    c = op["c"]
+    if kind in ("PHASE", "NEG", "MULI"):
+        w = {"PHASE": complex(c[0], c[1]), "NEG": -1.0, "MULI": 1j * c[0]}[kind]
+        u[sel] *= w
+        return
+    if kind == "DIAG":
+        d0, d1 = complex(c[0], c[1]), complex(c[2], c[3])
+        b = (rows >> op["dbit"]) & 1
+        u[sel & (b == 0)] *= d0
+        u[sel & (b == 1)] *= d1
+        return
+    t0 = op["t0"]
+    if kind in ("U1", "H", "X", "AD"):
+        if kind == "U1":
+            m = np.array([[complex(c[0], c[1]), complex(c[2], c[3])], [complex(c[4], c[5]), complex(c[6], c[7])]])
+        elif kind == "H":
+            m = np.array([[c[0], c[0]], [c[0], -c[0]]], dtype=complex)
+        elif kind == "X":
+            m = np.array([[0, 1], [1, 0]], dtype=complex)
+        else:
+            m = np.array([[0, complex(c[0], c[1])], [complex(c[2], c[3]), 0]])
+        lo = rows[sel & (((rows >> t0) & 1) == 0)]
+        hi = lo | (1 << t0)
+        a, b = u[lo].copy(), u[hi].copy()
+        u[lo] = m[0, 0] * a + m[0, 1] * b
+        u[hi] = m[1, 0] * a + m[1, 1] * b
+        return
+    t1 = op["t1"]
+    if kind == "SWAP":
+        x = rows[sel & (((rows >> t0) & 1) == 1) & (((rows >> t1) & 1) == 0)]
+        y = x ^ (1 << t0) ^ (1 << t1)
+        tmp = u[x].copy()
+        u[x] = u[y]
+        u[y] = tmp
+        return
+    if kind == "U2":
+        m = np.array(op["mat"]).reshape(4, 4, 2)
+        m = m[..., 0] + 1j * m[..., 1]
+        base = rows[sel & (((rows >> t0) & 1) == 0) & (((rows >> t1) & 1) == 0)]
+        idx = [base | (b1 << t0) | (b0 << t1) for b1 in (0, 1) for b0 in (0, 1)]
+        v = [u[i].copy() for i in idx]
+        for r in range(4):
+            u[idx[r]] = sum(m[r, k] * v[k] for k in range(4))
+        return
+    raise ValueError(kind)
+
+
+def run_plan(dump, u):
+    n = dump["n"]
+    for sw in dump["sweeps"]:
+        for st in sw["stages"]:
+            for op in st["ops"]:
+                apply_op(u, n, op)
+    return u
+
+
+def check_invariants(dump, n_ops_expected=None):
+    n, R = dump["n"], dump["R"]
+    seen = []
+    for sw in dump["sweeps"]:
+        tb = sw["tile_bits"]
+        assert tb == sorted(set(tb)) and all(0 <= b < n for b in tb)
+        assert len(tb) >= min(R, n)
+        assert len(sw["stages"]) >= 1
+        common = ~0
+        for st in sw["stages"]:
+            rb = st["reg_bits"]
+            assert len(rb) == R and len(set(rb)) == R and set(rb) <= set(tb), (rb, tb)
+            for op in st["ops"]:
+                seen.append(op["gate"])
+                common &= op["req"]
+                for t in (op["t0"], op["t1"]):
+                    assert t == -1 or t in rb, (op, rb)
+                if op["kind"] == "U2":
+                    assert rb[1] == op["t0"] and rb[0] == op["t1"]
+        # tiles skipped by fixed_one are untouched by every op of the sweep
+        assert sw["fixed_one"] & ~common == 0
+        assert all(not (sw["fixed_one"] >> b) & 1 for b in tb)
+    if n_ops_expected is not None:
+        assert len(seen) == n_ops_expected
+    return seen

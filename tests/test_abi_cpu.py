@@ -1,0 +1,155 @@
+"""CPU-only tests of the C-ABI library: it loads, exports every symbol include/qsx.h
+declares, and its host logic (gate lowering, scheduling, equivalence finish, phase
+conversion) matches the oracle.  No kernels are launched here."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import qsyn_b200 as Q
+from oracle import oracle as O
+from tests import plan_sim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "qsx.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(qsx_[a-z_0-9]+)\s*\(", hdr))
+    names -= {"qsx_stop_fn"}
+    assert len(names) >= 20
+    L = Q.lib()
+    for nm in sorted(names):
+        assert hasattr(L, nm), f"libqsx.so does not export {nm}"
+    assert L.qsx_abi_version() == 1
+
+
+def test_no_cpu_fallback_when_no_device():
+    if Q.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(Q.QsxError) as ei:
+        Q.Unitary(3)
+    assert ei.value.status == "QSX_ERR_CUDA" and "no CPU fallback" in str(ei.value)
+
+
+def _rand_circuit(n, g, seed, extra=True):
+    qc = O.qcir_from_qasm_text(O.random_clifford_t_qasm(n, g, seed))
+    if extra:  # sprinkle the rest of the reference gate set
+        rng = np.random.default_rng(seed + 1)
+        names1 = ["y", "sx", "sy", "sxdg", "tx", "ty", "id"]
+        namesp = ["rz", "rx", "ry", "p", "px", "py"]
+        for _ in range(g // 3):
+            k = rng.integers(0, 7)
+            if k == 0:
+                qc.append(O.str_to_operation(names1[rng.integers(len(names1))]), [int(rng.integers(n))])
+            elif k == 1:
+                ph = O.Phase(int(rng.integers(-7, 8)), int(rng.integers(1, 9)))
+                qc.append(O.str_to_operation(namesp[rng.integers(len(namesp))], [ph]), [int(rng.integers(n))])
+            elif k == 2 and n >= 2:
+                a, b = rng.choice(n, 2, replace=False)
+                qc.append(O.str_to_operation(["swap", "ecr", "cy", "ch"][rng.integers(4)]), [int(a), int(b)])
+            elif k == 3 and n >= 2:
+                a, b = rng.choice(n, 2, replace=False)
+                ph = O.Phase(int(rng.integers(-7, 8)), int(rng.integers(1, 9)))
+                qc.append(O.str_to_operation(["cp", "crz", "crx", "cry"][rng.integers(4)], [ph]), [int(a), int(b)])
+            elif k == 4 and n >= 3:
+                a, b, c = rng.choice(n, 3, replace=False)
+                qc.append(O.str_to_operation(["ccx", "ccz", "cswap", "cecr", "ccy"][rng.integers(5)]), [int(a), int(b), int(c)])
+            elif k == 5 and n >= 4:
+                q = rng.choice(n, 4, replace=False)
+                qc.append(O.str_to_operation(["cccx", "cccz", "ccswap"][rng.integers(3)]), [int(x) for x in q])
+            else:
+                qc.append(O.str_to_operation("h"), [int(rng.integers(n))])
+    return qc
+
+
+@pytest.mark.parametrize("n,g,seed", [(1, 12, 1), (2, 30, 2), (3, 40, 3), (5, 120, 4), (6, 200, 5), (7, 150, 6)])
+@pytest.mark.parametrize("fuse", [0, 1])
+def test_schedule_preserves_the_unitary(n, g, seed, fuse):
+    qc = _rand_circuit(n, g, seed)
+    want = O.to_matrix_rowform(qc)
+    for opt in (Q.PlanOptions(fuse=fuse), Q.PlanOptions(fuse=fuse, reg_qubits=3, tile_qubits=5, max_ops_per_sweep=9),
+                Q.PlanOptions(fuse=fuse, snap_tol=-1.0, reg_qubits=2)):
+        plan = Q.Plan(n, 2**n, O.gate_stream(qc), opt)
+        d = plan.dump()
+        st = plan.stats()
+        plan_sim.check_invariants(d, st.n_ops)
+        assert st.n_sweeps == len(d["sweeps"]) and st.n_gates == len(qc.gates)
+        if fuse == 0:
+            assert st.n_sweeps == st.n_ops
+        got = plan_sim.run_plan(d, np.eye(2**n, dtype=np.complex128))
+        err = np.linalg.norm(got - want) / np.linalg.norm(want)
+        assert err < 1e-13, err
+
+
+def test_snapping_is_optional_and_small():
+    qc = O.qcir_from_qasm_text(O.random_clifford_t_qasm(4, 300, 9))
+    want = O.to_matrix_rowform(qc)
+    d_exact = Q.Plan(4, 16, O.gate_stream(qc), Q.PlanOptions(snap_tol=-1.0)).dump()
+    d_snap = Q.Plan(4, 16, O.gate_stream(qc)).dump()
+    kinds = lambda d: {op["kind"] for sw in d["sweeps"] for st in sw["stages"] for op in st["ops"]}
+    assert "X" in kinds(d_snap) and "NEG" in kinds(d_snap) and "MULI" in kinds(d_snap)
+    assert "X" not in kinds(d_exact) and "NEG" not in kinds(d_exact)
+    for d in (d_exact, d_snap):
+        got = plan_sim.run_plan(d, np.eye(16, dtype=np.complex128))
+        assert np.linalg.norm(got - want) / 4.0 < 1e-13
+
+
+def test_plan_rejects_bad_input():
+    h = O.mat_h()
+    with pytest.raises(Q.QsxError) as ei:
+        Q.Plan(3, 8, [(0, [3], h)])
+    assert ei.value.status == "QSX_ERR_BAD_ARG"
+    with pytest.raises(Q.QsxError):
+        Q.Plan(3, 8, [(1, [1, 1], h)])
+    with pytest.raises(Q.QsxError):
+        Q.Plan(3, 6, [(0, [0], h)])  # ncols not a power of two
+    with pytest.raises(Q.QsxError) as ei:
+        Q.Plan(3, 8, [(0, [0, 1, 2], np.eye(8))])
+    assert ei.value.status == "QSX_ERR_UNSUPPORTED"
+    # identity gates vanish, empty stream is legal (zero gates -> identity, Appendix A.1)
+    p = Q.Plan(3, 8, [(0, [0], np.eye(2)), (1, [0, 1], np.eye(2))])
+    assert p.stats().n_ops == 0 and p.stats().n_sweeps == 0
+    assert Q.Plan(3, 8, []).stats().n_sweeps == 0
+
+
+def test_qft_needs_few_sweeps():
+    """Controlled phases need no locality: QFT-14 (105 gates) collapses to a couple of sweeps."""
+    qc = O.qcir_from_qasm_text(O.qft_qasm(14))
+    st = Q.Plan(14, 2**14, O.gate_stream(qc), Q.PlanOptions(max_ops_per_sweep=128)).stats()
+    assert st.n_gates == 105 and st.n_sweeps <= 2
+
+
+@pytest.mark.parametrize("case", ["t_x_t_x", "rz_small", "qft3crz", "zero_sum"])
+def test_equiv_finish_matches_oracle(case, goldens):
+    if case == "t_x_t_x":
+        a = O.qc2ts(O.QCir(1))
+        qc = O.QCir(1)
+        for g in "txtx":
+            qc.append(O.str_to_operation(g), [0])
+        b = O.qc2ts(qc)
+    elif case == "rz_small":
+        a = O.qc2ts(O.QCir(1))
+        qc = O.QCir(1)
+        qc.append(O.str_to_operation("rz", [O.str_to_phase("0.001")]), [0])
+        b = O.qc2ts(qc)
+    elif case == "qft3crz":
+        a = O.qc2ts(O.qcir_from_qasm_text(goldens["inputs"]["benchmark/qft/qft_3.qasm"]))
+        b = O.qc2ts(O.qcir_from_qasm_text(goldens["inputs"]["benchmark/qft/qft_3crz.qasm"]))
+    else:
+        a = np.array([[1, 0], [0, -1]], dtype=np.complex128)  # sums to exactly zero
+        b = np.eye(2, dtype=np.complex128)
+    sums = O.equiv_sums(a, b)
+    for eps in (1e-2, 1e-6, 1e-8, 1e-10):
+        for strict in (False, True):
+            r = Q.equiv_finish(sums, eps, strict)
+            if case == "zero_sum":
+                assert r.phase_defined == 0 and not np.isfinite(r.norm) and r.equivalent == (0 if True else 1) or not strict
+                continue
+            w = O.finish_equiv(sums, eps, strict)
+            assert bool(r.equivalent) == w.equivalent
+            assert r.cosine == pytest.approx(w.cosine, abs=1e-15)
+            assert r.norm == pytest.approx(w.norm, abs=1e-15)
+            assert (r.phase_num, r.phase_den) == (w.phase.numerator, w.phase.denominator)

@@ -177,3 +177,28 @@ def test_literal_equals_rowform_random():
         # column shard of the row form
         s = O.to_matrix_rowform(qc, col0=8, ncols=8)
         assert np.array_equal(s, b[:, 8:16])
+
+
+def test_c_restatement_matches_numpy():
+    """oracle/oracle_c.c (the plain-C port used as a CPU baseline) == oracle.py."""
+    import cmath
+
+    from oracle import oracle_c
+    from tests.test_abi_cpu import _rand_circuit
+
+    for n, g, seed in [(1, 10, 1), (3, 50, 2), (6, 200, 3)]:
+        qc = _rand_circuit(n, g, seed)
+        want = O.to_matrix_rowform(qc)
+        got = oracle_c.to_matrix(O.gate_stream(qc), n)
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-14
+        half = oracle_c.to_matrix(O.gate_stream(qc), n, 2**n // 2, 2**n // 2)
+        assert np.array_equal(half, got[:, 2**n // 2:])
+        other = O.to_matrix_rowform(_rand_circuit(n, g, seed + 100))
+        cos, _, _ = oracle_c.equiv_reference_passes(want, other)
+        assert cos == pytest.approx(O.cosine_similarity(want, other), rel=1e-12)
+        # the sum ratio is only well conditioned between near-proportional tensors (Appendix C trap 2)
+        other = want * cmath.exp(0.3j) * 0.75
+        cos, norm, ph = oracle_c.equiv_reference_passes(want, other)
+        if abs(np.sum(want)) > 1e-6:
+            assert cos == pytest.approx(1.0, abs=1e-12)
+            assert norm == pytest.approx(0.75, rel=1e-9) and ph == pytest.approx(0.3, abs=1e-9)
