@@ -109,6 +109,7 @@ typedef struct qsx_plan_stats {
     uint64_t n_ops;        /* lowered ops (identity gates dropped)                */
     uint64_t n_sweeps;     /* kernel launches per run                             */
     uint64_t n_stages;     /* register-blocking stages over all sweeps            */
+    uint64_t n_micro_ops;  /* register-level micro-ops after merging diagonal ops */
     uint64_t n_dense_blocks;
     double   alg_bytes_per_run;   /* sum over sweeps of 32 B x elements touched (this shard geometry) */
     double   gate_bytes_per_run;  /* sum over GATES of f*32*rows*ncols, f per SURVEY 8(d)              */

@@ -67,7 +67,7 @@ class PlanOptions(C.Structure):
 
 class PlanStats(C.Structure):
     _fields_ = [("n_gates", C.c_uint64), ("n_ops", C.c_uint64), ("n_sweeps", C.c_uint64), ("n_stages", C.c_uint64),
-                ("n_dense_blocks", C.c_uint64), ("alg_bytes_per_run", C.c_double), ("gate_bytes_per_run", C.c_double),
+                ("n_micro_ops", C.c_uint64), ("n_dense_blocks", C.c_uint64), ("alg_bytes_per_run", C.c_double), ("gate_bytes_per_run", C.c_double),
                 ("plan_host_ms", C.c_double)]
 
 

@@ -44,66 +44,91 @@ __device__ __forceinline__ void static_switch(int v, Fn&& fn) {
 }
 
 // ---------------------------------------------------------------------------------------
-// register-level ops.  E = 2^R elements; `creg` is a required-one mask over the register
-// index (uniform across the grid, so every test below is a uniform branch).
+// register-level micro-ops.  E = 2^R elements per thread.  `creg` is a required-one mask over
+// the register index; it is the same for every thread of the grid, so tests on it are uniform
+// branches.  ALL = true is the common uncontrolled case: no tests, no selects.
 // ---------------------------------------------------------------------------------------
-template <int R, int J>
+template <int R, int J, bool ALL>
 __device__ __forceinline__ void op_u1(double2 (&e)[1 << R], const double* __restrict__ c, uint32_t creg) {
-    double2 const m00 = make_double2(__ldg(c + 0), __ldg(c + 1)), m01 = make_double2(__ldg(c + 2), __ldg(c + 3));
-    double2 const m10 = make_double2(__ldg(c + 4), __ldg(c + 5)), m11 = make_double2(__ldg(c + 6), __ldg(c + 7));
+    double2 const m00 = make_double2(c[0], c[1]), m01 = make_double2(c[2], c[3]);
+    double2 const m10 = make_double2(c[4], c[5]), m11 = make_double2(c[6], c[7]);
 #pragma unroll
     for (int i = 0; i < (1 << R); ++i) {
         if ((i >> J) & 1) continue;
-        if ((i & creg) != creg) continue;
+        if constexpr (!ALL) {
+            if ((i & creg) != creg) continue;
+        }
         double2 const a = e[i], b = e[i | (1 << J)];
         e[i]            = cfma(m01, b, cmul(m00, a));
         e[i | (1 << J)] = cfma(m11, b, cmul(m10, a));
     }
 }
 
-template <int R, int J>
+template <int R, int J, bool ALL>
 __device__ __forceinline__ void op_h(double2 (&e)[1 << R], double s, uint32_t creg) {
 #pragma unroll
     for (int i = 0; i < (1 << R); ++i) {
         if ((i >> J) & 1) continue;
-        if ((i & creg) != creg) continue;
+        if constexpr (!ALL) {
+            if ((i & creg) != creg) continue;
+        }
         double2 const a = e[i], b = e[i | (1 << J)];
         e[i]            = make_double2(s * (a.x + b.x), s * (a.y + b.y));
         e[i | (1 << J)] = make_double2(s * (a.x - b.x), s * (a.y - b.y));
     }
 }
 
-template <int R, int J>
+template <int R, int J, bool ALL>
 __device__ __forceinline__ void op_x(double2 (&e)[1 << R], uint32_t creg) {
 #pragma unroll
     for (int i = 0; i < (1 << R); ++i) {
         if ((i >> J) & 1) continue;
-        if ((i & creg) != creg) continue;
+        if constexpr (!ALL) {
+            if ((i & creg) != creg) continue;
+        }
         double2 const a = e[i];
         e[i]            = e[i | (1 << J)];
         e[i | (1 << J)] = a;
     }
 }
 
-template <int R, int J>
+// X on register bit J controlled by register bit JC: the pairs are known at compile time
+template <int R, int J, int JC>
+__device__ __forceinline__ void op_xc(double2 (&e)[1 << R]) {
+    if constexpr (J != JC) {
+#pragma unroll
+        for (int i = 0; i < (1 << R); ++i) {
+            if (((i >> J) & 1) || !((i >> JC) & 1)) continue;
+            double2 const a = e[i];
+            e[i]            = e[i | (1 << J)];
+            e[i | (1 << J)] = a;
+        }
+    }
+}
+
+template <int R, int J, bool ALL>
 __device__ __forceinline__ void op_ad(double2 (&e)[1 << R], const double* __restrict__ c, uint32_t creg) {
-    double2 const m01 = make_double2(__ldg(c + 0), __ldg(c + 1)), m10 = make_double2(__ldg(c + 2), __ldg(c + 3));
+    double2 const m01 = make_double2(c[0], c[1]), m10 = make_double2(c[2], c[3]);
 #pragma unroll
     for (int i = 0; i < (1 << R); ++i) {
         if ((i >> J) & 1) continue;
-        if ((i & creg) != creg) continue;
+        if constexpr (!ALL) {
+            if ((i & creg) != creg) continue;
+        }
         double2 const a = e[i], b = e[i | (1 << J)];
         e[i]            = cmul(m01, b);
         e[i | (1 << J)] = cmul(m10, a);
     }
 }
 
-template <int R, int JA, int JB>
+template <int R, int JA, int JB, bool ALL>
 __device__ __forceinline__ void op_swap(double2 (&e)[1 << R], uint32_t creg) {
 #pragma unroll
     for (int i = 0; i < (1 << R); ++i) {
         if (!((i >> JA) & 1) || ((i >> JB) & 1)) continue;
-        if ((i & creg) != creg) continue;  // controls never include the swapped bits
+        if constexpr (!ALL) {
+            if ((i & creg) != creg) continue;  // controls never include the swapped bits
+        }
         constexpr int flip = (1 << JA) | (1 << JB);
         double2 const a    = e[i];
         e[i]               = e[i ^ flip];
@@ -125,7 +150,7 @@ __device__ __forceinline__ void op_u2(double2 (&e)[1 << R], const double* __rest
                 double2 acc = make_double2(0.0, 0.0);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    double2 const mk = make_double2(__ldg(m + 2 * (4 * r + k)), __ldg(m + 2 * (4 * r + k) + 1));
+                    double2 const mk = make_double2(m[2 * (4 * r + k)], m[2 * (4 * r + k) + 1]);
                     acc              = cfma(mk, v[k], acc);
                 }
                 w[r] = acc;
@@ -136,76 +161,108 @@ __device__ __forceinline__ void op_u2(double2 (&e)[1 << R], const double* __rest
     }
 }
 
+// merged diagonal: the 2^(R-1) elements with register bit J set
+template <int R, int J>
+__device__ __forceinline__ void op_dtab_half(double2 (&e)[1 << R], const double2* __restrict__ tab) {
+#pragma unroll
+    for (int i = 0; i < (1 << R); ++i) {
+        if (!((i >> J) & 1)) continue;
+        constexpr int lowmask = (1 << J) - 1;
+        int const k           = ((i >> (J + 1)) << J) | (i & lowmask);
+        e[i]                  = cmul(e[i], tab[k]);
+    }
+}
+
 template <int R>
-__device__ __forceinline__ void apply_op(double2 (&e)[1 << R], const DevOp* __restrict__ op, uint32_t grow,
+__device__ __forceinline__ void apply_op(double2 (&e)[1 << R], double2& scal, const DevOp* __restrict__ op, uint32_t grow,
                                          const double* __restrict__ pool) {
-    int4 const hdr        = __ldg(reinterpret_cast<const int4*>(op));       // kind, j0, j1, creg
-    int4 const hdr2       = __ldg(reinterpret_cast<const int4*>(op) + 1);   // cother, pool, pad0, pad1
+    // `op` lives in shared memory: broadcast LDS.128
+    int4 const hdr        = *reinterpret_cast<const int4*>(op);        // kind, j0, j1, creg
+    int4 const hdr2       = *(reinterpret_cast<const int4*>(op) + 1);  // cother, czero, pool, sel
     uint32_t const creg   = (uint32_t)hdr.w;
-    uint32_t const cother = (uint32_t)hdr2.x;
-    if ((grow & cother) != cother) return;
+    uint32_t const cother = (uint32_t)hdr2.x, czero = (uint32_t)hdr2.y;
+    if ((grow & cother) != cother || (grow & czero) != 0u) return;
     const double* c = op->c;
     switch (hdr.x) {
-        case OP_U1:
-            static_switch<R>(hdr.y, [&](auto J) { op_u1<R, decltype(J)::value>(e, c, creg); });
+        case K_U1:
+            static_switch<R>(hdr.y, [&](auto J) {
+                if (creg == 0)
+                    op_u1<R, decltype(J)::value, true>(e, c, 0);
+                else
+                    op_u1<R, decltype(J)::value, false>(e, c, creg);
+            });
             break;
-        case OP_H: {
-            double const s = __ldg(c);
-            static_switch<R>(hdr.y, [&](auto J) { op_h<R, decltype(J)::value>(e, s, creg); });
-            break;
-        }
-        case OP_X:
-            static_switch<R>(hdr.y, [&](auto J) { op_x<R, decltype(J)::value>(e, creg); });
-            break;
-        case OP_AD:
-            static_switch<R>(hdr.y, [&](auto J) { op_ad<R, decltype(J)::value>(e, c, creg); });
-            break;
-        case OP_PHASE: {
-            double2 const w = make_double2(__ldg(c), __ldg(c + 1));
-#pragma unroll
-            for (int i = 0; i < (1 << R); ++i)
-                if ((i & creg) == creg) e[i] = cmul(e[i], w);
+        case K_H: {
+            double const s = c[0];
+            static_switch<R>(hdr.y, [&](auto J) {
+                if (creg == 0)
+                    op_h<R, decltype(J)::value, true>(e, s, 0);
+                else
+                    op_h<R, decltype(J)::value, false>(e, s, creg);
+            });
             break;
         }
-        case OP_NEG:
-#pragma unroll
-            for (int i = 0; i < (1 << R); ++i)
-                if ((i & creg) == creg) e[i] = make_double2(-e[i].x, -e[i].y);
+        case K_X:
+            static_switch<R>(hdr.y, [&](auto J) {
+                if (creg == 0)
+                    op_x<R, decltype(J)::value, true>(e, 0);
+                else
+                    op_x<R, decltype(J)::value, false>(e, creg);
+            });
             break;
-        case OP_MULI: {
-            double const s = __ldg(c);  // +1: multiply by +i ; -1: by -i
-#pragma unroll
-            for (int i = 0; i < (1 << R); ++i)
-                if ((i & creg) == creg) e[i] = make_double2(-s * e[i].y, s * e[i].x);
+        case K_XC:
+            static_switch<R>(hdr.y, [&](auto J) {
+                static_switch<R>(hdr.z, [&](auto JC) { op_xc<R, decltype(J)::value, decltype(JC)::value>(e); });
+            });
             break;
-        }
-        case OP_DIAG: {
-            double2 const d0 = make_double2(__ldg(c), __ldg(c + 1)), d1 = make_double2(__ldg(c + 2), __ldg(c + 3));
-            int const j0 = hdr.y;
-            if (j0 >= 0) {
-#pragma unroll
-                for (int i = 0; i < (1 << R); ++i)
-                    if ((i & creg) == creg) e[i] = cmul(e[i], ((i >> j0) & 1) ? d1 : d0);
-            } else {
-                double2 const d = ((grow >> hdr2.z) & 1u) ? d1 : d0;
-#pragma unroll
-                for (int i = 0; i < (1 << R); ++i)
-                    if ((i & creg) == creg) e[i] = cmul(e[i], d);
-            }
+        case K_AD:
+            static_switch<R>(hdr.y, [&](auto J) {
+                if (creg == 0)
+                    op_ad<R, decltype(J)::value, true>(e, c, 0);
+                else
+                    op_ad<R, decltype(J)::value, false>(e, c, creg);
+            });
             break;
-        }
-        case OP_SWAP: {
+        case K_SWAP: {
             int const ja = hdr.y > hdr.z ? hdr.y : hdr.z, jb = hdr.y > hdr.z ? hdr.z : hdr.y;
             static_switch<R>(ja, [&](auto JA) {
                 static_switch<decltype(JA)::value>(jb, [&](auto JB) {
-                    op_swap<R, decltype(JA)::value, decltype(JB)::value>(e, creg);
+                    if (creg == 0)
+                        op_swap<R, decltype(JA)::value, decltype(JB)::value, true>(e, 0);
+                    else
+                        op_swap<R, decltype(JA)::value, decltype(JB)::value, false>(e, creg);
                 });
             });
             break;
         }
-        case OP_U2:
-            op_u2<R>(e, pool + hdr2.y, creg);
+        case K_U2:
+            op_u2<R>(e, pool + hdr2.z, creg);
             break;
+        case K_DSCAL: {
+            int const sel    = hdr2.w;
+            bool const hi    = sel >= 0 && ((grow >> sel) & 1u);
+            double2 const d  = hi ? make_double2(c[2], c[3]) : make_double2(c[0], c[1]);
+            scal             = cmul(scal, d);
+            break;
+        }
+        case K_DTABH: {
+            const double2* const tab = reinterpret_cast<const double2*>(pool + hdr2.z);
+            static_switch<R>(hdr.y, [&](auto J) { op_dtab_half<R, decltype(J)::value>(e, tab); });
+            break;
+        }
+        case K_DTABF: {
+            const double2* const tab = reinterpret_cast<const double2*>(pool + hdr2.z);
+#pragma unroll
+            for (int i = 0; i < (1 << R); ++i) e[i] = cmul(e[i], tab[i]);
+            break;
+        }
+        case K_SAPPLY: {
+            double2 const sv = scal;
+#pragma unroll
+            for (int i = 0; i < (1 << R); ++i) e[i] = cmul(e[i], sv);
+            scal = make_double2(1.0, 0.0);
+            break;
+        }
         default:
             break;
     }
@@ -216,9 +273,19 @@ __device__ __forceinline__ void apply_op(double2 (&e)[1 << R], const DevOp* __re
 // ---------------------------------------------------------------------------------------
 template <int R>
 __global__ void __launch_bounds__(1 << max_threads_log2(R), 1)
-    sweep_kernel(double2* __restrict__ u, const unsigned char* __restrict__ prog, uint64_t ncols, int log2_ncb) {
+    sweep_kernel(double2* __restrict__ u, const unsigned char* __restrict__ gprog, uint32_t prog_bytes, uint64_t ncols,
+                 int log2_ncb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2* const tile = reinterpret_cast<double2*>(smem_raw);
+    // the sweep program (a few KB, read by every thread for every op) is staged in shared
+    // memory once per CTA; the tile follows it
+    {
+        const uint4* const src = reinterpret_cast<const uint4*>(gprog);
+        uint4* const dst       = reinterpret_cast<uint4*>(smem_raw);
+        for (uint32_t i = threadIdx.x; i < prog_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const unsigned char* const prog = smem_raw;
+    double2* const tile             = reinterpret_cast<double2*>(smem_raw + prog_bytes);
 
     const DevSweep* const sw     = reinterpret_cast<const DevSweep*>(prog);
     const DevStage* const stages = reinterpret_cast<const DevStage*>(prog + sizeof(DevSweep));
@@ -272,7 +339,7 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), 1)
 #pragma unroll
                 for (int j = 0; j < R; ++j)
                     if ((i >> j) & 1) off += gs[j];
-                e[i] = gp[off];
+                e[i] = __ldcg(gp + off);
             }
         } else {
             uint32_t ss[R];
@@ -292,7 +359,8 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), 1)
 
         {
             int const ob = st->op_begin, oe = st->op_end;
-            for (int o = ob; o < oe; ++o) apply_op<R>(e, ops + o, grow, pool);
+            double2 scal = make_double2(1.0, 0.0);  // per-thread product of the stage's K_DSCAL ops
+            for (int o = ob; o < oe; ++o) apply_op<R>(e, scal, ops + o, grow, pool);
         }
 
         if (s == n_stages - 1) {
@@ -306,7 +374,7 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), 1)
 #pragma unroll
                 for (int j = 0; j < R; ++j)
                     if ((i >> j) & 1) off += gs[j];
-                gp[off] = e[i];
+                __stcg(gp + off, e[i]);
             }
         } else {
             uint32_t ss[R];
@@ -328,11 +396,12 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), 1)
 
 template <int R>
 cudaError_t launch_sweep_r(double2* u, int n, uint64_t ncols, const DevSweep& hs, const unsigned char* prog,
-                           cudaStream_t s) {
+                           size_t prog_bytes, cudaStream_t s) {
     (void)n;
     int const m        = hs.m;
     int const threads  = 1 << (m - R + hs.log2w);
-    size_t const smem  = hs.n_stages > 1 ? ((size_t)16 << (m + hs.log2w)) : 0;
+    size_t const smem  = prog_bytes + (hs.n_stages > 1 ? ((size_t)16 << (m + hs.log2w)) : 0);
+    if (prog_bytes % 16 != 0 || smem > 200 * 1024) return cudaErrorInvalidValue;
     int log2_ncols     = 0;
     while ((1ull << log2_ncols) < ncols) ++log2_ncols;
     int const log2_ncb = log2_ncols - hs.log2w;
@@ -348,7 +417,7 @@ cudaError_t launch_sweep_r(double2* u, int n, uint64_t ncols, const DevSweep& hs
         if (rc != cudaSuccess) return rc;
         attr_set[dev] = true;
     }
-    sweep_kernel<R><<<(unsigned)nblocks, threads, smem, s>>>(u, prog, ncols, log2_ncb);
+    sweep_kernel<R><<<(unsigned)nblocks, threads, smem, s>>>(u, prog, (uint32_t)prog_bytes, ncols, log2_ncb);
     return cudaGetLastError();
 }
 
@@ -513,12 +582,12 @@ cudaError_t launch_set_identity(double2* u, int n, uint64_t col0, uint64_t ncols
 }
 
 cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, int R, const DevSweep& hs, const unsigned char* prog,
-                         cudaStream_t s) {
+                         size_t prog_bytes, cudaStream_t s) {
     switch (R) {
-        case 1: return launch_sweep_r<1>(u, n, ncols, hs, prog, s);
-        case 2: return launch_sweep_r<2>(u, n, ncols, hs, prog, s);
-        case 3: return launch_sweep_r<3>(u, n, ncols, hs, prog, s);
-        case 4: return launch_sweep_r<4>(u, n, ncols, hs, prog, s);
+        case 1: return launch_sweep_r<1>(u, n, ncols, hs, prog, prog_bytes, s);
+        case 2: return launch_sweep_r<2>(u, n, ncols, hs, prog, prog_bytes, s);
+        case 3: return launch_sweep_r<3>(u, n, ncols, hs, prog, prog_bytes, s);
+        case 4: return launch_sweep_r<4>(u, n, ncols, hs, prog, prog_bytes, s);
         default: return cudaErrorInvalidValue;
     }
 }

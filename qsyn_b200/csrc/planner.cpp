@@ -211,6 +211,179 @@ void build_stages(Plan& plan, std::vector<int> chosen, PlannedSweep& sw) {
     }
 }
 
+// ---- micro-op emission ------------------------------------------------------------------
+//
+// Non-diagonal ops map 1:1 to register micro-ops.  Diagonal ops (PHASE/NEG/MULI/DIAG) commute
+// with each other and with any op that does not act non-diagonally on their bits, so they are
+// held back and merged:
+//   * a diagonal op whose bits are all OUTSIDE the registers multiplies every element a thread
+//     holds by the same number: it becomes one complex multiply of a per-thread scalar
+//     (K_DSCAL), applied to the registers once at the end of the stage (K_SAPPLY);
+//   * the others are multiplied together, per distinct thread-level condition, into a table
+//     indexed by the register index (K_DTABH when only elements with one register bit set are
+//     affected, K_DTABF otherwise).
+
+struct Cx {
+    double re = 1.0, im = 0.0;
+};
+inline Cx cmul(Cx a, Cx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+
+Cx phase_of(LoweredOp const& op) {
+    switch (op.kind) {
+        case OP_NEG: return {-1.0, 0.0};
+        case OP_MULI: return {0.0, op.c[0]};
+        default: return {op.c[0], op.c[1]};
+    }
+}
+
+void emit_uops(Plan const& plan, PlannedStage& st) {
+    int const R = (int)st.reg_bits.size();
+    int const E = 1 << R;
+    int regidx_of[kMaxRowBits];
+    for (int b = 0; b < kMaxRowBits; ++b) regidx_of[b] = -1;
+    uint32_t regmask = 0;
+    for (int j = 0; j < R; ++j) regidx_of[st.reg_bits[j]] = j, regmask |= 1u << st.reg_bits[j];
+    auto creg_of = [&](uint32_t req) {
+        uint32_t c = 0;
+        for (int j = 0; j < R; ++j)
+            if ((req >> st.reg_bits[j]) & 1u) c |= 1u << j;
+        return c;
+    };
+
+    std::vector<int> pending;  // positions in st.ops of held-back diagonal ops
+    bool used_scalar = false;
+
+    struct Group {
+        uint32_t cother, czero;
+        std::vector<Cx> tab;
+    };
+
+    auto flush = [&](uint32_t filter) {
+        std::vector<int> keep;
+        std::vector<Group> groups;
+        auto group_for = [&](uint32_t cother, uint32_t czero) -> Group& {
+            for (Group& g : groups)
+                if (g.cother == cother && g.czero == czero) return g;
+            groups.push_back(Group{cother, czero, std::vector<Cx>((size_t)E)});
+            return groups.back();
+        };
+        for (int pos : pending) {
+            LoweredOp const& op = plan.ops[st.ops[pos]];
+            if ((op.dmask() & filter) == 0) {
+                keep.push_back(pos);
+                continue;
+            }
+            uint32_t const creg   = creg_of(op.req);
+            uint32_t const cother = op.req & ~regmask;
+            bool const is_diag2   = op.kind == OP_DIAG;
+            int const dj          = is_diag2 ? regidx_of[op.dbit] : -1;
+            if (creg == 0 && dj < 0) {  // nothing in registers: per-thread scalar
+                MicroOp u;
+                u.kind   = K_DSCAL;
+                u.cother = cother;
+                if (is_diag2) {
+                    u.sel  = op.dbit;
+                    u.c[0] = op.c[0], u.c[1] = op.c[1], u.c[2] = op.c[2], u.c[3] = op.c[3];
+                } else {
+                    Cx const w = phase_of(op);
+                    u.c[0] = w.re, u.c[1] = w.im;
+                }
+                st.uops.push_back(std::move(u));
+                used_scalar = true;
+                continue;
+            }
+            if (!is_diag2) {
+                Group& g   = group_for(cother, 0);
+                Cx const w = phase_of(op);
+                for (int i = 0; i < E; ++i)
+                    if (((uint32_t)i & creg) == creg) g.tab[i] = cmul(g.tab[i], w);
+            } else if (dj >= 0) {
+                Group& g = group_for(cother, 0);
+                Cx const d0{op.c[0], op.c[1]}, d1{op.c[2], op.c[3]};
+                for (int i = 0; i < E; ++i)
+                    if (((uint32_t)i & creg) == creg) g.tab[i] = cmul(g.tab[i], ((i >> dj) & 1) ? d1 : d0);
+            } else {  // selecting bit outside the registers, a control inside
+                Cx const d0{op.c[0], op.c[1]}, d1{op.c[2], op.c[3]};
+                Group& g1 = group_for(cother | (1u << op.dbit), 0);
+                for (int i = 0; i < E; ++i)
+                    if (((uint32_t)i & creg) == creg) g1.tab[i] = cmul(g1.tab[i], d1);
+                Group& g0 = group_for(cother, 1u << op.dbit);
+                for (int i = 0; i < E; ++i)
+                    if (((uint32_t)i & creg) == creg) g0.tab[i] = cmul(g0.tab[i], d0);
+            }
+        }
+        pending.swap(keep);
+        for (Group const& g : groups) {
+            uint32_t active = 0;
+            for (int i = 0; i < E; ++i)
+                if (g.tab[i].re != 1.0 || g.tab[i].im != 0.0) active |= 1u << i;
+            if (active == 0) continue;
+            MicroOp u;
+            u.cother = g.cother;
+            u.czero  = g.czero;
+            int half = -1;
+            for (int j = 0; j < R && half < 0; ++j) {
+                bool ok = true;
+                for (int i = 0; i < E; ++i)
+                    if (((active >> i) & 1u) && !((i >> j) & 1)) ok = false;
+                if (ok) half = j;
+            }
+            if (half >= 0) {
+                u.kind = K_DTABH;
+                u.j0   = half;
+                for (int i = 0; i < E; ++i)
+                    if ((i >> half) & 1) u.table.push_back(g.tab[i].re), u.table.push_back(g.tab[i].im);
+            } else {
+                u.kind = K_DTABF;
+                for (int i = 0; i < E; ++i) u.table.push_back(g.tab[i].re), u.table.push_back(g.tab[i].im);
+            }
+            st.uops.push_back(std::move(u));
+        }
+    };
+
+    for (int pos = 0; pos < (int)st.ops.size(); ++pos) {
+        LoweredOp const& op = plan.ops[st.ops[pos]];
+        if (op.tmask() == 0) {
+            pending.push_back(pos);
+            continue;
+        }
+        flush(op.tmask());
+        MicroOp u;
+        u.src    = pos;
+        u.creg   = creg_of(op.req);
+        u.cother = op.req & ~regmask;
+        u.j0     = regidx_of[op.t0];
+        u.j1     = op.t1 >= 0 ? regidx_of[op.t1] : -1;
+        std::memcpy(u.c, op.c, sizeof(u.c));
+        switch (op.kind) {
+            case OP_U1: u.kind = K_U1; break;
+            case OP_H: u.kind = K_H; break;
+            case OP_AD: u.kind = K_AD; break;
+            case OP_SWAP: u.kind = K_SWAP; break;
+            case OP_U2:
+                u.kind  = K_U2;
+                u.table = op.mat;
+                break;
+            default:  // OP_X
+                if (__builtin_popcount(u.creg) == 1) {
+                    u.kind = K_XC;
+                    u.j1   = __builtin_ctz(u.creg);
+                    u.creg = 0;
+                } else {
+                    u.kind = K_X;
+                }
+                break;
+        }
+        st.uops.push_back(std::move(u));
+    }
+    flush(~0u);
+    if (used_scalar) {
+        MicroOp u;
+        u.kind = K_SAPPLY;
+        st.uops.push_back(std::move(u));
+    }
+}
+
 void finish_sweep(Plan& plan, std::vector<int> const& chosen, uint32_t S) {
     PlanConfig const& cfg = plan.cfg;
     PlannedSweep sw;
@@ -226,6 +399,10 @@ void finish_sweep(Plan& plan, std::vector<int> const& chosen, uint32_t S) {
     for (int idx : chosen) common &= plan.ops[idx].req;
     sw.fixed_one = chosen.empty() ? 0u : (common & ~S);
     build_stages(plan, chosen, sw);
+    for (PlannedStage& st : sw.stages) {
+        emit_uops(plan, st);
+        plan.stats.n_micro_ops += st.uops.size();
+    }
     sw.alg_bytes = 32.0 * std::ldexp(1.0, cfg.n - popc(sw.fixed_one)) * (double)cfg.ncols;
     plan.stats.n_stages += sw.stages.size();
     plan.stats.alg_bytes_per_run += sw.alg_bytes;
@@ -298,46 +475,30 @@ void serialize(Plan& plan) {
             std::memset(&ds, 0, sizeof(ds));
             ds.op_begin = (int)ops.size();
             ds.r        = (int)st.reg_bits.size();
-            uint32_t regmask_local = 0, regmask_global = 0;
-            int regidx_of[kMaxRowBits];
-            for (int b = 0; b < kMaxRowBits; ++b) regidx_of[b] = -1;
+            uint32_t regmask_local = 0;
             for (int j = 0; j < ds.r; ++j) {
-                ds.rl[j]                    = local_of[st.reg_bits[j]];
-                regidx_of[st.reg_bits[j]] = j;
+                ds.rl[j] = local_of[st.reg_bits[j]];
                 regmask_local |= 1u << ds.rl[j];
-                regmask_global |= 1u << st.reg_bits[j];
             }
             int nt = 0;
             for (int l = 0; l < m; ++l)
                 if (!((regmask_local >> l) & 1u)) ds.tl[nt++] = l;
             ds.n_t = nt;
-            for (int idx : st.ops) {
-                LoweredOp const& lo = plan.ops[idx];
+            for (MicroOp const& mo : st.uops) {
                 DevOp d;
                 std::memset(&d, 0, sizeof(d));
-                d.kind = lo.kind;
-                d.j0   = lo.t0 >= 0 ? regidx_of[lo.t0] : -1;
-                d.j1   = lo.t1 >= 0 ? regidx_of[lo.t1] : -1;
-                d.pool = -1;
-                d.pad0 = -1;
-                for (int b = 0; b < cfg.n; ++b)
-                    if ((lo.req >> b) & 1u) {
-                        if (regidx_of[b] >= 0)
-                            d.creg |= 1u << regidx_of[b];
-                        else
-                            d.cother |= 1u << b;
-                    }
-                if (lo.kind == OP_DIAG) {
-                    // the selecting bit is either a register bit (j0) or any other row bit (pad0)
-                    if (regidx_of[lo.dbit] >= 0)
-                        d.j0 = regidx_of[lo.dbit];
-                    else
-                        d.pad0 = lo.dbit;
-                }
-                std::memcpy(d.c, lo.c, sizeof(d.c));
-                if (lo.kind == OP_U2) {
+                d.kind   = mo.kind;
+                d.j0     = mo.j0;
+                d.j1     = mo.j1;
+                d.creg   = mo.creg;
+                d.cother = mo.cother;
+                d.czero  = mo.czero;
+                d.sel    = mo.sel;
+                d.pool   = -1;
+                std::memcpy(d.c, mo.c, sizeof(d.c));
+                if (!mo.table.empty()) {
                     d.pool = (int)pool.size();
-                    pool.insert(pool.end(), lo.mat.begin(), lo.mat.end());
+                    pool.insert(pool.end(), mo.table.begin(), mo.table.end());
                 }
                 ops.push_back(d);
             }
@@ -419,6 +580,11 @@ int build_plan(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gat
         for (size_t k = before; k < plan.ops.size(); ++k) plan.stats.gate_bytes_per_run += 32.0 * shard_elems * plan.ops[k].frac;
     }
     plan.stats.n_ops = plan.ops.size();
+    for (LoweredOp const& op : plan.ops)
+        if (op.t1 >= 0 && cfg.R < 2) {  // two-target ops need both bits in registers
+            cfg.R     = 2;
+            cfg.m_cap = std::max(cfg.m_cap, 2);
+        }
     schedule(plan);
     plan.stats.n_sweeps = plan.sweeps.size();
     serialize(plan);
@@ -450,6 +616,18 @@ std::string dump_plan_json(const Plan& plan) {
                 for (int k = 0; k < 8; ++k) os << (k ? "," : "") << op.c[k];
                 os << "],\"mat\":[";
                 for (size_t k = 0; k < op.mat.size(); ++k) os << (k ? "," : "") << op.mat[k];
+                os << "]}";
+            }
+            static char const* const kMicro[] = {"U1", "H", "X", "AD", "XC", "SWAP", "U2", "DSCAL", "DTABH", "DTABF", "SAPPLY"};
+            os << "],\"uops\":[";
+            for (size_t i = 0; i < st.uops.size(); ++i) {
+                MicroOp const& u = st.uops[i];
+                os << (i ? "," : "") << "{\"kind\":\"" << kMicro[u.kind] << "\",\"j0\":" << u.j0 << ",\"j1\":" << u.j1
+                   << ",\"creg\":" << u.creg << ",\"cother\":" << u.cother << ",\"czero\":" << u.czero
+                   << ",\"sel\":" << u.sel << ",\"src\":" << u.src << ",\"c\":[";
+                for (int k = 0; k < 8; ++k) os << (k ? "," : "") << u.c[k];
+                os << "],\"table\":[";
+                for (size_t k = 0; k < u.table.size(); ++k) os << (k ? "," : "") << u.table[k];
                 os << "]}";
             }
             os << "]}";

@@ -25,9 +25,23 @@ struct LoweredOp {
     uint32_t dmask() const { return req | (dbit >= 0 ? 1u << dbit : 0u); }
 };
 
+// what the kernel executes (see MicroKind); masks are in GLOBAL row bits except creg
+struct MicroOp {
+    int32_t  kind   = K_U1;
+    int      j0     = -1, j1 = -1;  // register-bit indices
+    uint32_t creg   = 0;            // in-register required-one mask (non-diagonal kinds)
+    uint32_t cother = 0;            // thread-level required-one mask (global row bits outside the registers)
+    uint32_t czero  = 0;            // thread-level required-zero mask
+    int      sel    = -1;           // K_DSCAL: global row bit choosing d1
+    double   c[8]   = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<double> table;      // K_DTAB*: complex entries ; K_U2: 4x4 matrix
+    int      src    = -1;           // non-diagonal kinds: position in PlannedStage::ops
+};
+
 struct PlannedStage {
     std::vector<int> reg_bits;  // global row bit of register bit j (size R)
-    std::vector<int> ops;       // indices into Plan::ops
+    std::vector<int> ops;       // indices into Plan::ops (semantic order)
+    std::vector<MicroOp> uops;  // what the kernel runs for this stage
 };
 
 struct PlannedSweep {

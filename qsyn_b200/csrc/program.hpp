@@ -9,7 +9,9 @@
 //   stage         : within a sweep, each thread holds 2^r rows x 1 column in registers
 //                   (r "register bits" out of the tile bits); stages are separated by a
 //                   shared-memory transpose that changes which tile bits are in registers
-//   op            : one lowered gate, applied in registers
+//   op            : one lowered gate (semantic form, global row bits)
+//   micro-op      : what the kernel executes in registers; diagonal ops of a stage are merged
+//                   into per-thread scalars (K_DSCAL) and small phase tables (K_DTAB*)
 #pragma once
 #include <cstdint>
 
@@ -23,34 +25,51 @@ constexpr int kMaxRowBits  = 26;
 // R = 4 instantiation is compiled for <= 512 threads (128 registers), the others for 1024.
 constexpr int max_threads_log2(int R) { return R >= 4 ? 9 : 10; }
 
+// semantic kinds of lowered gates (host side, planner + dumps)
 enum OpKind : int32_t {
-    OP_U1    = 0,  // general 2x2 on register bit j0:  c = m00,m01,m10,m11 (re,im)
+    OP_U1    = 0,  // general 2x2 on target bit t0:  c = m00,m01,m10,m11 (re,im)
     OP_H     = 1,  // s*(a+b), s*(a-b)                  c[0] = s
     OP_X     = 2,  // swap the pair (exact permutation)
     OP_AD    = 3,  // anti-diagonal: a' = m01*b, b' = m10*a   c = m01, m10
     OP_PHASE = 4,  // e *= w where all required bits are 1    c = w
-    OP_DIAG  = 5,  // e *= (bit j0 ? d1 : d0)                 c = d0, d1
-    OP_SWAP  = 6,  // swap register bits j0 and j1
-    OP_U2    = 7,  // dense 4x4 on register bits (1,0) (first target = bit 1); matrix in the pool
-    OP_NEG   = 8,  // e = -e where required bits are 1  (snapped Z / CZ)
-    OP_MULI  = 9,  // e *= +i (c[0] = +1) or -i (c[0] = -1) where required bits are 1 (snapped S / Sdg)
+    OP_DIAG  = 5,  // e *= (dbit ? d1 : d0) where required     c = d0, d1
+    OP_SWAP  = 6,  // swap row bits t0 and t1
+    OP_U2    = 7,  // dense 4x4 on (t0,t1) (t0 = MSB)
+    OP_NEG   = 8,  // PHASE with w = -1  (snapped Z / CZ)
+    OP_MULI  = 9,  // PHASE with w = +-i (snapped S / Sdg), c[0] = +-1
 };
 
-// All masks are "required-one" masks: the op acts on an element only if every bit of the
-// mask is 1 in the element's row index.
+// kinds the kernel interprets
+enum MicroKind : int32_t {
+    K_U1     = 0,   // 2x2 on register bit j0, creg = in-register controls
+    K_H      = 1,
+    K_X      = 2,
+    K_AD     = 3,
+    K_XC     = 4,   // X on register bit j0 controlled by register bit j1 (compile-time specialised CX)
+    K_SWAP   = 5,   // swap register bits j0, j1
+    K_U2     = 6,   // dense 4x4 on register bits (1,0); matrix at pool
+    K_DSCAL  = 7,   // per-thread scalar: s *= (sel >= 0 && row bit sel) ? d1 : d0    c = d0, d1
+    K_DTABH  = 8,   // e[i] *= tab[i without bit j0] for the 8 (2^(R-1)) elements with bit j0 set; table at pool
+    K_DTABF  = 9,   // e[i] *= tab[i] for all 2^R elements; table at pool
+    K_SAPPLY = 10,  // e[i] *= s for all i ; s = 1   (emitted once at the end of a stage that used K_DSCAL)
+};
+
+// Thread-level predicate of every micro-op: (row & cother) == cother && (row & czero) == 0, where
+// `row` is the thread's global row index with the register bits cleared.
 struct alignas(16) DevOp {
     int32_t  kind;
-    int32_t  j0, j1;   // register-bit indices of the non-diagonal targets (or -1)
-    uint32_t creg;     // required-one mask over the register index (bits 0..r-1)
+    int32_t  j0, j1;   // register-bit indices (or -1)
+    uint32_t creg;     // required-one mask over the register index (bits 0..r-1), non-diagonal kinds only
     uint32_t cother;   // required-one mask over GLOBAL row bits that are not register bits this stage
-    int32_t  pool;     // OP_U2: offset in doubles into the constant pool
-    int32_t  pad0, pad1;
+    uint32_t czero;    // required-zero mask over GLOBAL row bits that are not register bits this stage
+    int32_t  pool;     // offset in doubles into the constant pool (K_U2 matrix, K_DTAB* table)
+    int32_t  sel;      // K_DSCAL: global row bit selecting d1 (or -1)
     double   c[8];
 };
 static_assert(sizeof(DevOp) == 96, "DevOp layout");
 
 struct alignas(16) DevStage {
-    int32_t op_begin, op_end;     // [begin,end) into the sweep's op array
+    int32_t op_begin, op_end;     // [begin,end) into the sweep's micro-op array
     int32_t r;                    // register bits used (== kernel template R)
     int32_t n_t;                  // number of thread-row bits = m - r
     int32_t rl[kMaxRegBits];      // tile-local bit position of register bit j

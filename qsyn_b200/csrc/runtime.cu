@@ -308,7 +308,8 @@ int qsx_plan_run(const qsx_plan* cplan, qsx_unitary* u, qsx_stop_fn should_stop,
             }
         }
         qsx::DevSweep const& hs = *reinterpret_cast<qsx::DevSweep const*>(pl.blob.data() + pl.sweep_offset[s]);
-        QSX_CUDA(qsx::launch_sweep(u->data, u->n, u->ncols, pl.cfg.R, hs, dblob + pl.sweep_offset[s], c->stream));
+        QSX_CUDA(qsx::launch_sweep(u->data, u->n, u->ncols, pl.cfg.R, hs, dblob + pl.sweep_offset[s], pl.sweep_size[s],
+                                   c->stream));
         pending_bytes += pl.sweeps[s].alg_bytes;
         ++launches;
     }

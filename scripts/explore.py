@@ -1,10 +1,7 @@
 """Exploratory timing of plan options on one GPU (not the bench; numbers guide tuning)."""
-import itertools
 import json
 import sys
 import time
-
-import numpy as np
 
 sys.path.insert(0, ".")
 import qsyn_b200 as Q
@@ -30,16 +27,15 @@ def time_plan(n, gs, opt, reps=3):
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 12
     g = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
+    configs = json.loads(sys.argv[3]) if len(sys.argv) > 3 else [
+        (0, 4, 10, 3, 48), (0, 4, 10, 5, 48),
+        (1, 4, 10, 3, 8), (1, 4, 10, 3, 16), (1, 4, 10, 3, 48), (1, 4, 10, 3, 200),
+        (1, 4, 9, 3, 48), (1, 4, 8, 3, 48), (1, 3, 9, 3, 48), (1, 3, 8, 3, 48), (1, 4, 6, 3, 48), (1, 3, 7, 4, 48),
+    ]
     qc = O.qcir_from_qasm_text(O.random_clifford_t_qasm(n, g, 20261019))
     gs = O.gate_stream(qc)
     print("n", n, "gates", g, flush=True)
-    rows = []
-    for fuse, R, tile, w, cap in [
-        (0, 4, 10, 3, 48), (0, 3, 10, 3, 48), (0, 4, 10, 4, 48), (0, 4, 10, 5, 48),
-        (1, 4, 10, 3, 16), (1, 4, 10, 3, 32), (1, 4, 10, 3, 48), (1, 4, 10, 3, 96), (1, 4, 10, 3, 200),
-        (1, 4, 9, 3, 48), (1, 4, 9, 4, 48), (1, 4, 8, 3, 48), (1, 4, 8, 5, 48), (1, 3, 10, 3, 48), (1, 3, 9, 3, 48), (1, 3, 8, 3, 48),
-        (1, 4, 6, 3, 48), (1, 4, 4, 3, 48), (1, 3, 3, 3, 48),
-    ]:
+    for fuse, R, tile, w, cap in configs:
         opt = Q.PlanOptions(fuse=fuse, reg_qubits=R, tile_qubits=tile, log2_tile_cols=w, max_ops_per_sweep=cap)
         try:
             r = time_plan(n, gs, opt)
@@ -47,11 +43,8 @@ def main():
             r = {"error": str(e)}
         r.update(fuse=fuse, R=R, tile=tile, log2w=w, cap=cap)
         print(json.dumps(r), flush=True)
-    # QFT
     qft = O.gate_stream(O.qcir_from_qasm_text(O.qft_qasm(n)))
-    for cap in (48, 200):
-        print("qft", json.dumps(time_plan(n, qft, Q.PlanOptions(max_ops_per_sweep=cap))), flush=True)
-    # equiv
+    print("qft", json.dumps(time_plan(n, qft, Q.PlanOptions(max_ops_per_sweep=128))), flush=True)
     a, b = Q.Unitary(n), Q.Unitary(n)
     a.equiv_partial(b)
     t0 = time.perf_counter()

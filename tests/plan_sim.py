@@ -62,11 +62,77 @@ def apply_op(u, n, op):
 
 
 def run_plan(dump, u):
+    """Executes the SEMANTIC ops in scheduled order."""
     n = dump["n"]
     for sw in dump["sweeps"]:
         for st in sw["stages"]:
             for op in st["ops"]:
                 apply_op(u, n, op)
+    return u
+
+
+def run_plan_uops(dump, u):
+    """Executes the MICRO-ops the kernel runs (merged diagonals, per-thread scalars), with the
+    kernel's semantics: thread-level predicate on (cother, czero); K_DSCAL accumulates a
+    per-thread scalar that K_SAPPLY applies at the end of the stage."""
+    n = dump["n"]
+    rows = np.arange(2**n)
+    for sw in dump["sweeps"]:
+        for st in sw["stages"]:
+            rb = st["reg_bits"]
+            regidx = np.zeros(2**n, dtype=np.int64)
+            for j, b in enumerate(rb):
+                regidx |= ((rows >> b) & 1) << j
+            scal = np.ones(2**n, dtype=np.complex128)
+            used_scalar = False
+            nondiag_seen = []
+            for uop in st["uops"]:
+                k = uop["kind"]
+                tsel = ((rows & uop["cother"]) == uop["cother"]) & ((rows & uop["czero"]) == 0)
+                c = uop["c"]
+                if k == "DSCAL":
+                    d0, d1 = complex(c[0], c[1]), complex(c[2], c[3])
+                    w = np.full(2**n, d0)
+                    if uop["sel"] >= 0:
+                        w = np.where(((rows >> uop["sel"]) & 1) == 1, d1, d0)
+                    scal = np.where(tsel, scal * w, scal)
+                    used_scalar = True
+                    assert all(not (uop["cother"] >> b) & 1 and not (uop["czero"] >> b) & 1 for b in rb)
+                elif k == "SAPPLY":
+                    u *= scal[:, None]
+                    scal[:] = 1
+                elif k == "DTABF":
+                    tab = np.array(uop["table"]).reshape(-1, 2)
+                    tab = tab[:, 0] + 1j * tab[:, 1]
+                    assert len(tab) == 2 ** len(rb)
+                    u[tsel] *= tab[regidx[tsel]][:, None]
+                elif k == "DTABH":
+                    j = uop["j0"]
+                    tab = np.array(uop["table"]).reshape(-1, 2)
+                    tab = tab[:, 0] + 1j * tab[:, 1]
+                    assert len(tab) == 2 ** (len(rb) - 1)
+                    kidx = ((regidx >> (j + 1)) << j) | (regidx & ((1 << j) - 1))
+                    sel = tsel & (((regidx >> j) & 1) == 1)
+                    u[sel] *= tab[kidx[sel]][:, None]
+                else:
+                    op = st["ops"][uop["src"]]
+                    nondiag_seen.append(uop["src"])
+                    # the micro-op must encode the same condition as the semantic op
+                    req = uop["cother"]
+                    creg = uop["creg"] | ((1 << uop["j1"]) if k == "XC" else 0)
+                    for j, b in enumerate(rb):
+                        if (creg >> j) & 1:
+                            req |= 1 << b
+                    assert req == op["req"] and uop["czero"] == 0, (uop, op)
+                    assert rb[uop["j0"]] == op["t0"]
+                    if op["t1"] >= 0 and k != "XC":
+                        assert rb[uop["j1"]] == op["t1"]
+                    apply_op(u, n, op)
+            assert nondiag_seen == sorted(nondiag_seen)
+            assert nondiag_seen == [i for i, op in enumerate(st["ops"]) if op["t0"] >= 0]
+            if used_scalar:
+                assert st["uops"][-1]["kind"] == "SAPPLY"
+            assert np.all(scal == 1)
     return u
 
 

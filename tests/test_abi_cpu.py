@@ -71,7 +71,7 @@ def test_schedule_preserves_the_unitary(n, g, seed, fuse):
     qc = _rand_circuit(n, g, seed)
     want = O.to_matrix_rowform(qc)
     for opt in (Q.PlanOptions(fuse=fuse), Q.PlanOptions(fuse=fuse, reg_qubits=3, tile_qubits=5, max_ops_per_sweep=9),
-                Q.PlanOptions(fuse=fuse, snap_tol=-1.0, reg_qubits=2)):
+                Q.PlanOptions(fuse=fuse, snap_tol=-1.0, reg_qubits=2), Q.PlanOptions(fuse=fuse, reg_qubits=1, tile_qubits=2)):
         plan = Q.Plan(n, 2**n, O.gate_stream(qc), opt)
         d = plan.dump()
         st = plan.stats()
@@ -82,6 +82,10 @@ def test_schedule_preserves_the_unitary(n, g, seed, fuse):
         got = plan_sim.run_plan(d, np.eye(2**n, dtype=np.complex128))
         err = np.linalg.norm(got - want) / np.linalg.norm(want)
         assert err < 1e-13, err
+        # ... and so do the merged micro-ops the kernel actually executes
+        got = plan_sim.run_plan_uops(d, np.eye(2**n, dtype=np.complex128))
+        err = np.linalg.norm(got - want) / np.linalg.norm(want)
+        assert err < 1e-13, err
 
 
 def test_snapping_is_optional_and_small():
@@ -90,10 +94,16 @@ def test_snapping_is_optional_and_small():
     d_exact = Q.Plan(4, 16, O.gate_stream(qc), Q.PlanOptions(snap_tol=-1.0)).dump()
     d_snap = Q.Plan(4, 16, O.gate_stream(qc)).dump()
     kinds = lambda d: {op["kind"] for sw in d["sweeps"] for st in sw["stages"] for op in st["ops"]}
+    ukinds = {u["kind"] for sw in d_snap["sweeps"] for st in sw["stages"] for u in st["uops"]}
+    assert "H" in ukinds and ukinds & {"DTABH", "DTABF"}  # n = R = 4: every bit is a register bit
+    d6 = Q.Plan(6, 64, O.gate_stream(O.qcir_from_qasm_text(O.random_clifford_t_qasm(6, 300, 9)))).dump()
+    assert {"DSCAL", "SAPPLY"} <= {u["kind"] for sw in d6["sweeps"] for st in sw["stages"] for u in st["uops"]}
     assert "X" in kinds(d_snap) and "NEG" in kinds(d_snap) and "MULI" in kinds(d_snap)
     assert "X" not in kinds(d_exact) and "NEG" not in kinds(d_exact)
     for d in (d_exact, d_snap):
         got = plan_sim.run_plan(d, np.eye(16, dtype=np.complex128))
+        assert np.linalg.norm(got - want) / 4.0 < 1e-13
+        got = plan_sim.run_plan_uops(d, np.eye(16, dtype=np.complex128))
         assert np.linalg.norm(got - want) / 4.0 < 1e-13
 
 
@@ -146,7 +156,10 @@ def test_equiv_finish_matches_oracle(case, goldens):
         for strict in (False, True):
             r = Q.equiv_finish(sums, eps, strict)
             if case == "zero_sum":
-                assert r.phase_defined == 0 and not np.isfinite(r.norm) and r.equivalent == (0 if True else 1) or not strict
+                # Appendix C trap 2: defined behaviour instead of the reference's NaN -> UB
+                assert r.phase_defined == 0 and not np.isfinite(r.norm)
+                if strict:
+                    assert r.equivalent == 0
                 continue
             w = O.finish_equiv(sums, eps, strict)
             assert bool(r.equivalent) == w.equivalent
