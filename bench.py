@@ -1,0 +1,434 @@
+#!/usr/bin/env python
+"""bench.py -- qcir->unitary gate-apply + tensor-equiv on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one verification job, exactly what the
+reference does for `qc2ts; qc2ts; tensor equiv 0 1`:
+    build U_A for circuit A   (identity + all gates)
+    build U_B for circuit B   (A followed by t,x,t,x on qubit 0 -> equivalent, global phase pi/4)
+    fused equivalence reduction of (U_A, U_B) + host finish (verdict / norm / phase)
+The unitary's columns are sharded over the N ranks (one process per GPU, no communication
+during construction); the 8 partial sums are combined with ONE all-reduce (NCCL).
+
+metric `value` = effective gate-apply throughput: sum over GATES of the algorithmic bytes the
+reference touches for that gate (f * 32 B * 4^n) divided by the device time of
+the whole step (construction of both operands + equivalence), inputs resident in HBM
+(schedules prebuilt and uploaded).  `e2e` = the same metric through the C ABI from HOST
+gate arrays: scheduling, program upload (H2D) and the verdict read-back (D2H) are inside the
+timed region.  `roofline` = the dominant kernel (sweep_kernel) against measured HBM copy
+bandwidth.  `cpu_baseline` = the oracle restatement of the reference's per-gate tensordot
+algorithm (numpy/OpenBLAS, all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_qubits, generator, n_gates, seed, description)   -- SURVEY.md 8(d) C2..C5
+    "c2": (12, "clifford_t", 2000, 20261019, "C2: 12-qubit random Clifford+T, 2000 gates (256 MiB unitary)"),
+    "c3": (14, "qft", 105, 0, "C3: 14-qubit QFT (benchmark/qft generator), 105 gates (4 GiB unitary)"),
+    "c4": (15, "clifford_t", 10000, 20261020, "C4: 15-qubit random Clifford+T, 10000 gates (16 GiB unitary)"),
+    "c5": (16, "clifford_t", 10000, 20261021, "C5: 16-qubit random Clifford+T, 10000 gates (64 GiB unitary)"),
+    "tiny": (8, "clifford_t", 400, 7, "tiny: 8-qubit random Clifford+T, 400 gates (smoke)"),
+}
+
+
+def build_workload(name):
+    """Circuits A and B as gate streams.  Uses the oracle ONLY as the synthetic-input generator +
+    QASM/gate-matrix front end of the checker side; the timed product path receives plain
+    (n_ctrls, qubits, matrix) arrays through the C ABI."""
+    from oracle import oracle as O
+
+    n, gen, g, seed, desc = WORKLOADS[name]
+    text = O.random_clifford_t_qasm(n, g, seed) if gen == "clifford_t" else O.qft_qasm(n)
+    qc_a = O.qcir_from_qasm_text(text)
+    qc_b = O.qcir_from_qasm_text(text)
+    for nm in "txtx":
+        qc_b.append(O.str_to_operation(nm), [0])
+    return n, desc, qc_a, qc_b, O.gate_stream(qc_a), O.gate_stream(qc_b)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.rows, self.proc, self.idx = [], None, device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import qsyn_b200 as Q
+    from qsyn_b200 import abi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    if Q.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n, desc, qc_a, qc_b, gs_a, gs_b = build_workload(args.workload)
+    dim = 2**n
+    assert dim % world == 0
+    ncols = dim // world
+    col0 = rank * ncols
+    opt = Q.PlanOptions(max_ops_per_sweep=args.cap, tile_qubits=args.tile, reg_qubits=args.reg, log2_tile_cols=args.log2w)
+
+    stream = torch.cuda.ExternalStream(abi.device_stream(local), device=torch.device("cuda", local))
+    ua = Q.Unitary(n, local, col0, ncols)
+    ub = Q.Unitary(n, local, col0, ncols)
+    plan_a = Q.Plan(n, ncols, gs_a, opt)
+    plan_b = Q.Plan(n, ncols, gs_b, opt)
+    st_a, st_b = plan_a.stats(), plan_b.stats()
+    sums_dev = torch.zeros(8, dtype=torch.float64, device="cuda")
+
+    launches = {"n": 0}
+
+    def combine(sums):
+        if world > 1:  # ONE all-reduce of 8 doubles over NVLink
+            sums_dev.copy_(torch.from_numpy(sums))
+            dist.all_reduce(sums_dev, op=dist.ReduceOp.SUM)
+            return sums_dev.cpu().numpy()
+        return sums
+
+    def step_resident():
+        """inputs resident: prebuilt schedules, device-side identity, async sweeps."""
+        ua.set_identity()
+        ra = plan_a.run(ua, flags=abi.QSX_RUN_ASYNC)
+        ub.set_identity()
+        rb = plan_b.run(ub, flags=abi.QSX_RUN_ASYNC)
+        sums = combine(ua.equiv_partial(ub))
+        launches["n"] += 2 + ra.launches + rb.launches + 2
+        return Q.equiv_finish(sums, 1e-6, False)
+
+    # host-side input buffers of the C ABI (array of qsx_gate + matrices), built once
+    import ctypes as C
+    arr_a, keep_a, na = abi.pack_gates(gs_a)
+    arr_b, keep_b, nb = abi.pack_gates(gs_b)
+    null_stop = C.cast(None, abi.STOP_FN)
+
+    def step_e2e():
+        """through the C ABI from host gate arrays: schedule + program upload + sweeps + verdict."""
+        L = Q.lib()
+        ua.set_identity()
+        abi._check(L.qsx_apply_gates(ua._h, arr_a, na, C.byref(opt), null_stop, None, None))
+        ub.set_identity()
+        abi._check(L.qsx_apply_gates(ub._h, arr_b, nb, C.byref(opt), null_stop, None, None))
+        return Q.equiv_finish(combine(ua.equiv_partial(ub)), 1e-6, False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        abi.device_synchronize(local)
+
+    # ---- correctness of the thing we time (cheap, size independent) ----
+    r = step_resident()
+    assert r.equivalent == 1 and (r.phase_num, r.phase_den) == (1, 4) and abs(r.norm - 1) < 1e-9, \
+        (r.equivalent, r.phase_num, r.phase_den, r.norm)
+
+    for _ in range(max(args.warmup, 3) - 1):
+        step_resident()
+
+    # ---- device-resident timing: CUDA events on the library stream ----
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches["n"] = 0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    gpu_launches = launches["n"]
+
+    # ---- dominant kernel, timed live with CUDA events around the sweep launches only ----
+    ua.set_identity()
+    abi.device_synchronize(local)
+    kr = []
+    for _ in range(3):
+        kr.append(plan_a.run(ua).device_ms)
+    sweep_ms = min(kr)
+    t = torch.tensor([sweep_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sweep_ms = float(t.item())
+
+    # equivalence alone (wall, includes the 64-byte read-back and the all-reduce)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        combine(ua.equiv_partial(ub))
+    barrier()
+    equiv_ms = (time.perf_counter() - t0) / 5 * 1e3
+
+    # ---- end-to-end through the C ABI from host buffers ----
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+
+    # per-gate algorithmic bytes of the WHOLE job (all shards): both operands
+    gate_bytes = (st_a.gate_bytes_per_run + st_b.gate_bytes_per_run) * world
+    value = gate_bytes / (ms_step * 1e-3) / 1e9
+    e2e_value = gate_bytes / e2e_s / 1e9
+    h2d = int(_plan_blob_bytes(plan_a) + _plan_blob_bytes(plan_b))
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = st_a.alg_bytes_per_run / (sweep_ms * 1e-3) / 1e9  # per GPU
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload)
+
+    out = None
+    if rank == 0:
+        out = {
+            "metric": "qcir2unitary_gate_apply_effective_GBps",
+            "value": round(value, 2),
+            "unit": "GB/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms_step, 4),
+            "higher_is_better": True,
+            "scaling": "strong",
+            "vs_baseline": None,
+            "dtype": "complex128 (f64)",
+            "data": "synthetic (seeded random Clifford+T / generated QFT circuits; no reference dataset exists)",
+            "config": {
+                "workload": desc,
+                "n_qubits": n,
+                "gates_A": len(gs_a), "gates_B": len(gs_b),
+                "columns_per_gpu": ncols,
+                "step": "identity+construct A, identity+construct B, fused equiv + host finish (verdict Equivalent, phase pi/4)",
+                "l2": "unitary shard per GPU is %.0f MiB; L2 is 126 MB: %s" % (
+                    16 * dim * ncols / 2**20, "inputs larger than L2" if 16 * dim * ncols > 126e6 else "shard fits in L2 (strong scaling), no flush"),
+                "schedule": {"sweeps_A": st_a.n_sweeps, "stages_A": st_a.n_stages, "micro_ops_A": st_a.n_micro_ops,
+                             "max_ops_per_sweep": args.cap, "tile_qubits": args.tile, "reg_qubits": args.reg},
+            },
+            "construct_ms_A": round(sweep_ms, 4),
+            "equiv_ms": round(equiv_ms, 4),
+            "equiv_GBps": round(2 * 16 * dim * dim / (equiv_ms * 1e-3) / 1e9, 1),
+            "gpu_launches": gpu_launches,
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 2), "unit": "GB/s", "ms_per_step": round(e2e_s * 1e3, 4),
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64,
+                    "note": "host gate arrays -> qsx_apply_gates (schedule + program upload + sweeps) x2 -> qsx_equiv_partial -> verdict"},
+            "roofline": {"bound": "hbm", "kernel": "sweep_kernel<%d>" % args.reg, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": st_a.alg_bytes_per_run / max(st_a.n_sweeps, 1),
+                         "launches": st_a.n_sweeps, "avg_launch_us": round(sweep_ms * 1e3 / max(st_a.n_sweeps, 1), 2)},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args.workload, budget_s=args.cpu_budget)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+def _plan_blob_bytes(plan):
+    # program bytes uploaded per qsx_apply_gates call: 192 B header + 80 B/stage + 96 B/micro-op (+ tables)
+    d = plan.dump()
+    total = 0
+    for sw in d["sweeps"]:
+        total += 192
+        for st in sw["stages"]:
+            total += 80 + sum(96 + 8 * len(u["table"]) for u in st["uops"])
+        total = (total + 255) // 256 * 256
+    return total
+
+
+# ------------------------------------------------------------------------------------------
+# CPU side: the oracle restatement of the reference algorithm, as a REPORTED baseline
+# ------------------------------------------------------------------------------------------
+def _gate_fraction(op):
+    # touched fraction f per gate class
+    f = 0.5 ** op.n_ctrls
+    if op.kind == "pz":
+        f *= 0.5
+    if op.kind == "swap":
+        f *= 0.5
+    return f
+
+
+def cpu_reference_sample(workload: str, n_gates: int):
+    """Times the literal per-gate tensordot loop of qcir_to_tensor.cpp:173-194 (numpy tensordot =
+    transpose + zgemm on OpenBLAS, all host threads) for the first n_gates of the workload,
+    then the 8-pass equivalence of tensor_cmd.cpp:152-154 (single-thread C port)."""
+    import numpy as np
+
+    from oracle import oracle as O
+    from oracle import oracle_c
+
+    n, desc, qc_a, _, _, _ = build_workload(workload)
+    sub = O.QCir(n)
+    for g in qc_a.topological_order()[:n_gates]:
+        sub.append(g.op, g.qubits)
+    t0 = time.perf_counter()
+    t = O.to_tensor_literal(sub)
+    m = O.interleaved_to_matrix(t)
+    t_construct = time.perf_counter() - t0
+    ident = np.eye(2**n, dtype=np.complex128)
+    t0 = time.perf_counter()
+    oracle_c.equiv_reference_passes(ident, m)
+    t_equiv = time.perf_counter() - t0
+    gate_bytes = sum(_gate_fraction(g.op) * 32.0 * 4.0**n for g in sub.gates)
+    return {"n": n, "gates": len(sub.gates), "construct_s": t_construct, "equiv_s": t_equiv, "gate_bytes": gate_bytes,
+            "desc": desc}
+
+
+def cpu_baseline(workload: str, budget_s: float = 20.0):
+    n = WORKLOADS[workload][0]
+    # measured ballpark: ~0.18 s per gate at n=12, x4 per extra qubit
+    per_gate = 0.18 * 4.0 ** (n - 12)
+    if n > 13:
+        return {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "port",
+                "sample": f"not run: the tensordot scheme needs ~3 x 16 x 4^{n} B of host RAM and ~{per_gate:.0f} s per gate at n={n}"}
+    g = min(WORKLOADS[workload][2], max(4, int(budget_s / per_gate)))
+    s = cpu_reference_sample(workload, g)
+    return {"value": round(s["gate_bytes"] / s["construct_s"] / 1e9, 3), "unit": "GB/s", "cores": os.cpu_count(),
+            "kind": "port",
+            "sample": f"first {s['gates']} gates of the same n={s['n']} circuit through the oracle's literal per-gate "
+                      f"numpy.tensordot loop (OpenBLAS, all host threads): {s['construct_s']:.2f} s; "
+                      f"8-pass equivalence (single-thread C port): {s['equiv_s']:.2f} s",
+            "ms_per_gate": round(s["construct_s"] / s["gates"] * 1e3, 2), "equiv_s": round(s["equiv_s"], 3)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm (oracle port; the reference binary cannot be
+    built here: xtensor/xtensor-blas/OpenBLAS are not vendored) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, gen, g_total, seed, desc = WORKLOADS[args.workload]
+    if n > 13:
+        print(json.dumps({"impl": "reference", "unavailable": f"the CPU tensordot path needs ~3x16x4^{n} B RAM and minutes per gate at n={n}"}))
+        return
+    per_gate = 0.18 * 4.0 ** (n - 12)
+    g = min(g_total, max(4, int(8.0 / per_gate)))
+    for _ in range(max(args.warmup, 1) if args.warmup < 3 else 1):
+        cpu_reference_sample(args.workload, max(2, g // 8))
+    tot_s, tot_bytes, eq_s = 0.0, 0.0, 0.0
+    for _ in range(args.steps):
+        s = cpu_reference_sample(args.workload, g)
+        tot_s += s["construct_s"] + s["equiv_s"]
+        eq_s += s["equiv_s"]
+        tot_bytes += s["gate_bytes"]
+    value = tot_bytes / tot_s / 1e9
+    out = {
+        "impl": "reference",
+        "metric": "qcir2unitary_gate_apply_effective_GBps", "value": round(value, 3), "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(tot_s / args.steps * 1e3, 2),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "complex128 (f64)",
+        "data": "synthetic (same seeded circuit as the GPU arm)",
+        "config": {"workload": desc, "n_qubits": n,
+                   "step": f"bounded sample: first {g} gates of circuit A via per-gate numpy.tensordot (OpenBLAS) + 8-pass equivalence vs identity"},
+        "cpu_baseline": {"value": round(value, 3), "unit": "GB/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{g} of {g_total} gates per step; restatement of the reference algorithm, not the reference binary"},
+        "e2e": {"value": round(value, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cap", type=int, default=96, help="max ops per sweep")
+    ap.add_argument("--tile", type=int, default=9)
+    ap.add_argument("--reg", type=int, default=4)
+    ap.add_argument("--log2w", type=int, default=3)
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

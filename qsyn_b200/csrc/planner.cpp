@@ -445,6 +445,26 @@ void schedule(Plan& plan) {
 
 // ---- serialization ----------------------------------------------------------------------
 
+int handler_of(MicroOp const& u) {
+    bool const g = u.creg != 0;
+    switch (u.kind) {
+        case K_H: return (g ? H_HG : H_H) + u.j0;
+        case K_X: return (g ? H_XG : H_X) + u.j0;
+        case K_XC: return H_XC + u.j0 * 4 + u.j1;
+        case K_U1: return (g ? H_U1G : H_U1) + u.j0;
+        case K_AD: return (g ? H_ADG : H_AD) + u.j0;
+        case K_SWAP: {
+            int const ja = std::max(u.j0, u.j1), jb = std::min(u.j0, u.j1);
+            return (g ? H_SWAPG : H_SWAP) + ja * 4 + jb;
+        }
+        case K_U2: return H_U2;
+        case K_DSCAL: return H_DSCAL;
+        case K_DTABH: return H_DTABH + u.j0;
+        case K_DTABF: return H_DTABF;
+        default: return H_SAPPLY;
+    }
+}
+
 void serialize(Plan& plan) {
     PlanConfig const& cfg = plan.cfg;
     for (PlannedSweep const& sw : plan.sweeps) {
@@ -487,7 +507,7 @@ void serialize(Plan& plan) {
             for (MicroOp const& mo : st.uops) {
                 DevOp d;
                 std::memset(&d, 0, sizeof(d));
-                d.kind   = mo.kind;
+                d.handler = handler_of(mo);
                 d.j0     = mo.j0;
                 d.j1     = mo.j1;
                 d.creg   = mo.creg;

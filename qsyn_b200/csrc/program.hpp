@@ -22,8 +22,8 @@ constexpr int kMaxTileBits = 11;
 constexpr int kMaxRowBits  = 26;
 
 // CTA size limit of sweep_kernel<R>: 2^R complex128 live in registers per thread, so the
-// R = 4 instantiation is compiled for <= 512 threads (128 registers), the others for 1024.
-constexpr int max_threads_log2(int R) { return R >= 4 ? 9 : 10; }
+// R >= 3 instantiations are compiled for <= 512 threads (128 registers), the others for 1024.
+constexpr int max_threads_log2(int R) { return R >= 3 ? 9 : 10; }
 
 // semantic kinds of lowered gates (host side, planner + dumps)
 enum OpKind : int32_t {
@@ -54,11 +54,34 @@ enum MicroKind : int32_t {
     K_SAPPLY = 10,  // e[i] *= s for all i ; s = 1   (emitted once at the end of a stage that used K_DSCAL)
 };
 
+// Flat handler ids: the kernel dispatches every micro-op with ONE jump-table branch.  A handler
+// is a (kind, register bit(s), "has in-register controls") combination, numbered for the
+// maximum R = 4; combinations that do not exist for a smaller R are never emitted.
+enum Handler : int32_t {
+    H_H      = 0,   // +J          uncontrolled inside the registers (no per-element tests)
+    H_HG     = 4,   // +J          generic: runtime creg
+    H_X      = 8,   // +J
+    H_XG     = 12,  // +J
+    H_XC     = 16,  // +J*4+JC
+    H_U1     = 32,  // +J
+    H_U1G    = 36,  // +J
+    H_AD     = 40,  // +J
+    H_ADG    = 44,  // +J
+    H_SWAP   = 48,  // +JA*4+JB  (JA > JB)
+    H_SWAPG  = 64,  // +JA*4+JB
+    H_U2     = 80,
+    H_DSCAL  = 81,
+    H_DTABH  = 82,  // +J
+    H_DTABF  = 86,
+    H_SAPPLY = 87,
+    H_COUNT  = 88,
+};
+
 // Thread-level predicate of every micro-op: (row & cother) == cother && (row & czero) == 0, where
 // `row` is the thread's global row index with the register bits cleared.
 struct alignas(16) DevOp {
-    int32_t  kind;
-    int32_t  j0, j1;   // register-bit indices (or -1)
+    int32_t  handler;  // Handler id (kind + register bits folded in)
+    int32_t  j0, j1;   // register-bit indices (or -1); informative, the handler already encodes them
     uint32_t creg;     // required-one mask over the register index (bits 0..r-1), non-diagonal kinds only
     uint32_t cother;   // required-one mask over GLOBAL row bits that are not register bits this stage
     uint32_t czero;    // required-zero mask over GLOBAL row bits that are not register bits this stage
