@@ -101,7 +101,10 @@ typedef struct qsx_plan_options {
     int32_t max_ops_per_sweep; /* cap on ops per sweep (default 48)                                             */
     int32_t lookahead;     /* scheduler scan window in gates (default 4096)                                     */
     int32_t dense_block;   /* 0 (default): never; k>=3: fold runs of gates on <=k qubits into dense k-blocks    */
-    int32_t reserved[8];
+    int32_t no_perm_folding; /* 0 (default): fold X / CX / SWAP into the addressing of stage boundaries when they can
+                                be hoisted there, else swap registers; 1: always swap registers; 2: never swap
+                                registers (an op that cannot be hoisted waits for the next boundary)            */
+    int32_t reserved[7];
 } qsx_plan_options;
 
 typedef struct qsx_plan_stats {
@@ -110,6 +113,7 @@ typedef struct qsx_plan_stats {
     uint64_t n_sweeps;     /* kernel launches per run                             */
     uint64_t n_stages;     /* register-blocking stages over all sweeps            */
     uint64_t n_micro_ops;  /* register-level micro-ops after merging diagonal ops */
+    uint64_t n_folded_perms; /* X / CX / SWAP ops executed purely as address permutations */
     uint64_t n_dense_blocks;
     double   alg_bytes_per_run;   /* sum over sweeps of 32 B x elements touched (this shard geometry) */
     double   gate_bytes_per_run;  /* sum over GATES of f*32*rows*ncols, f per SURVEY 8(d)              */

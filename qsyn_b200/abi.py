@@ -53,7 +53,7 @@ class GateStruct(C.Structure):
 class PlanOptions(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("fuse", C.c_int32), ("snap_tol", C.c_double), ("reg_qubits", C.c_int32),
                 ("tile_qubits", C.c_int32), ("log2_tile_cols", C.c_int32), ("max_ops_per_sweep", C.c_int32),
-                ("lookahead", C.c_int32), ("dense_block", C.c_int32), ("reserved", C.c_int32 * 8)]
+                ("lookahead", C.c_int32), ("dense_block", C.c_int32), ("no_perm_folding", C.c_int32), ("reserved", C.c_int32 * 7)]
 
     def __init__(self, fuse: int = 1, **kw):
         super().__init__()
@@ -67,7 +67,7 @@ class PlanOptions(C.Structure):
 
 class PlanStats(C.Structure):
     _fields_ = [("n_gates", C.c_uint64), ("n_ops", C.c_uint64), ("n_sweeps", C.c_uint64), ("n_stages", C.c_uint64),
-                ("n_micro_ops", C.c_uint64), ("n_dense_blocks", C.c_uint64), ("alg_bytes_per_run", C.c_double), ("gate_bytes_per_run", C.c_double),
+                ("n_micro_ops", C.c_uint64), ("n_folded_perms", C.c_uint64), ("n_dense_blocks", C.c_uint64), ("alg_bytes_per_run", C.c_double), ("gate_bytes_per_run", C.c_double),
                 ("plan_host_ms", C.c_double)]
 
 

@@ -85,9 +85,11 @@ __device__ __forceinline__ void op_h(double2 (&e)[1 << R], double s, uint32_t cr
         if constexpr (!ALL) {
             if ((i & creg) != creg) continue;
         }
+        // 3 FP64 instructions per component (DMUL + 2 DFMA) instead of 4 (2 DADD + 2 DMUL)
         double2 const a = e[i], b = e[i | (1 << J)];
-        e[i]            = make_double2(s * (a.x + b.x), s * (a.y + b.y));
-        e[i | (1 << J)] = make_double2(s * (a.x - b.x), s * (a.y - b.y));
+        double const tx = s * b.x, ty = s * b.y;
+        e[i]            = make_double2(fma(s, a.x, tx), fma(s, a.y, ty));
+        e[i | (1 << J)] = make_double2(fma(s, a.x, -tx), fma(s, a.y, -ty));
     }
 }
 
@@ -221,6 +223,22 @@ __device__ __forceinline__ void run_handler(double2 (&e)[1 << R], double2& scal,
 #pragma unroll
         for (int i = 0; i < (1 << R); ++i) e[i] = cmul(e[i], sv);
         scal = make_double2(1.0, 0.0);
+    } else if constexpr (H == H_SCALN) {
+        // every per-thread scalar of the stage, without a dispatch per gate
+        const uint4* const ent = reinterpret_cast<const uint4*>(pool + pool_off);
+        int const count        = op->j0;
+        double2 sv             = scal;
+        for (int k = 0; k < count; ++k) {
+            uint4 const w    = ent[3 * k];  // cother, czero, sel, pad
+            bool const pass  = (grow & w.x) == w.x && (grow & w.y) == 0u;
+            bool const hi    = (int)w.z >= 0 && ((grow >> (w.z & 31u)) & 1u);
+            double2 const d  = *reinterpret_cast<const double2*>(ent + 3 * k + (hi ? 2 : 1));
+            double2 const nv = cmul(sv, d);
+            sv               = pass ? nv : sv;
+        }
+#pragma unroll
+        for (int i = 0; i < (1 << R); ++i) e[i] = cmul(e[i], sv);
+        scal = make_double2(1.0, 0.0);
     }
 }
 
@@ -248,6 +266,7 @@ __device__ __forceinline__ void apply_op(double2 (&e)[1 << R], double2& scal, co
         QSX_CASE8(64)
         QSX_CASE8(72)
         QSX_CASE8(80)
+        QSX_CASE(88)
         default: break;
     }
 }
@@ -257,9 +276,32 @@ __device__ __forceinline__ void apply_op(double2 (&e)[1 << R], double2& scal, co
 // ---------------------------------------------------------------------------------------
 // the sweep interpreter
 // ---------------------------------------------------------------------------------------
+// Address permutation of a stage boundary (DevPerm list), evaluated on tile-local row indices.
+// rows[0] is the thread's base row (register bits clear), rows[1+j] = base ^ (register bit j).
+// FORWARD applies the steps in list order (store side), !FORWARD in reverse (load side: every
+// step is an involution, so the reversed list is the inverse permutation).
+template <int R, bool FORWARD>
+__device__ __forceinline__ void permute_rows(uint32_t (&rows)[R + 1], const DevPerm* __restrict__ perms, int begin, int end,
+                                             uint32_t row_outer) {
+    for (int k = 0; k < end - begin; ++k) {
+        int const idx = FORWARD ? begin + k : end - 1 - k;
+        uint4 const p = *reinterpret_cast<const uint4*>(perms + idx);  // cml, cmo, tml, pad
+        if ((row_outer & p.y) != p.y) continue;                        // uniform per CTA
+#pragma unroll
+        for (int v = 0; v <= R; ++v) rows[v] ^= ((rows[v] & p.x) == p.x) ? p.z : 0u;
+    }
+}
+
+// tile-local row bits -> their global row-bit positions
+__device__ __forceinline__ uint32_t deposit_tile_bits(uint32_t x, const int32_t* __restrict__ sp, int m) {
+    uint32_t r = 0;
+    for (int l = 0; l < m; ++l) r |= ((x >> l) & 1u) << sp[l];
+    return r;
+}
+
 template <int R>
 __global__ void __launch_bounds__(1 << max_threads_log2(R), 1)
-    sweep_kernel(double2* __restrict__ u, const unsigned char* __restrict__ gprog, uint32_t prog_bytes, uint64_t ncols,
+    sweep_kernel(double2* __restrict__ u, const unsigned char* __restrict__ gprog, uint32_t prog_bytes, int log2_ncols,
                  int log2_ncb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // the sweep program (a few KB, read by every thread for every op) is staged in shared
@@ -277,9 +319,11 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), 1)
     const DevStage* const stages = reinterpret_cast<const DevStage*>(prog + sizeof(DevSweep));
     int const n_stages           = sw->n_stages;
     const DevOp* const ops       = reinterpret_cast<const DevOp*>(stages + n_stages);
-    const double* const pool     = reinterpret_cast<const double*>(ops + sw->n_ops);
+    const DevPerm* const perms   = reinterpret_cast<const DevPerm*>(ops + sw->n_ops);
+    const double* const pool     = reinterpret_cast<const double*>(perms + sw->n_perms);
 
     int const log2w      = sw->log2w;
+    int const m          = sw->m;
     uint32_t const tid   = threadIdx.x;
     uint32_t const cw    = tid & ((1u << log2w) - 1u);
     uint32_t const trow  = tid >> log2w;
@@ -315,17 +359,30 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), 1)
         for (int j = 0; j < R; ++j) rl[j] = st->rl[j];
 
         if (s == 0) {
-            size_t gs[R];
+            // global load; X-type ops scheduled before the first register op are folded into the addresses
+            uint32_t gb = grow, gc[R];
+            int const pb = st->pre_begin, pe = st->pre_end;
+            if (pb == pe) {
 #pragma unroll
-            for (int j = 0; j < R; ++j) gs[j] = ((size_t)1 << sw->sp[rl[j]]) * ncols;
-            const double2* const gp = u + (size_t)grow * ncols + col;
+                for (int j = 0; j < R; ++j) gc[j] = 1u << sw->sp[rl[j]];
+            } else {
+                uint32_t rows[R + 1];
+                rows[0] = lbase;
+#pragma unroll
+                for (int j = 0; j < R; ++j) rows[1 + j] = lbase | (1u << rl[j]);
+                permute_rows<R, false>(rows, perms, pb, pe, row_outer);
+                gb = row_outer | deposit_tile_bits(rows[0], sw->sp, m);
+#pragma unroll
+                for (int j = 0; j < R; ++j) gc[j] = deposit_tile_bits(rows[1 + j] ^ rows[0], sw->sp, m);
+            }
+            const double2* const gp = u + col;
 #pragma unroll
             for (int i = 0; i < (1 << R); ++i) {
-                size_t off = 0;
+                uint32_t r = gb;
 #pragma unroll
                 for (int j = 0; j < R; ++j)
-                    if ((i >> j) & 1) off += gs[j];
-                e[i] = __ldcg(gp + off);
+                    if ((i >> j) & 1) r ^= gc[j];
+                e[i] = __ldcg(gp + ((size_t)r << log2_ncols));
             }
         } else {
             uint32_t ss[R];
@@ -346,47 +403,55 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), 1)
         {
             int const ob = st->op_begin, oe = st->op_end;
             double2 scal = make_double2(1.0, 0.0);  // per-thread product of the stage's K_DSCAL ops
-            // software-pipelined fetch: the next micro-op's header is in flight while this one runs
-            int4 hdr = make_int4(H_COUNT, 0, 0, 0), hdr2 = make_int4(0, 0, 0, 0);
-            if (ob < oe) {
-                hdr  = *reinterpret_cast<const int4*>(ops + ob);
-                hdr2 = *(reinterpret_cast<const int4*>(ops + ob) + 1);
-            }
+            // (prefetching the next header was measured: the 8 extra live registers spill, -12 %)
             for (int o = ob; o < oe; ++o) {
-                int4 const h = hdr, h2 = hdr2;
-                if (o + 1 < oe) {
-                    hdr  = *reinterpret_cast<const int4*>(ops + o + 1);
-                    hdr2 = *(reinterpret_cast<const int4*>(ops + o + 1) + 1);
-                }
-                apply_op<R>(e, scal, ops + o, h, h2, grow, pool);
+                int4 const hdr  = *reinterpret_cast<const int4*>(ops + o);
+                int4 const hdr2 = *(reinterpret_cast<const int4*>(ops + o) + 1);
+                apply_op<R>(e, scal, ops + o, hdr, hdr2, grow, pool);
             }
         }
 
-        if (s == n_stages - 1) {
-            size_t gs[R];
+        // store; X-type ops scheduled after this stage's register ops are folded into the addresses
+        uint32_t rows[R + 1];
+        rows[0] = lbase;
 #pragma unroll
-            for (int j = 0; j < R; ++j) gs[j] = ((size_t)1 << sw->sp[rl[j]]) * ncols;
-            double2* const gp = u + (size_t)grow * ncols + col;
+        for (int j = 0; j < R; ++j) rows[1 + j] = lbase | (1u << rl[j]);
+        int const qb = st->post_begin, qe = st->post_end;
+        if (qb != qe) permute_rows<R, true>(rows, perms, qb, qe, row_outer);
+
+        if (s == n_stages - 1) {
+            uint32_t gb, gc[R];
+            if (qb == qe) {
+                gb = grow;
+#pragma unroll
+                for (int j = 0; j < R; ++j) gc[j] = 1u << sw->sp[rl[j]];
+            } else {
+                gb = row_outer | deposit_tile_bits(rows[0], sw->sp, m);
+#pragma unroll
+                for (int j = 0; j < R; ++j) gc[j] = deposit_tile_bits(rows[1 + j] ^ rows[0], sw->sp, m);
+            }
+            double2* const gp = u + col;
 #pragma unroll
             for (int i = 0; i < (1 << R); ++i) {
-                size_t off = 0;
+                uint32_t r = gb;
 #pragma unroll
                 for (int j = 0; j < R; ++j)
-                    if ((i >> j) & 1) off += gs[j];
-                __stcg(gp + off, e[i]);
+                    if ((i >> j) & 1) r ^= gc[j];
+                __stcg(gp + ((size_t)r << log2_ncols), e[i]);
             }
         } else {
-            uint32_t ss[R];
+            uint32_t const sb = rows[0];
+            uint32_t sc[R];
 #pragma unroll
-            for (int j = 0; j < R; ++j) ss[j] = (1u << rl[j]) << log2w;
-            double2* const sp_ = tile + ((lbase << log2w) + cw);
+            for (int j = 0; j < R; ++j) sc[j] = rows[1 + j] ^ rows[0];
+            double2* const sp_ = tile + cw;
 #pragma unroll
             for (int i = 0; i < (1 << R); ++i) {
-                uint32_t off = 0;
+                uint32_t r = sb;
 #pragma unroll
                 for (int j = 0; j < R; ++j)
-                    if ((i >> j) & 1) off += ss[j];
-                sp_[off] = e[i];
+                    if ((i >> j) & 1) r ^= sc[j];
+                sp_[r << log2w] = e[i];
             }
             __syncthreads();
         }
@@ -416,7 +481,7 @@ cudaError_t launch_sweep_r(double2* u, int n, uint64_t ncols, const DevSweep& hs
         if (rc != cudaSuccess) return rc;
         attr_set[dev] = true;
     }
-    sweep_kernel<R><<<(unsigned)nblocks, threads, smem, s>>>(u, prog, (uint32_t)prog_bytes, ncols, log2_ncb);
+    sweep_kernel<R><<<(unsigned)nblocks, threads, smem, s>>>(u, prog, (uint32_t)prog_bytes, log2_ncols, log2_ncb);
     return cudaGetLastError();
 }
 

@@ -16,6 +16,7 @@
 #include "planner.hpp"
 
 #include <algorithm>
+#include <cassert>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -169,29 +170,87 @@ struct Picker {
     }
 };
 
+inline bool is_perm_op(LoweredOp const& op) { return op.kind == OP_X || op.kind == OP_SWAP; }
+
+// X / CX / SWAP are permutations of rows.  At a stage boundary every element is written to
+// (read from) an address the thread computes anyway, so such an op can be executed by
+// permuting ADDRESSES instead of data, at no cost per element.  The kernel evaluates the
+// boundary's permutation only at the thread's base row and at base ^ (register bit j) and
+// XOR-combines the differences; that is exact iff the composed permutation is affine in the
+// register bits.  `taint` = row bits whose value, after the steps accepted so far, depends on
+// a register bit.  A step  t ^= AND(controls)  keeps every bit affine iff at most one of its
+// controls is tainted (the others are per-thread constants); t then becomes tainted too.
+bool boundary_accept(LoweredOp const& op, uint32_t& taint) {
+    uint32_t tt = taint;
+    auto step = [&](uint32_t ctrl, int t) {
+        int const k = popc(ctrl & tt);
+        if (k > 1) return false;
+        if (k == 1) tt |= 1u << t;
+        return true;
+    };
+    bool ok;
+    if (op.kind == OP_SWAP) {  // CX(a,b) CX(b,a) CX(a,b), each with the explicit controls
+        ok = step(op.req | (1u << op.t0), op.t1) && step(op.req | (1u << op.t1), op.t0) &&
+             step(op.req | (1u << op.t0), op.t1);
+    } else {
+        ok = step(op.req, op.t0);
+    }
+    if (ok) taint = tt;
+    return ok;
+}
+
 void build_stages(Plan& plan, std::vector<int> chosen, PlannedSweep& sw) {
     int const R = plan.cfg.R;
-    uint32_t tile_mask = 0;
-    for (int b : sw.tile_bits) tile_mask |= 1u << b;
     while (!chosen.empty()) {
         PlannedStage st;
-        uint32_t rm = 0;
+        bool const first = sw.stages.empty();
+        // load-side list of the first stage: its register bits are not chosen yet (and the list is
+        // executed in reverse), so treat every bit as tainted: only steps with <= 1 control fold
+        uint32_t pre_taint = ~0u;
+        uint32_t rm = 0, chosenT = 0, chosenA = 0;
         int u2_t0 = -1, u2_t1 = -1;
         Picker pk;
         std::vector<int> rest;
         for (int idx : chosen) {
             LoweredOp const& op = plan.ops[idx];
-            bool ok = pk.passes(op) && popc(rm | op.tmask()) <= R;
+            if (!pk.passes(op)) {
+                pk.block(op);
+                rest.push_back(idx);
+                continue;
+            }
+            uint32_t const T = op.tmask(), A = T | op.dmask();
+            if (plan.cfg.fold_perms && is_perm_op(op)) {
+                // commutes with everything already placed in this stage -> hoist to the boundary before it
+                bool const commutes = (T & chosenA) == 0 && (A & chosenT) == 0;
+                if (commutes && boundary_accept(op, first ? pre_taint : sw.stages.back().post_taint)) {
+                    (first ? st.pre : sw.stages.back().post).push_back(idx);
+                    ++plan.stats.n_folded_perms;
+                    continue;
+                }
+                // not hoistable: either swap registers inside this stage, or (defer_perms) wait for
+                // the next stage boundary, where it is first in line and always folds
+                uint32_t probe = ~0u;
+                if (plan.cfg.defer_perms && !st.ops.empty() && boundary_accept(op, probe)) {
+                    pk.block(op);
+                    rest.push_back(idx);
+                    continue;
+                }
+            }
+            bool ok = popc(rm | T) <= R;
             if (ok && op.kind == OP_U2 && u2_t0 >= 0 && (u2_t0 != op.t0 || u2_t1 != op.t1)) ok = false;
             if (ok) {
                 if (op.kind == OP_U2) u2_t0 = op.t0, u2_t1 = op.t1;
-                rm |= op.tmask();
+                rm |= T;
+                chosenT |= T;
+                chosenA |= A;
                 st.ops.push_back(idx);
             } else {
                 pk.block(op);
                 rest.push_back(idx);
             }
         }
+        chosen.swap(rest);
+        if (st.ops.empty() && st.pre.empty()) continue;  // everything went to the previous boundary
         // register-bit assignment: a U2 pair must sit on register bits (1,0)
         std::vector<int> rb;
         if (u2_t0 >= 0) {
@@ -205,9 +264,10 @@ void build_stages(Plan& plan, std::vector<int> chosen, PlannedSweep& sw) {
             if ((int)rb.size() >= R) break;
             if (std::find(rb.begin(), rb.end(), b) == rb.end()) rb.push_back(b);
         }
-        st.reg_bits = rb;
+        st.reg_bits   = rb;
+        st.post_taint = 0;
+        for (int b : rb) st.post_taint |= 1u << b;
         sw.stages.push_back(std::move(st));
-        chosen.swap(rest);
     }
 }
 
@@ -251,7 +311,9 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
     };
 
     std::vector<int> pending;  // positions in st.ops of held-back diagonal ops
-    bool used_scalar = false;
+    // per-thread scalars commute with every register op of the stage: they are all collected
+    // into ONE micro-op at the end of the stage
+    std::vector<MicroOp> scalars;
 
     struct Group {
         uint32_t cother, czero;
@@ -288,8 +350,7 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
                     Cx const w = phase_of(op);
                     u.c[0] = w.re, u.c[1] = w.im;
                 }
-                st.uops.push_back(std::move(u));
-                used_scalar = true;
+                scalars.push_back(std::move(u));
                 continue;
             }
             if (!is_diag2) {
@@ -377,9 +438,27 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
         st.uops.push_back(std::move(u));
     }
     flush(~0u);
-    if (used_scalar) {
+    if (!scalars.empty()) {
         MicroOp u;
-        u.kind = K_SAPPLY;
+        u.kind = K_SCALN;
+        u.j0   = (int)scalars.size();
+        for (MicroOp const& e : scalars) {
+            // entry = 2 doubles of packed ints {cother, czero, sel, 0} + d0 + d1
+            uint32_t w[4] = {e.cother, e.czero, (uint32_t)e.sel, 0u};
+            double packed[2];
+            std::memcpy(packed, w, sizeof(packed));
+            u.table.push_back(packed[0]);
+            u.table.push_back(packed[1]);
+            u.table.push_back(e.c[0]);
+            u.table.push_back(e.c[1]);
+            if (e.sel >= 0) {
+                u.table.push_back(e.c[2]);
+                u.table.push_back(e.c[3]);
+            } else {
+                u.table.push_back(e.c[0]);
+                u.table.push_back(e.c[1]);
+            }
+        }
         st.uops.push_back(std::move(u));
     }
 }
@@ -461,6 +540,7 @@ int handler_of(MicroOp const& u) {
         case K_DSCAL: return H_DSCAL;
         case K_DTABH: return H_DTABH + u.j0;
         case K_DTABF: return H_DTABF;
+        case K_SCALN: return H_SCALN;
         default: return H_SAPPLY;
     }
 }
@@ -489,7 +569,30 @@ void serialize(Plan& plan) {
         hs.n_outer = no;
         std::vector<DevStage> stages;
         std::vector<DevOp> ops;
+        std::vector<DevPerm> perms;
         std::vector<double> pool;
+        auto add_perm_steps = [&](int idx) {
+            LoweredOp const& lo = plan.ops[idx];
+            auto step = [&](uint32_t ctrl_global, int target_global) {
+                DevPerm d{0, 0, 0, 0};
+                for (int b = 0; b < cfg.n; ++b)
+                    if ((ctrl_global >> b) & 1u) {
+                        if (local_of[b] >= 0)
+                            d.cml |= 1u << local_of[b];
+                        else
+                            d.cmo |= 1u << b;
+                    }
+                d.tml = 1u << local_of[target_global];
+                perms.push_back(d);
+            };
+            if (lo.kind == OP_SWAP) {
+                step(lo.req | (1u << lo.t0), lo.t1);
+                step(lo.req | (1u << lo.t1), lo.t0);
+                step(lo.req | (1u << lo.t0), lo.t1);
+            } else {
+                step(lo.req, lo.t0);
+            }
+        };
         for (PlannedStage const& st : sw.stages) {
             DevStage ds;
             std::memset(&ds, 0, sizeof(ds));
@@ -522,14 +625,21 @@ void serialize(Plan& plan) {
                 }
                 ops.push_back(d);
             }
-            ds.op_end = (int)ops.size();
+            ds.op_end   = (int)ops.size();
+            ds.pre_begin = (int)perms.size();
+            for (int idx : st.pre) add_perm_steps(idx);
+            ds.pre_end    = (int)perms.size();
+            ds.post_begin = (int)perms.size();
+            for (int idx : st.post) add_perm_steps(idx);
+            ds.post_end = (int)perms.size();
             stages.push_back(ds);
         }
         hs.n_ops        = (int)ops.size();
+        hs.n_perms      = (int)perms.size();
         hs.pool_doubles = (int)pool.size();
         size_t const off = (plan.blob.size() + 255) / 256 * 256;
         size_t const sz  = sizeof(DevSweep) + stages.size() * sizeof(DevStage) + ops.size() * sizeof(DevOp) +
-                          pool.size() * sizeof(double);
+                          perms.size() * sizeof(DevPerm) + pool.size() * sizeof(double);
         plan.blob.resize(off + sz, 0);
         unsigned char* p = plan.blob.data() + off;
         std::memcpy(p, &hs, sizeof(hs));
@@ -538,6 +648,8 @@ void serialize(Plan& plan) {
         p += stages.size() * sizeof(DevStage);
         if (!ops.empty()) std::memcpy(p, ops.data(), ops.size() * sizeof(DevOp));
         p += ops.size() * sizeof(DevOp);
+        if (!perms.empty()) std::memcpy(p, perms.data(), perms.size() * sizeof(DevPerm));
+        p += perms.size() * sizeof(DevPerm);
         if (!pool.empty()) std::memcpy(p, pool.data(), pool.size() * sizeof(double));
         plan.sweep_offset.push_back(off);
         plan.sweep_size.push_back(sz);
@@ -578,6 +690,8 @@ int build_plan(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gat
     cfg.n           = n_qubits;
     cfg.ncols       = ncols;
     cfg.fuse        = o.fuse != 0;
+    cfg.fold_perms  = o.no_perm_folding != 1;
+    cfg.defer_perms = o.no_perm_folding == 2;
     cfg.snap_tol    = (opt != nullptr && o.snap_tol == 0.0) ? 1e-15 : o.snap_tol;
     cfg.R           = std::min(n_qubits, o.reg_qubits > 0 ? std::min((int)o.reg_qubits, kMaxRegBits) : 4);
     cfg.log2w       = std::min(lc, o.log2_tile_cols > 0 ? std::min((int)o.log2_tile_cols, 5) : 3);
@@ -628,7 +742,18 @@ std::string dump_plan_json(const Plan& plan) {
             PlannedStage const& st = sw.stages[t];
             os << (t ? "," : "") << "{\"reg_bits\":[";
             for (size_t i = 0; i < st.reg_bits.size(); ++i) os << (i ? "," : "") << st.reg_bits[i];
-            os << "],\"ops\":[";
+            os << "]";
+            for (int which = 0; which < 2; ++which) {
+                std::vector<int> const& lst = which == 0 ? st.pre : st.post;
+                os << ",\"" << (which == 0 ? "pre" : "post") << "\":[";
+                for (size_t i = 0; i < lst.size(); ++i) {
+                    LoweredOp const& op = plan.ops[lst[i]];
+                    os << (i ? "," : "") << "{\"kind\":\"" << kNames[op.kind] << "\",\"t0\":" << op.t0 << ",\"t1\":" << op.t1
+                       << ",\"dbit\":-1,\"req\":" << op.req << ",\"gate\":" << op.src_gate << ",\"c\":[0,0,0,0,0,0,0,0],\"mat\":[]}";
+                }
+                os << "]";
+            }
+            os << ",\"ops\":[";
             for (size_t i = 0; i < st.ops.size(); ++i) {
                 LoweredOp const& op = plan.ops[st.ops[i]];
                 os << (i ? "," : "") << "{\"kind\":\"" << kNames[op.kind] << "\",\"t0\":" << op.t0 << ",\"t1\":" << op.t1
@@ -638,7 +763,7 @@ std::string dump_plan_json(const Plan& plan) {
                 for (size_t k = 0; k < op.mat.size(); ++k) os << (k ? "," : "") << op.mat[k];
                 os << "]}";
             }
-            static char const* const kMicro[] = {"U1", "H", "X", "AD", "XC", "SWAP", "U2", "DSCAL", "DTABH", "DTABF", "SAPPLY"};
+            static char const* const kMicro[] = {"U1", "H", "X", "AD", "XC", "SWAP", "U2", "DSCAL", "DTABH", "DTABF", "SAPPLY", "SCALN"};
             os << "],\"uops\":[";
             for (size_t i = 0; i < st.uops.size(); ++i) {
                 MicroOp const& u = st.uops[i];
@@ -647,7 +772,17 @@ std::string dump_plan_json(const Plan& plan) {
                    << ",\"sel\":" << u.sel << ",\"src\":" << u.src << ",\"c\":[";
                 for (int k = 0; k < 8; ++k) os << (k ? "," : "") << u.c[k];
                 os << "],\"table\":[";
-                for (size_t k = 0; k < u.table.size(); ++k) os << (k ? "," : "") << u.table[k];
+                if (u.kind != K_SCALN)
+                    for (size_t k = 0; k < u.table.size(); ++k) os << (k ? "," : "") << u.table[k];
+                os << "],\"scalars\":[";
+                if (u.kind == K_SCALN)
+                    for (int k = 0; k < u.j0; ++k) {
+                        uint32_t w[4];
+                        std::memcpy(w, &u.table[(size_t)6 * k], sizeof(w));
+                        os << (k ? "," : "") << "{\"cother\":" << w[0] << ",\"czero\":" << w[1] << ",\"sel\":" << (int)w[2]
+                           << ",\"d\":[" << u.table[6 * k + 2] << "," << u.table[6 * k + 3] << "," << u.table[6 * k + 4] << ","
+                           << u.table[6 * k + 5] << "]}";
+                    }
                 os << "]}";
             }
             os << "]}";

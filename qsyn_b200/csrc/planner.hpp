@@ -40,7 +40,10 @@ struct MicroOp {
 
 struct PlannedStage {
     std::vector<int> reg_bits;  // global row bit of register bit j (size R)
-    std::vector<int> ops;       // indices into Plan::ops (semantic order)
+    std::vector<int> pre;       // X-type ops folded into this stage's load addressing (first stage only)
+    std::vector<int> ops;       // indices into Plan::ops executed in registers (semantic order)
+    std::vector<int> post;      // X-type ops folded into this stage's store addressing
+    uint32_t post_taint = 0;    // row bits that depend on a register bit after the post list so far
     std::vector<MicroOp> uops;  // what the kernel runs for this stage
 };
 
@@ -60,6 +63,8 @@ struct PlanConfig {
     int  max_ops = 48;
     int  lookahead = 4096;
     bool fuse = true;
+    bool fold_perms = true;  // fold X / CX / SWAP into the addressing of stage boundaries
+    bool defer_perms = false;  // never swap registers: an X-type op that cannot be hoisted ends the stage
     double snap_tol = 1e-15;
 };
 

@@ -51,7 +51,10 @@ enum MicroKind : int32_t {
     K_DSCAL  = 7,   // per-thread scalar: s *= (sel >= 0 && row bit sel) ? d1 : d0    c = d0, d1
     K_DTABH  = 8,   // e[i] *= tab[i without bit j0] for the 8 (2^(R-1)) elements with bit j0 set; table at pool
     K_DTABF  = 9,   // e[i] *= tab[i] for all 2^R elements; table at pool
-    K_SAPPLY = 10,  // e[i] *= s for all i ; s = 1   (emitted once at the end of a stage that used K_DSCAL)
+    K_SAPPLY = 10,  // e[i] *= s for all i ; s = 1
+    K_SCALN  = 11,  // all per-thread scalars of a stage in one micro-op: for k < j0 entries at pool
+                    // {cother, czero, sel, pad, d0.re, d0.im, d1.re, d1.im} (48 B each):
+                    //   s *= pass ? (sel >= 0 && row bit sel ? d1 : d0) : 1 ; then e[i] *= s
 };
 
 // Flat handler ids: the kernel dispatches every micro-op with ONE jump-table branch.  A handler
@@ -74,7 +77,8 @@ enum Handler : int32_t {
     H_DTABH  = 82,  // +J
     H_DTABF  = 86,
     H_SAPPLY = 87,
-    H_COUNT  = 88,
+    H_SCALN  = 88,
+    H_COUNT  = 89,
 };
 
 // Thread-level predicate of every micro-op: (row & cother) == cother && (row & czero) == 0, where
@@ -91,6 +95,17 @@ struct alignas(16) DevOp {
 };
 static_assert(sizeof(DevOp) == 96, "DevOp layout");
 
+// A permutation step folded into the addressing of a stage boundary: within the tile,
+// row ^= tml  wherever (row & cml) == cml and the CTA's outer row bits contain cmo.
+// X / CX / CCX.. are one step; SWAP is three.  Executed on ADDRESSES, never on data: the
+// element a thread holds is simply stored to (loaded from) the permuted row.
+struct alignas(16) DevPerm {
+    uint32_t cml;  // required-one mask, tile-local bit positions
+    uint32_t cmo;  // required-one mask, global positions of row bits outside the tile
+    uint32_t tml;  // flipped bit, tile-local position (exactly one bit)
+    uint32_t pad;
+};
+
 struct alignas(16) DevStage {
     int32_t op_begin, op_end;     // [begin,end) into the sweep's micro-op array
     int32_t r;                    // register bits used (== kernel template R)
@@ -98,6 +113,8 @@ struct alignas(16) DevStage {
     int32_t rl[kMaxRegBits];      // tile-local bit position of register bit j
     int32_t tl[kMaxTileBits];     // tile-local bit positions of the thread-row bits, ascending
     int32_t pad;
+    int32_t pre_begin, pre_end;   // permutation steps applied at this stage's LOAD (stage 0 only: global load)
+    int32_t post_begin, post_end; // permutation steps applied at this stage's STORE
 };
 static_assert(sizeof(DevStage) % 16 == 0, "DevStage layout");
 
@@ -109,11 +126,12 @@ struct alignas(16) DevSweep {
     uint32_t fixed_one;           // outer row bits forced to 1 (tile skipping for all-controlled sweeps)
     int32_t  n_ops;
     int32_t  pool_doubles;
-    int32_t  pad;
+    int32_t  n_perms;
     int32_t  sp[kMaxTileBits];    // global row-bit position of tile-local bit l, ascending
     int32_t  outer[kMaxRowBits];  // global positions of the enumerated outer bits, ascending
     int32_t  pad2[3];
-    // followed in memory by: DevStage stages[n_stages]; DevOp ops[n_ops]; double pool[pool_doubles]
+    // followed in memory by: DevStage stages[n_stages]; DevOp ops[n_ops]; DevPerm perms[n_perms];
+    // double pool[pool_doubles]
 };
 static_assert(sizeof(DevSweep) % 16 == 0, "DevSweep layout");
 

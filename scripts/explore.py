@@ -35,13 +35,15 @@ def main():
     qc = O.qcir_from_qasm_text(O.random_clifford_t_qasm(n, g, 20261019))
     gs = O.gate_stream(qc)
     print("n", n, "gates", g, flush=True)
-    for fuse, R, tile, w, cap in configs:
-        opt = Q.PlanOptions(fuse=fuse, reg_qubits=R, tile_qubits=tile, log2_tile_cols=w, max_ops_per_sweep=cap)
+    for cfg in configs:
+        fuse, R, tile, w, cap = cfg[:5]
+        pol = cfg[5] if len(cfg) > 5 else 0
+        opt = Q.PlanOptions(fuse=fuse, reg_qubits=R, tile_qubits=tile, log2_tile_cols=w, max_ops_per_sweep=cap, no_perm_folding=pol)
         try:
             r = time_plan(n, gs, opt)
         except Exception as e:  # noqa
             r = {"error": str(e)}
-        r.update(fuse=fuse, R=R, tile=tile, log2w=w, cap=cap)
+        r.update(fuse=fuse, R=R, tile=tile, log2w=w, cap=cap, pol=pol)
         print(json.dumps(r), flush=True)
     qft = O.gate_stream(O.qcir_from_qasm_text(O.qft_qasm(n)))
     print("qft", json.dumps(time_plan(n, qft, Q.PlanOptions(max_ops_per_sweep=128))), flush=True)

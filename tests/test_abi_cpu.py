@@ -65,13 +65,16 @@ def _rand_circuit(n, g, seed, extra=True):
     return qc
 
 
-@pytest.mark.parametrize("n,g,seed", [(1, 12, 1), (2, 30, 2), (3, 40, 3), (5, 120, 4), (6, 200, 5), (7, 150, 6)])
+@pytest.mark.parametrize("n,g,seed", [(1, 12, 1), (2, 30, 2), (3, 40, 3), (5, 120, 4), (6, 200, 5), (7, 150, 6), (9, 300, 16)])
 @pytest.mark.parametrize("fuse", [0, 1])
 def test_schedule_preserves_the_unitary(n, g, seed, fuse):
     qc = _rand_circuit(n, g, seed)
     want = O.to_matrix_rowform(qc)
     for opt in (Q.PlanOptions(fuse=fuse), Q.PlanOptions(fuse=fuse, reg_qubits=3, tile_qubits=5, max_ops_per_sweep=9),
-                Q.PlanOptions(fuse=fuse, snap_tol=-1.0, reg_qubits=2), Q.PlanOptions(fuse=fuse, reg_qubits=1, tile_qubits=2)):
+                Q.PlanOptions(fuse=fuse, snap_tol=-1.0, reg_qubits=2), Q.PlanOptions(fuse=fuse, reg_qubits=1, tile_qubits=2),
+                Q.PlanOptions(fuse=fuse, no_perm_folding=1), Q.PlanOptions(fuse=fuse, no_perm_folding=2, reg_qubits=3),
+                Q.PlanOptions(fuse=fuse, reg_qubits=4, tile_qubits=8, max_ops_per_sweep=200),
+                Q.PlanOptions(fuse=fuse, no_perm_folding=2, tile_qubits=7)):
         plan = Q.Plan(n, 2**n, O.gate_stream(qc), opt)
         d = plan.dump()
         st = plan.stats()
@@ -97,7 +100,7 @@ def test_snapping_is_optional_and_small():
     ukinds = {u["kind"] for sw in d_snap["sweeps"] for st in sw["stages"] for u in st["uops"]}
     assert "H" in ukinds and ukinds & {"DTABH", "DTABF"}  # n = R = 4: every bit is a register bit
     d6 = Q.Plan(6, 64, O.gate_stream(O.qcir_from_qasm_text(O.random_clifford_t_qasm(6, 300, 9)))).dump()
-    assert {"DSCAL", "SAPPLY"} <= {u["kind"] for sw in d6["sweeps"] for st in sw["stages"] for u in st["uops"]}
+    assert "SCALN" in {u["kind"] for sw in d6["sweeps"] for st in sw["stages"] for u in st["uops"]}
     assert "X" in kinds(d_snap) and "NEG" in kinds(d_snap) and "MULI" in kinds(d_snap)
     assert "X" not in kinds(d_exact) and "NEG" not in kinds(d_exact)
     for d in (d_exact, d_snap):

@@ -104,7 +104,9 @@ def test_random_circuits_match_oracle(n, g, seed, fuse):
                 Q.PlanOptions(fuse=fuse, reg_qubits=3, tile_qubits=6, max_ops_per_sweep=17),
                 Q.PlanOptions(fuse=fuse, reg_qubits=2, tile_qubits=4, log2_tile_cols=1, snap_tol=-1.0),
                 Q.PlanOptions(fuse=fuse, reg_qubits=4, tile_qubits=8, log2_tile_cols=4, max_ops_per_sweep=200),
-                Q.PlanOptions(fuse=fuse, reg_qubits=1, tile_qubits=3, log2_tile_cols=-1)):
+                Q.PlanOptions(fuse=fuse, reg_qubits=1, tile_qubits=3, log2_tile_cols=-1),
+                Q.PlanOptions(fuse=fuse, no_perm_folding=1), Q.PlanOptions(fuse=fuse, no_perm_folding=2, tile_qubits=7),
+                Q.PlanOptions(fuse=fuse, no_perm_folding=2, reg_qubits=3, max_ops_per_sweep=200)):
         got = run_device(qc, opt)
         assert frob_rel(got, want) < TOL
 
