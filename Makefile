@@ -6,6 +6,8 @@ CXX       ?= g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := -O3 -std=c++20 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wextra -Xptxas -v
 CXXFLAGS  := -O2 -std=c++20 -fPIC -Wall -Wextra -Werror
+# gcc 13 reports a false -Wfree-nonheap-object inside std::vector<T*> growth at -O2
+HOSTFLAGS := $(CXXFLAGS) -Wno-free-nonheap-object
 
 CSRC      := qsyn_b200/csrc
 LIBDIR    := qsyn_b200/lib
@@ -14,7 +16,27 @@ OBJDIR    := build/obj
 LIBQSX    := $(LIBDIR)/libqsx.so
 OBJS      := $(OBJDIR)/kernels.o $(OBJDIR)/runtime.o $(OBJDIR)/planner.o
 
-all: $(LIBQSX)
+HOST      := qsyn_b200/host
+SHIM      := bin/qsyn-b200
+HOSTHDRS  := $(wildcard $(HOST)/*/*.hpp) include/qsx.h
+
+all: $(LIBQSX) $(SHIM)
+
+# host layer (reference-shaped QTensor / to_tensor / QCir API) + the dofile-runner shim
+$(OBJDIR)/host_%.o: $(HOST)/qcir/%.cpp $(HOSTHDRS)
+	@mkdir -p $(OBJDIR)
+	$(CXX) $(HOSTFLAGS) -c $< -o $@
+$(OBJDIR)/host_%.o: $(HOST)/convert/%.cpp $(HOSTHDRS)
+	@mkdir -p $(OBJDIR)
+	$(CXX) $(HOSTFLAGS) -c $< -o $@
+$(OBJDIR)/host_%.o: $(HOST)/cli/%.cpp $(HOSTHDRS)
+	@mkdir -p $(OBJDIR)
+	$(CXX) $(HOSTFLAGS) -c $< -o $@
+
+$(SHIM): $(OBJDIR)/host_qcir_io.o $(OBJDIR)/host_qcir_to_tensor.o $(OBJDIR)/host_shim_main.o $(LIBQSX)
+	@mkdir -p bin
+	$(CXX) -o $@ $(OBJDIR)/host_qcir_io.o $(OBJDIR)/host_qcir_to_tensor.o $(OBJDIR)/host_shim_main.o \
+	    -L$(LIBDIR) -lqsx -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.hpp) include/qsx.h $(wildcard qsyn_b200/host/util/*.hpp)
 	@mkdir -p $(OBJDIR)
@@ -35,6 +57,6 @@ oracle/_build/liboracle_c.so: oracle/oracle_c.c
 	gcc -O3 -march=native -std=c11 -fPIC -shared -Wall -Wextra -o $@ $< -lm
 
 clean:
-	rm -rf build $(LIBDIR) oracle/_build
+	rm -rf build $(LIBDIR) bin oracle/_build
 
 .PHONY: all clean oracle

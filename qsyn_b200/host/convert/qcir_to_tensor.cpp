@@ -1,0 +1,196 @@
+// qcir_to_tensor.cpp -- QCir -> QTensor<double>, B200 path.
+//
+// Drop-in for the reference's src/convert/qcir_to_tensor.cpp.  Same entry points
+// (to_tensor(QCirGate), to_tensor(QCir), the per-operation specialisations), same failure
+// behaviour (std::nullopt + log line for an empty circuit, an unsupported gate, an interrupt
+// or an allocation failure) and the same debug/trace log text -- but the main tensor is a
+// device-resident unitary and the per-gate `tensordot(gate, main)` of the reference
+// (qcir_to_tensor.cpp:184-193) becomes ONE gate stream handed to the C ABI
+// (qsx_apply_gates), which schedules it into in-place multi-gate sweeps.
+//
+// The reference's axis bookkeeping (Qubit2TensorPinMap / update_tensor_pin,
+// qcir_to_tensor.cpp:24,116-136) no longer drives any data movement -- gates act on row bits of
+// U[out,in] in place -- but its [trace] lines are part of the golden logs
+// (tests/conversion/qc2ts/ref/qc2ts.log), so the integer bookkeeping is replayed on the side,
+// with the same container type so that the iteration order matches too.
+#include "./qcir_to_tensor.hpp"
+
+#include <complex>
+#include <unordered_map>
+
+extern bool stop_requested();
+
+namespace qsyn {
+
+using Qubit2TensorPinMap = std::unordered_map<QubitIdType, std::pair<size_t, size_t>>;
+using qsyn::tensor::QTensor;
+
+// ---- per-operation tensors: the reference formulas (qtensor.hpp builders) ---------------------
+template <>
+std::optional<QTensor<double>> to_tensor(HGate const& /* op */) { return QTensor<double>::hbox(2); }
+template <>
+std::optional<QTensor<double>> to_tensor(IdGate const& /* op */) { return QTensor<double>::identity(1); }
+template <>
+std::optional<QTensor<double>> to_tensor(SwapGate const& /* op */) {
+    QTensor<double> const m{{1.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 1.0, 0.0}, {0.0, 1.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 1.0}};
+    return m.to_qtensor();
+}
+template <>
+std::optional<QTensor<double>> to_tensor(ECRGate const& /* op */) {
+    using C = std::complex<double>;
+    C const a = 1.0 / std::sqrt(2), b = C(0, 1) / std::sqrt(2), z = 0.0;
+    QTensor<double> const m{{z, z, a, b}, {z, z, b, a}, {a, -b, z, z}, {-b, a, z, z}};
+    return m.to_qtensor();
+}
+template <>
+std::optional<QTensor<double>> to_tensor(PZGate const& op) { return QTensor<double>::pzgate(op.get_phase()); }
+template <>
+std::optional<QTensor<double>> to_tensor(PXGate const& op) { return QTensor<double>::pxgate(op.get_phase()); }
+template <>
+std::optional<QTensor<double>> to_tensor(PYGate const& op) { return QTensor<double>::pygate(op.get_phase()); }
+template <>
+std::optional<QTensor<double>> to_tensor(RZGate const& op) { return QTensor<double>::rzgate(op.get_phase()); }
+template <>
+std::optional<QTensor<double>> to_tensor(RXGate const& op) { return QTensor<double>::rxgate(op.get_phase()); }
+template <>
+std::optional<QTensor<double>> to_tensor(RYGate const& op) { return QTensor<double>::rygate(op.get_phase()); }
+template <>
+std::optional<QTensor<double>> to_tensor(ControlGate const& op) {
+    if (auto target = to_tensor(op.get_target_operation())) {
+        return QTensor<double>::control(*target, op.get_num_qubits() - op.get_target_operation().get_num_qubits());
+    }
+    return std::nullopt;
+}
+
+std::optional<QTensor<double>> to_tensor(QCirGate const& gate) { return to_tensor(gate.get_operation()); }
+
+namespace {
+
+// One entry of the gate stream: the gate's controls are peeled off so that only the 2^t x 2^t
+// TARGET matrix crosses the ABI -- a multi-controlled gate must not be materialised as a dense
+// 2^k x 2^k block the way QTensor::control does (qtensor.hpp:363-371).
+struct StreamGate {
+    size_t n_ctrls = 0;
+    std::vector<double> matrix;  // row-major complex, first target = MSB
+    size_t n_targets = 0;
+};
+
+std::optional<StreamGate> lower_to_stream(Operation const& op) {
+    StreamGate g;
+    Operation target = op;
+    while (target.is<ControlGate>()) {
+        auto const cg = target.get_underlying<ControlGate>();
+        g.n_ctrls += cg.get_num_ctrls();
+        target = cg.get_target_operation();
+    }
+    auto t = to_tensor(target);
+    if (!t.has_value()) return std::nullopt;
+    g.n_targets  = target.get_num_qubits();
+    auto const m = t->to_matrix().host_elements();  // rank-2k [o0,i0,..] -> 2^k x 2^k
+    g.matrix.reserve(2 * m.size());
+    for (auto const& z : m) {
+        g.matrix.push_back(z.real());
+        g.matrix.push_back(z.imag());
+    }
+    return g;
+}
+
+// The reference's pin bookkeeping after tensordot(gate, main): result axes are the gate's
+// output pins 0..k-1 followed by the surviving main axes in order (tensor.hpp:419-430).
+void update_tensor_pin(Qubit2TensorPinMap& qubit2pin, QCirGate const& gate, size_t n_main_axes) {
+    spdlog::trace("Pin Permutation");
+    auto const operands = gate.get_qubits();
+    size_t const k      = operands.size();
+    std::vector<size_t> contracted;
+    for (auto q : operands) contracted.push_back(qubit2pin[q].first);
+    auto shifted = [&](size_t x) {
+        size_t below = 0;
+        for (auto c : contracted) below += c < x ? 1 : 0;
+        return k + x - below;
+    };
+    (void)n_main_axes;
+    for (auto& [qubit, pin] : qubit2pin) {
+        auto const [old_out, old_in] = pin;
+        auto const it                = std::find(operands.begin(), operands.end(), qubit);
+        size_t const new_out         = it != operands.end() ? static_cast<size_t>(it - operands.begin()) : shifted(old_out);
+        size_t const new_in          = shifted(old_in);
+        pin                          = {new_out, new_in};
+        spdlog::trace("  - Qubit: {} input : {} -> {} output: {} -> {}", qubit, old_in, new_in, old_out, new_out);
+    }
+}
+
+int stop_trampoline(void*) { return stop_requested() ? 1 : 0; }
+
+}  // namespace
+
+template <>
+std::optional<QTensor<double>> to_tensor(QCir const& qcir) try {
+    if (qcir.get_num_qubits() == 0) {
+        spdlog::warn("QCir is empty!!");
+        return std::nullopt;
+    }
+    spdlog::debug("Add boundary");
+    size_t const n = qcir.get_num_qubits();
+    if (stop_requested()) {
+        spdlog::warn("Conversion interrupted.");
+        return std::nullopt;
+    }
+    // identity on n qubits: one write pass on the device
+    auto unitary = tensor::DeviceUnitary::identity(static_cast<int>(n));
+
+    Qubit2TensorPinMap qubit_to_pins;  // qubit -> (output, input)
+    for (size_t q = 0; q < n; ++q) {
+        qubit_to_pins.emplace(q, std::make_pair(2 * q, 2 * q + 1));
+        spdlog::trace("  - Add Qubit: {} input: {} output: {}", q, 2 * q + 1, 2 * q);
+    }
+
+    bool const tracing = spdlog::get_level() <= spdlog::level::trace;
+    std::vector<StreamGate> lowered;
+    std::vector<qsx_gate> stream;
+    lowered.reserve(qcir.get_num_gates());
+    for (auto const& gate : qcir.get_gates()) {
+        if (stop_requested()) {
+            spdlog::warn("Conversion interrupted.");
+            return std::nullopt;
+        }
+        spdlog::debug("Gate {} ({})", gate->get_id(), gate->get_operation().get_repr());
+        auto g = lower_to_stream(gate->get_operation());
+        if (!g.has_value() || gate->get_num_qubits() > QSX_MAX_GATE_QUBITS) {
+            spdlog::error("Conversion of Gate {} ({}) to Tensor is not supported yet!!", gate->get_id(), gate->get_operation().get_repr());
+            return std::nullopt;
+        }
+        lowered.push_back(std::move(*g));
+        if (tracing) update_tensor_pin(qubit_to_pins, *gate, 2 * n);
+    }
+    size_t i = 0;
+    for (auto const& gate : qcir.get_gates()) {
+        qsx_gate d{};
+        d.n_ctrls   = static_cast<int32_t>(lowered[i].n_ctrls);
+        d.n_targets = static_cast<int32_t>(lowered[i].n_targets);
+        for (size_t p = 0; p < gate->get_num_qubits(); ++p) d.qubits[p] = static_cast<int32_t>(gate->get_qubit(p));
+        d.matrix = lowered[i].matrix.data();
+        stream.push_back(d);
+        ++i;
+    }
+
+    int const rc = unitary.apply(stream, &stop_trampoline, nullptr);
+    if (rc == QSX_ERR_INTERRUPTED || stop_requested()) {
+        spdlog::warn("Conversion interrupted.");
+        return std::nullopt;
+    }
+    if (rc == QSX_ERR_UNSUPPORTED) {
+        spdlog::error("Conversion of a gate to Tensor is not supported yet!! ({})", qsx_last_error());
+        return std::nullopt;
+    }
+    if (rc != QSX_OK) {
+        spdlog::error("Conversion failed: {}", qsx_last_error());
+        return std::nullopt;
+    }
+    // rank-2n tensor with axes [o0,i0,o1,i1,...], like the reference after to_matrix + to_qtensor
+    return QTensor<double>(std::move(unitary), /*as_matrix=*/false);
+} catch (std::bad_alloc const& e) {
+    spdlog::error("Memory allocation failed!!");
+    return std::nullopt;
+}
+
+}  // namespace qsyn
