@@ -110,7 +110,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import qsyn_b200 as Q
-    from qsyn_b200 import abi
+    from qsyn_b200 import abi, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -126,9 +126,7 @@ def run_ours(args):
 
     n, desc, qc_a, qc_b, gs_a, gs_b = build_workload(args.workload)
     dim = 2**n
-    assert dim % world == 0
-    ncols = dim // world
-    col0 = rank * ncols
+    col0, ncols = sharding.shard_columns(n, rank, world)
     opt = Q.PlanOptions(max_ops_per_sweep=args.cap, tile_qubits=args.tile, reg_qubits=args.reg, log2_tile_cols=args.log2w)
 
     stream = torch.cuda.ExternalStream(abi.device_stream(local), device=torch.device("cuda", local))
@@ -137,16 +135,12 @@ def run_ours(args):
     plan_a = Q.Plan(n, ncols, gs_a, opt)
     plan_b = Q.Plan(n, ncols, gs_b, opt)
     st_a, st_b = plan_a.stats(), plan_b.stats()
-    sums_dev = torch.zeros(8, dtype=torch.float64, device="cuda")
-
     launches = {"n": 0}
+    cuda = torch.device("cuda", local)
 
     def combine(sums):
-        if world > 1:  # ONE all-reduce of 8 doubles over NVLink
-            sums_dev.copy_(torch.from_numpy(sums))
-            dist.all_reduce(sums_dev, op=dist.ReduceOp.SUM)
-            return sums_dev.cpu().numpy()
-        return sums
+        # ONE all-reduce of 8 doubles over NVLink; identity at world size 1
+        return sharding.allreduce_sums(sums, cuda)
 
     def step_resident():
         """inputs resident: prebuilt schedules, device-side identity, async sweeps."""

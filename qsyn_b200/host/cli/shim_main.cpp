@@ -2,7 +2,7 @@
 //
 // enough of qsyn's command surface to replay the reference's own dofiles for
 // this path verbatim and diff the output against its golden logs:
-//     qcir {new|read|delete|list|qubit add|gate add}, convert qcir tensor (alias qc2ts),
+//     qcir {new|read|delete|list|print|qubit add|gate add}, convert qcir tensor (alias qc2ts),
 //     tensor {list|print|equiv|adjoint|delete|checkout|write|read}, logger, quit -f.
 // Echo / spacing rules and message texts follow cli_exec.cpp:40-105, conversion_cmd.cpp:84-98,
 // tensor_cmd.cpp:100-177, data_structure_manager.hpp and the golden logs.  The CLI framework
@@ -182,6 +182,13 @@ struct Shell {
                 qcir_mgr.remove(std::stoul(a[0]));
         } else if (is_prefix(sub, "list")) {
             qcir_mgr.print_list([](QCir const& q) { return pad_right(q.get_filename().substr(0, 19), 19) + " " + join(q.get_procedures(), " ➔ "); });
+        } else if (is_prefix(sub, "print")) {
+            if (!need_qcir()) return;
+            if (!a.empty() && (a[0] == "-d" || (a[0].size() > 2 && is_prefix(a[0], "--diagram")))) {
+                for (auto const& l : qcir_mgr.get()->circuit_diagram_lines()) std::cout << l << "\n";
+            } else {
+                std::cout << std::format("QCir ({} qubits, {} gates)\n", qcir_mgr.get()->get_num_qubits(), qcir_mgr.get()->get_num_gates());
+            }
         } else if (is_prefix(sub, "qubit")) {
             if (a.empty() || !is_prefix(a[0], "add")) return;
             size_t const n = a.size() > 1 ? std::stoul(a[1]) : 1;

@@ -331,6 +331,51 @@ public:
         _dirty = true;
     }
 
+    // ASAP level of every gate: 1 + the latest level among its predecessors
+    std::unordered_map<size_t, size_t> calculate_gate_times() const {
+        std::unordered_map<size_t, size_t> level;
+        for (QCirGate* g : get_gates()) {
+            size_t latest = 0;
+            for (auto const& pred : _predecessors[g->get_id()])
+                if (pred.has_value()) latest = std::max(latest, level.at(*pred));
+            level.emplace(g->get_id(), latest + 1);
+        }
+        return level;
+    }
+
+    // `qcir print --diagram`: one text lane per qubit, one fixed-width cell "-<name>(<id>)-" per
+    // time step (same layout as the reference's qcir_print.cpp:116-165)
+    std::vector<std::string> circuit_diagram_lines() const {
+        auto const level = calculate_gate_times();
+        size_t id_w = 0, name_w = 0, depth = 0;
+        auto bare_name = [](QCirGate const& g) {
+            auto r = g.get_operation().get_repr();
+            return r.substr(0, r.find('('));
+        };
+        for (auto const& g : _gates_by_id) {
+            id_w   = std::max(id_w, std::to_string(g->get_id()).size());
+            name_w = std::max(name_w, bare_name(*g).size());
+            depth  = std::max(depth, level.at(g->get_id()));
+        }
+        size_t const cell = 4 + name_w + id_w;
+        std::vector<std::string> lines;
+        for (size_t q = 0; q < _qubits.size(); ++q) {
+            std::string line = std::format("Q{:>2}  ", q);
+            size_t at        = 0;
+            for (QCirGate* g = _qubits[q].get_first_gate(); g != nullptr;) {
+                size_t const t = level.at(g->get_id());
+                line += std::string(cell * (t - at - 1), '-');
+                line += std::format("-{:>{}}({:>{}})-", bare_name(*g), name_w, g->get_id(), id_w);
+                at            = t;
+                auto const nx = _successors[g->get_id()][*g->get_pin_by_qubit(q)];
+                g             = nx.has_value() ? _gates_by_id[*nx].get() : nullptr;
+            }
+            line += std::string(cell * (depth - at), '-');
+            lines.push_back(std::move(line));
+        }
+        return lines;
+    }
+
     void set_filename(std::string const& f) { _filename = f; }
     std::string get_filename() const { return _filename; }
     void add_procedures(std::vector<std::string> const& ps) { _procedures.insert(_procedures.end(), ps.begin(), ps.end()); }
