@@ -267,6 +267,55 @@ void build_stages(Plan& plan, std::vector<int> chosen, PlannedSweep& sw) {
         st.reg_bits   = rb;
         st.post_taint = 0;
         for (int b : rb) st.post_taint |= 1u << b;
+        // sink: an X-type op that had to stay in registers (something before it in this stage does
+        // not commute with it) can still leave through the END of the stage if it commutes with
+        // everything AFTER it.  Scan backwards so that "after" already excludes sunk ops.
+        if (plan.cfg.fold_perms) {
+            std::vector<int> sunk;  // collected back to front
+            uint32_t laterT = 0, laterA = 0;
+            for (size_t k = st.ops.size(); k-- > 0;) {
+                LoweredOp const& op = plan.ops[st.ops[k]];
+                uint32_t const T = op.tmask(), A = T | op.dmask();
+                if (is_perm_op(op) && (T & laterA) == 0 && (A & laterT) == 0) {
+                    sunk.push_back(st.ops[k]);
+                    st.ops.erase(st.ops.begin() + (long)k);
+                    continue;
+                }
+                laterT |= T;
+                laterA |= A;
+            }
+            // `sunk` is back to front; in circuit order it is s_1 < ... < s_k.  The boundary list must
+            // stay affine in the register bits, so sink the longest suffix s_j..s_k that the taint
+            // check accepts and put s_1..s_{j-1} back where they were (a kept op precedes every
+            // sunk one, so the order among them is unchanged).
+            std::vector<int> order(sunk.rbegin(), sunk.rend());
+            size_t first_sunk = order.size();
+            for (size_t j = 0; j < order.size(); ++j) {
+                uint32_t taint = st.post_taint;
+                bool ok        = true;
+                for (size_t k = j; k < order.size() && ok; ++k) ok = boundary_accept(plan.ops[order[k]], taint);
+                if (ok) {
+                    first_sunk = j;
+                    break;
+                }
+            }
+            for (size_t k = first_sunk; k < order.size(); ++k) {
+                boundary_accept(plan.ops[order[k]], st.post_taint);
+                st.post.push_back(order[k]);
+                ++plan.stats.n_folded_perms;
+            }
+            if (first_sunk > 0) {
+                // re-insert the kept ones at their original relative positions: merge by op index
+                std::vector<int> merged;
+                size_t a = 0;
+                for (int idx : st.ops) {
+                    while (a < first_sunk && order[a] < idx) merged.push_back(order[a++]);
+                    merged.push_back(idx);
+                }
+                while (a < first_sunk) merged.push_back(order[a++]);
+                st.ops.swap(merged);
+            }
+        }
         sw.stages.push_back(std::move(st));
     }
 }
