@@ -182,6 +182,15 @@ __device__ __forceinline__ void op_dtab_half(double2 (&e)[1 << R], const double2
     }
 }
 
+// The handlers almost every sweep uses.  sweep_kernel<R, LEAN = true> contains only these: the
+// kernel is an interpreter whose hot loop jumps between handler bodies, and the full set is
+// ~160 KB of SASS -- far beyond the instruction caches ("no_instruction" was the third largest
+// stall reason).  A sweep that needs any other handler runs in the LEAN = false instantiation.
+__host__ __device__ constexpr bool is_common_handler(int h) {
+    return (h >= H_H && h < H_H + 4) || (h >= H_X && h < H_X + 4) || (h >= H_XC && h < H_XC + 16) ||
+           (h >= H_U1 && h < H_U1 + 4) || (h >= H_DTABH && h < H_DTABH + 4) || h == H_DTABF || h == H_SCALN;
+}
+
 // One handler = one straight-line body; everything about it is known at compile time.
 template <int R, int H>
 __device__ __forceinline__ void run_handler(double2 (&e)[1 << R], double2& scal, const DevOp* __restrict__ op, uint32_t creg,
@@ -242,12 +251,14 @@ __device__ __forceinline__ void run_handler(double2 (&e)[1 << R], double2& scal,
     }
 }
 
-#define QSX_CASE(h) \
-    case h: run_handler<R, h>(e, scal, op, creg, pool_off, sel, grow, pool); break;
+#define QSX_CASE(h)                                                                \
+    case h:                                                                        \
+        if constexpr (!LEAN || is_common_handler(h)) run_handler<R, h>(e, scal, op, creg, pool_off, sel, grow, pool); \
+        break;
 #define QSX_CASE8(b) QSX_CASE(b) QSX_CASE(b + 1) QSX_CASE(b + 2) QSX_CASE(b + 3) QSX_CASE(b + 4) QSX_CASE(b + 5) QSX_CASE(b + 6) QSX_CASE(b + 7)
 
 // hdr = {handler, j0, j1, creg}, hdr2 = {cother, czero, pool, sel}: already loaded (prefetched) by the caller
-template <int R>
+template <int R, bool LEAN>
 __device__ __forceinline__ void apply_op(double2 (&e)[1 << R], double2& scal, const DevOp* __restrict__ op, int4 hdr, int4 hdr2,
                                          uint32_t grow, const double* __restrict__ pool) {
     uint32_t const creg   = (uint32_t)hdr.w;
@@ -299,7 +310,7 @@ __device__ __forceinline__ uint32_t deposit_tile_bits(uint32_t x, const int32_t*
     return r;
 }
 
-template <int R>
+template <int R, bool LEAN>
 __global__ void __launch_bounds__(1 << max_threads_log2(R), 1)
     sweep_kernel(double2* __restrict__ u, const unsigned char* __restrict__ gprog, uint32_t prog_bytes, int log2_ncols,
                  int log2_ncb) {
@@ -407,7 +418,7 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), 1)
             for (int o = ob; o < oe; ++o) {
                 int4 const hdr  = *reinterpret_cast<const int4*>(ops + o);
                 int4 const hdr2 = *(reinterpret_cast<const int4*>(ops + o) + 1);
-                apply_op<R>(e, scal, ops + o, hdr, hdr2, grow, pool);
+                apply_op<R, LEAN>(e, scal, ops + o, hdr, hdr2, grow, pool);
             }
         }
 
@@ -458,7 +469,7 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), 1)
     }
 }
 
-template <int R>
+template <int R, bool LEAN>
 cudaError_t launch_sweep_r(double2* u, int n, uint64_t ncols, const DevSweep& hs, const unsigned char* prog,
                            size_t prog_bytes, cudaStream_t s) {
     (void)n;
@@ -477,11 +488,11 @@ cudaError_t launch_sweep_r(double2* u, int n, uint64_t ncols, const DevSweep& hs
     if (cudaError_t const rc = cudaGetDevice(&dev); rc != cudaSuccess) return rc;
     if (dev < 64 && !attr_set[dev]) {
         cudaError_t const rc =
-            cudaFuncSetAttribute(sweep_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(sweep_kernel<R, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (rc != cudaSuccess) return rc;
         attr_set[dev] = true;
     }
-    sweep_kernel<R><<<(unsigned)nblocks, threads, smem, s>>>(u, prog, (uint32_t)prog_bytes, log2_ncols, log2_ncb);
+    sweep_kernel<R, LEAN><<<(unsigned)nblocks, threads, smem, s>>>(u, prog, (uint32_t)prog_bytes, log2_ncols, log2_ncb);
     return cudaGetLastError();
 }
 
@@ -647,11 +658,22 @@ cudaError_t launch_set_identity(double2* u, int n, uint64_t col0, uint64_t ncols
 
 cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, int R, const DevSweep& hs, const unsigned char* prog,
                          size_t prog_bytes, cudaStream_t s) {
-    switch (R) {
-        case 1: return launch_sweep_r<1>(u, n, ncols, hs, prog, prog_bytes, s);
-        case 2: return launch_sweep_r<2>(u, n, ncols, hs, prog, prog_bytes, s);
-        case 3: return launch_sweep_r<3>(u, n, ncols, hs, prog, prog_bytes, s);
-        case 4: return launch_sweep_r<4>(u, n, ncols, hs, prog, prog_bytes, s);
+    // does every micro-op of this sweep have a handler in the lean instantiation?
+    bool lean = true;
+    {
+        const unsigned char* const host = reinterpret_cast<const unsigned char*>(&hs);
+        const DevOp* const ops = reinterpret_cast<const DevOp*>(host + sizeof(DevSweep) + (size_t)hs.n_stages * sizeof(DevStage));
+        for (int i = 0; i < hs.n_ops && lean; ++i) lean = is_common_handler(ops[i].handler);
+    }
+    switch (R * 2 + (lean ? 1 : 0)) {
+        case 2: return launch_sweep_r<1, false>(u, n, ncols, hs, prog, prog_bytes, s);
+        case 3: return launch_sweep_r<1, true>(u, n, ncols, hs, prog, prog_bytes, s);
+        case 4: return launch_sweep_r<2, false>(u, n, ncols, hs, prog, prog_bytes, s);
+        case 5: return launch_sweep_r<2, true>(u, n, ncols, hs, prog, prog_bytes, s);
+        case 6: return launch_sweep_r<3, false>(u, n, ncols, hs, prog, prog_bytes, s);
+        case 7: return launch_sweep_r<3, true>(u, n, ncols, hs, prog, prog_bytes, s);
+        case 8: return launch_sweep_r<4, false>(u, n, ncols, hs, prog, prog_bytes, s);
+        case 9: return launch_sweep_r<4, true>(u, n, ncols, hs, prog, prog_bytes, s);
         default: return cudaErrorInvalidValue;
     }
 }
