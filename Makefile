@@ -20,7 +20,13 @@ HOST      := qsyn_b200/host
 SHIM      := bin/qsyn-b200
 HOSTHDRS  := $(wildcard $(HOST)/*/*.hpp) include/qsx.h
 
-all: $(LIBQSX) $(SHIM)
+FP64PEAK  := bin/fp64_peak
+
+all: $(LIBQSX) $(SHIM) $(FP64PEAK)
+
+$(FP64PEAK): $(CSRC)/tools/fp64_peak.cu
+	@mkdir -p bin
+	$(NVCC) -O3 -std=c++20 -lineinfo $(ARCH) -o $@ $<
 
 # host layer (reference-shaped QTensor / to_tensor / QCir API) + the dofile-runner shim
 $(OBJDIR)/host_%.o: $(HOST)/qcir/%.cpp $(HOSTHDRS)

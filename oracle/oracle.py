@@ -872,3 +872,19 @@ def qft_qasm(n: int) -> str:
         for j in range(i + 1, n):
             lines.append(f"cp(pi/{2 ** (j - i)}) q[{j}],q[{i}];")
     return "\n".join(lines) + "\n"
+
+
+def random_rotation_qasm(n: int, n_gates: int, seed: int) -> str:
+    """Dense-rotation workload (where fused dense blocks pay off): rx/ry/rz with random rational
+    angles on random qubits, 25 % cx on random pairs."""
+    rng = np.random.default_rng(seed)
+    lines = ["OPENQASM 2.0;", 'include "qelib1.inc";', f"qreg q[{n}];"]
+    for _ in range(n_gates):
+        if n >= 2 and rng.random() < 0.25:
+            a, b = rng.choice(n, size=2, replace=False)
+            lines.append(f"cx q[{int(a)}],q[{int(b)}];")
+        else:
+            name = ["rx", "ry", "rz"][int(rng.integers(3))]
+            num, den = int(rng.integers(1, 64)), 64
+            lines.append(f"{name}({num}*pi/{den}) q[{int(rng.integers(n))}];")
+    return "\n".join(lines) + "\n"

@@ -12,6 +12,7 @@
 //   equiv_*           K4: fused 8-sum reduction with compensated accumulation
 //                     (replaces the lazy xt::sum loops of tensor.hpp:393-403, qtensor.hpp:383-385).
 //   adjoint_inplace   K5: tiled conjugate transpose (tensor.hpp:303-306).
+#include <algorithm>
 #include <cstdint>
 #include <type_traits>
 
@@ -497,6 +498,154 @@ cudaError_t launch_sweep_r(double2* u, int n, uint64_t ncols, const DevSweep& hs
 }
 
 // ---------------------------------------------------------------------------------------
+// dense_kernel<K>: one dense 2^K x 2^K complex block on the FP64 tensor pipe (K1f).
+//
+// A CTA stages a tile of 2^m rows x 8 columns in shared memory (same tiles as sweep_kernel).
+// The block's K row bits are tile bits; for every combination j of the other m-K tile bits the
+// 8 columns give 8 independent complex vectors v of length D = 2^K.  In real form
+// [v'_re; v'_im] = A [v_re; v_im] with A = [[Gr, -Gi], [Gi, Gr]] interleaved per component, so one
+// j is a (2D x 2D) x (2D x 8) real GEMM, computed with mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4):
+//   B fragment (k = lane%4, n = lane/4): component k of column n -> one 8-byte LDS from the tile
+//   A fragment (row = lane/4, k = lane%4): from the padded copy of A in shared memory
+//   C fragment (row = lane/4, n = 2*(lane%4)+{0,1}): written back in place
+// A warp owns whole j's, loads all B fragments of a j into registers before writing, so the
+// update is in place without extra buffering.  Flops: 8 * 2^K per element.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
+
+template <int K>
+__global__ void __launch_bounds__(256, 2)
+    dense_kernel(double2* __restrict__ u, const unsigned char* __restrict__ gprog, int log2_ncols, int log2_ncb,
+                 uint32_t n_tiles) {
+    constexpr int D   = 1 << K;        // complex components per vector
+    constexpr int D2  = 2 * D;         // real GEMM size
+    constexpr int LDA = dense_lda(K);  // padded leading dimension of A (doubles)
+    constexpr int KB  = D2 / 4;        // k-blocks
+    constexpr int RB  = D2 / 8;        // row-blocks
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ DevSweep sw;
+    __shared__ int32_t block_local[8];
+    __shared__ uint32_t comp_row[D];  // tile-local row offset of component c
+
+    // ---- once per (persistent) CTA: header, the real block matrix, row tables ----
+    if (threadIdx.x < sizeof(DevSweep) / 16)
+        reinterpret_cast<uint4*>(&sw)[threadIdx.x] = __ldg(reinterpret_cast<const uint4*>(gprog) + threadIdx.x);
+    if (threadIdx.x < 8) block_local[threadIdx.x] = __ldg(reinterpret_cast<const int32_t*>(gprog + sizeof(DevSweep)) + threadIdx.x);
+    double* const As    = reinterpret_cast<double*>(smem_raw);
+    double2* const tile = reinterpret_cast<double2*>(smem_raw + sizeof(double) * D2 * LDA);
+    {
+        const double* const Ag = reinterpret_cast<const double*>(gprog + sizeof(DevSweep) + 32);
+        for (int i = threadIdx.x; i < D2 * LDA; i += blockDim.x) As[i] = __ldg(Ag + i);
+    }
+    __syncthreads();
+    int const m           = sw.m;
+    int const rows        = 1 << m;
+    uint32_t* const growl = reinterpret_cast<uint32_t*>(tile + ((size_t)8 << m));  // tile-local row -> its global tile bits
+    for (int l = threadIdx.x; l < rows; l += blockDim.x) {
+        uint32_t g = 0;
+        for (int b = 0; b < m; ++b) g |= ((l >> b) & 1u) << sw.sp[b];
+        growl[l] = g;
+    }
+    if (threadIdx.x < D) {
+        uint32_t off = 0;
+        for (int i = 0; i < K; ++i) off |= ((threadIdx.x >> i) & 1u) << block_local[i];
+        comp_row[threadIdx.x] = off;
+    }
+    uint32_t block_mask = 0;
+    for (int i = 0; i < K; ++i) block_mask |= 1u << block_local[i];
+    __syncthreads();
+
+    uint32_t const cw = threadIdx.x & 7u;
+    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    int const g = lane >> 2, t = lane & 3;
+    double* const tile_d = reinterpret_cast<double*>(tile);
+
+    for (uint32_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
+        uint64_t const cb  = tile_id & ((1u << log2_ncb) - 1u);
+        uint32_t const rc  = tile_id >> log2_ncb;
+        uint32_t row_outer = 0;
+        for (int k = 0; k < sw.n_outer; ++k) row_outer |= ((rc >> k) & 1u) << sw.outer[k];
+        uint64_t const col = (cb << 3) + cw;
+
+        // ---- load the tile: 8 columns x 2^m rows, 128 B per row ----
+        for (int l = threadIdx.x >> 3; l < rows; l += blockDim.x >> 3)
+            tile[(l << 3) + cw] = __ldcg(u + ((size_t)(row_outer | growl[l]) << log2_ncols) + col);
+        __syncthreads();
+
+        // ---- GEMM: each warp owns whole j's ----
+        for (int j = warp; j < (rows >> K); j += n_warps) {
+            uint32_t base = 0;  // j deposited into the tile-local bits that are not block bits
+            {
+                int jj = j;
+                for (int b = 0; b < m; ++b)
+                    if (!((block_mask >> b) & 1u)) {
+                        base |= (uint32_t)(jj & 1) << b;
+                        jj >>= 1;
+                    }
+            }
+            double bfrag[KB];
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) {
+                int const kidx = 4 * kb + t;  // real component index = 2*c + part
+                bfrag[kb]      = tile_d[(((size_t)(base | comp_row[kidx >> 1]) << 3) + g) * 2 + (kidx & 1)];
+            }
+            double out[RB][2];
+#pragma unroll
+            for (int rb = 0; rb < RB; ++rb) {
+                double acc[2] = {0.0, 0.0};
+                const double* const arow = As + (size_t)(rb * 8 + g) * LDA + t;
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) dmma_m8n8k4(acc, arow[4 * kb], bfrag[kb]);
+                out[rb][0] = acc[0];
+                out[rb][1] = acc[1];
+            }
+            __syncwarp();  // every lane has read its B fragments of this j
+#pragma unroll
+            for (int rb = 0; rb < RB; ++rb) {
+                int const ridx    = rb * 8 + g;  // output real component = 2*c' + part'
+                double* const dst = tile_d + (((size_t)(base | comp_row[ridx >> 1]) << 3) + 2 * t) * 2 + (ridx & 1);
+                dst[0]            = out[rb][0];  // column 2t
+                dst[2]            = out[rb][1];  // column 2t + 1
+            }
+        }
+        __syncthreads();
+
+        for (int l = threadIdx.x >> 3; l < rows; l += blockDim.x >> 3)
+            __stcg(u + ((size_t)(row_outer | growl[l]) << log2_ncols) + col, tile[(l << 3) + cw]);
+        __syncthreads();  // the tile buffer is reused by the next iteration
+    }
+}
+
+template <int K>
+cudaError_t launch_dense_k(double2* u, uint64_t ncols, const DevSweep& hs, const unsigned char* prog, cudaStream_t s) {
+    int log2_ncols = 0;
+    while ((1ull << log2_ncols) < ncols) ++log2_ncols;
+    int const log2_ncb     = log2_ncols - 3;
+    uint64_t const nblocks = 1ull << (log2_ncb + hs.n_outer);
+    if (log2_ncb < 0 || hs.m > kMaxTileBits || hs.m < K || nblocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    size_t const smem = sizeof(double) * (2 << K) * dense_lda(K) + ((size_t)16 * 8 << hs.m) + sizeof(uint32_t) * ((size_t)1 << hs.m);
+    static bool attr_set[64] = {};
+    int dev                  = 0;
+    if (cudaError_t const rc = cudaGetDevice(&dev); rc != cudaSuccess) return rc;
+    if (dev < 64 && !attr_set[dev]) {
+        if (cudaError_t const rc = cudaFuncSetAttribute(dense_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            rc != cudaSuccess)
+            return rc;
+        attr_set[dev] = true;
+    }
+    // persistent CTAs (2 per SM): the 2^(K+1) x 2^(K+1) real matrix is staged once per CTA, not once per tile
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    unsigned const grid = (unsigned)std::min<uint64_t>(nblocks, (uint64_t)sms * 2);
+    dense_kernel<K><<<grid, 256, smem, s>>>(u, prog, log2_ncols, log2_ncb, (uint32_t)nblocks);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
 // identity
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) set_identity_kernel(double2* __restrict__ u, uint64_t n_elems, uint64_t col0,
@@ -658,6 +807,14 @@ cudaError_t launch_set_identity(double2* u, int n, uint64_t col0, uint64_t ncols
 
 cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, int R, const DevSweep& hs, const unsigned char* prog,
                          size_t prog_bytes, cudaStream_t s) {
+    if (hs.dense_k != 0) {
+        switch (hs.dense_k) {
+            case 3: return launch_dense_k<3>(u, ncols, hs, prog, s);
+            case 4: return launch_dense_k<4>(u, ncols, hs, prog, s);
+            case 5: return launch_dense_k<5>(u, ncols, hs, prog, s);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     // does every micro-op of this sweep have a handler in the lean instantiation?
     bool lean = true;
     {

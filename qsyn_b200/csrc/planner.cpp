@@ -19,6 +19,7 @@
 #include <cassert>
 #include <chrono>
 #include <cmath>
+#include <complex>
 #include <cstring>
 #include <sstream>
 
@@ -571,6 +572,152 @@ void schedule(Plan& plan) {
     }
 }
 
+// ---- dense k-qubit blocks (north_star: "fused k-qubit blocks ... on the DMMA tensor pipe") ----
+//
+// With `dense_block = k` the gate stream is folded into dense 2^k x 2^k complex blocks: a block
+// absorbs every op (taken in commutation-respecting order, like a sweep) ALL of whose bits --
+// targets, controls and diagonal bits -- fit in the block's k row bits; the ops are multiplied
+// together on the host and the block is applied as a real (2^(k+1))^2 GEMM by dense_kernel<k>.
+// A dense block costs 8 * 2^k real flops per element no matter how many gates it absorbed, so it
+// pays off only for circuits of dense rotations; for Clifford+T the interpreter is faster
+// (B200's FP64 tensor pipe has the same peak as its FMA pipe).
+
+using CMat = std::vector<std::complex<double>>;
+
+// M <- (op acting on the block's local bits) * M, M is D x D row-major; lb(global bit) -> local bit
+void fold_op_into_block(CMat& M, int k, LoweredOp const& op, int const* local_of_bit) {
+    size_t const D = size_t{1} << k;
+    auto lbit = [&](int g) { return local_of_bit[g]; };
+    uint32_t req = 0;
+    for (int b = 0; b < kMaxRowBits; ++b)
+        if ((op.req >> b) & 1u) req |= 1u << lbit(b);
+    using C = std::complex<double>;
+    auto for_rows = [&](auto fn) {
+        for (size_t r = 0; r < D; ++r)
+            if (((uint32_t)r & req) == req) fn(r);
+    };
+    auto scale_row = [&](size_t r, C w) {
+        for (size_t c = 0; c < D; ++c) M[r * D + c] *= w;
+    };
+    switch (op.kind) {
+        case OP_PHASE: for_rows([&](size_t r) { scale_row(r, C(op.c[0], op.c[1])); }); return;
+        case OP_NEG: for_rows([&](size_t r) { scale_row(r, C(-1, 0)); }); return;
+        case OP_MULI: for_rows([&](size_t r) { scale_row(r, C(0, op.c[0])); }); return;
+        case OP_DIAG: {
+            int const d = lbit(op.dbit);
+            for_rows([&](size_t r) { scale_row(r, ((r >> d) & 1) ? C(op.c[2], op.c[3]) : C(op.c[0], op.c[1])); });
+            return;
+        }
+        default: break;
+    }
+    int const t0 = lbit(op.t0);
+    if (op.kind == OP_SWAP || op.kind == OP_U2) {
+        int const t1 = lbit(op.t1);
+        C g[16];
+        if (op.kind == OP_SWAP) {
+            static double const sw[16] = {1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1};
+            for (int i = 0; i < 16; ++i) g[i] = sw[i];
+        } else {
+            for (int i = 0; i < 16; ++i) g[i] = C(op.mat[2 * i], op.mat[2 * i + 1]);
+        }
+        for_rows([&](size_t r) {
+            if (((r >> t0) & 1) || ((r >> t1) & 1)) return;
+            size_t const idx[4] = {r, r | (size_t{1} << t1), r | (size_t{1} << t0), r | (size_t{1} << t0) | (size_t{1} << t1)};
+            for (size_t c = 0; c < D; ++c) {
+                C v[4], w[4];
+                for (int x = 0; x < 4; ++x) v[x] = M[idx[x] * D + c];
+                for (int y = 0; y < 4; ++y) {
+                    w[y] = 0;
+                    for (int x = 0; x < 4; ++x) w[y] += g[4 * y + x] * v[x];
+                }
+                for (int y = 0; y < 4; ++y) M[idx[y] * D + c] = w[y];
+            }
+        });
+        return;
+    }
+    C m00, m01, m10, m11;
+    switch (op.kind) {
+        case OP_H: m00 = m01 = m10 = op.c[0], m11 = -op.c[0]; break;
+        case OP_X: m00 = m11 = 0, m01 = m10 = 1; break;
+        case OP_AD: m00 = m11 = 0, m01 = C(op.c[0], op.c[1]), m10 = C(op.c[2], op.c[3]); break;
+        default: m00 = C(op.c[0], op.c[1]), m01 = C(op.c[2], op.c[3]), m10 = C(op.c[4], op.c[5]), m11 = C(op.c[6], op.c[7]); break;
+    }
+    for_rows([&](size_t r) {
+        if ((r >> t0) & 1) return;
+        size_t const hi = r | (size_t{1} << t0);
+        for (size_t c = 0; c < D; ++c) {
+            C const a = M[r * D + c], b = M[hi * D + c];
+            M[r * D + c]  = m00 * a + m01 * b;
+            M[hi * D + c] = m10 * a + m11 * b;
+        }
+    });
+}
+
+void schedule_dense(Plan& plan) {
+    PlanConfig const& cfg = plan.cfg;
+    int const k           = cfg.dense_k;
+    size_t const N        = plan.ops.size();
+    std::vector<char> done(N, 0);
+    size_t first = 0;
+    while (true) {
+        while (first < N && done[first]) ++first;
+        if (first >= N) break;
+        if (popc(plan.ops[first].tmask() | plan.ops[first].dmask()) > k) {
+            // touches more than k bits (e.g. cccx for k = 3): no dense block can hold it ->
+            // an interpreted sweep of its own
+            done[first] = 1;
+            finish_sweep(plan, {(int)first}, plan.ops[first].tmask());
+            continue;
+        }
+        uint32_t S = 0;
+        std::vector<int> chosen;
+        Picker pk;
+        int scanned = 0;
+        for (size_t i = first; i < N && scanned < cfg.lookahead; ++i) {
+            if (done[i]) continue;
+            ++scanned;
+            LoweredOp const& op = plan.ops[i];
+            uint32_t const bits = op.tmask() | op.dmask();  // a dense matrix needs every touched bit inside
+            if (pk.passes(op) && popc(S | bits) <= k) {
+                S |= bits;
+                chosen.push_back((int)i);
+                done[i] = 1;
+            } else {
+                pk.block(op);
+                if (popc(pk.blockedT) >= cfg.n) break;
+            }
+        }
+        PlannedSweep sw;
+        for (int b = 0; b < cfg.n && popc(S) < k; ++b) S |= 1u << b;  // pad the block to exactly k bits
+        int local_of_bit[kMaxRowBits];
+        for (int b = 0; b < kMaxRowBits; ++b) local_of_bit[b] = -1;
+        for (int b = 0; b < cfg.n; ++b)
+            if ((S >> b) & 1u) {
+                local_of_bit[b] = (int)sw.block_bits.size();
+                sw.block_bits.push_back(b);
+            }
+        size_t const D = size_t{1} << k;
+        CMat M(D * D, 0.0);
+        for (size_t r = 0; r < D; ++r) M[r * D + r] = 1.0;
+        for (int idx : chosen) fold_op_into_block(M, k, plan.ops[idx], local_of_bit);
+        for (auto const& z : M) {
+            sw.block_matrix.push_back(z.real());
+            sw.block_matrix.push_back(z.imag());
+        }
+        sw.block_ops = chosen;
+        // tile: the block bits plus enough other row bits for a full CTA
+        uint32_t T       = S;
+        int const m_want = std::min(cfg.n, std::max(k, std::min(cfg.m_cap, 9)));
+        for (int b = 0; b < cfg.n && popc(T) < m_want; ++b) T |= 1u << b;
+        for (int b = 0; b < cfg.n; ++b)
+            if ((T >> b) & 1u) sw.tile_bits.push_back(b);
+        sw.alg_bytes = 32.0 * std::ldexp(1.0, cfg.n) * (double)cfg.ncols;
+        plan.stats.alg_bytes_per_run += sw.alg_bytes;
+        ++plan.stats.n_dense_blocks;
+        plan.sweeps.push_back(std::move(sw));
+    }
+}
+
 // ---- serialization ----------------------------------------------------------------------
 
 int handler_of(MicroOp const& u) {
@@ -600,6 +747,47 @@ void serialize(Plan& plan) {
         DevSweep hs;
         std::memset(&hs, 0, sizeof(hs));
         int const m   = (int)sw.tile_bits.size();
+        if (!sw.block_bits.empty()) {
+            int const k = (int)sw.block_bits.size();
+            hs.m        = m;
+            hs.log2w    = cfg.log2w;
+            hs.dense_k  = k;
+            uint32_t S  = 0;
+            int local_of[kMaxRowBits];
+            for (int b = 0; b < kMaxRowBits; ++b) local_of[b] = -1;
+            for (int l = 0; l < m; ++l) {
+                hs.sp[l]                   = sw.tile_bits[l];
+                local_of[sw.tile_bits[l]] = l;
+                S |= 1u << sw.tile_bits[l];
+            }
+            int no = 0;
+            for (int b = 0; b < cfg.n; ++b)
+                if (!((S >> b) & 1u)) hs.outer[no++] = b;
+            hs.n_outer = no;
+            int32_t bl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int i = 0; i < k; ++i) bl[i] = local_of[sw.block_bits[i]];
+            size_t const D = size_t{1} << k, lda = (size_t)dense_lda(k);
+            std::vector<double> A(2 * D * lda, 0.0);
+            for (size_t r = 0; r < D; ++r)
+                for (size_t c = 0; c < D; ++c) {
+                    double const gr = sw.block_matrix[2 * (r * D + c)], gi = sw.block_matrix[2 * (r * D + c) + 1];
+                    A[(2 * r) * lda + 2 * c]         = gr;
+                    A[(2 * r) * lda + 2 * c + 1]     = -gi;
+                    A[(2 * r + 1) * lda + 2 * c]     = gi;
+                    A[(2 * r + 1) * lda + 2 * c + 1] = gr;
+                }
+            hs.pool_doubles  = (int)A.size();
+            size_t const off = (plan.blob.size() + 255) / 256 * 256;
+            size_t const sz  = sizeof(DevSweep) + sizeof(bl) + A.size() * sizeof(double);
+            plan.blob.resize(off + sz, 0);
+            unsigned char* p = plan.blob.data() + off;
+            std::memcpy(p, &hs, sizeof(hs));
+            std::memcpy(p + sizeof(hs), bl, sizeof(bl));
+            std::memcpy(p + sizeof(hs) + sizeof(bl), A.data(), A.size() * sizeof(double));
+            plan.sweep_offset.push_back(off);
+            plan.sweep_size.push_back(sz);
+            continue;
+        }
         hs.n_stages   = (int)sw.stages.size();
         hs.m          = m;
         hs.log2w      = cfg.log2w;
@@ -768,7 +956,22 @@ int build_plan(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gat
             cfg.R     = 2;
             cfg.m_cap = std::max(cfg.m_cap, 2);
         }
-    schedule(plan);
+    cfg.dense_k = 0;
+    if (o.dense_block != 0) {
+        if (o.dense_block < 3 || o.dense_block > kMaxDenseK) {
+            msg = "dense_block must be 0 or 3.." + std::to_string(kMaxDenseK);
+            return QSX_ERR_BAD_ARG;
+        }
+        if (cfg.log2w != 3 || n_qubits < o.dense_block) {
+            msg = "dense blocks need >= k qubits and >= 8 columns per shard";
+            return QSX_ERR_BAD_ARG;
+        }
+        cfg.dense_k = o.dense_block;
+    }
+    if (cfg.dense_k > 0)
+        schedule_dense(plan);
+    else
+        schedule(plan);
     plan.stats.n_sweeps = plan.sweeps.size();
     serialize(plan);
     plan.stats.plan_host_ms =
@@ -786,7 +989,13 @@ std::string dump_plan_json(const Plan& plan) {
         PlannedSweep const& sw = plan.sweeps[s];
         os << (s ? "," : "") << "{\"tile_bits\":[";
         for (size_t i = 0; i < sw.tile_bits.size(); ++i) os << (i ? "," : "") << sw.tile_bits[i];
-        os << "],\"fixed_one\":" << sw.fixed_one << ",\"stages\":[";
+        os << "],\"dense\":{\"bits\":[";
+        for (size_t i = 0; i < sw.block_bits.size(); ++i) os << (i ? "," : "") << sw.block_bits[i];
+        os << "],\"gates\":[";
+        for (size_t i = 0; i < sw.block_ops.size(); ++i) os << (i ? "," : "") << plan.ops[sw.block_ops[i]].src_gate;
+        os << "],\"mat\":[";
+        for (size_t i = 0; i < sw.block_matrix.size(); ++i) os << (i ? "," : "") << sw.block_matrix[i];
+        os << "]},\"fixed_one\":" << sw.fixed_one << ",\"stages\":[";
         for (size_t t = 0; t < sw.stages.size(); ++t) {
             PlannedStage const& st = sw.stages[t];
             os << (t ? "," : "") << "{\"reg_bits\":[";

@@ -52,6 +52,10 @@ struct PlannedSweep {
     uint32_t fixed_one = 0;
     std::vector<PlannedStage> stages;
     double alg_bytes = 0;
+    // dense sweep (dense_block option): one 2^k x 2^k complex block applied on the tensor pipe
+    std::vector<int> block_bits;        // global row bit of component-index bit i (size k), empty = interpreted sweep
+    std::vector<double> block_matrix;   // complex, row-major, 2^k x 2^k
+    std::vector<int> block_ops;         // the ops folded into it (indices into Plan::ops)
 };
 
 struct PlanConfig {
@@ -64,7 +68,8 @@ struct PlanConfig {
     int  lookahead = 4096;
     bool fuse = true;
     bool fold_perms = true;  // fold X / CX / SWAP into the addressing of stage boundaries
-    bool defer_perms = false;  // never swap registers: an X-type op that cannot be hoisted ends the stage
+    bool defer_perms = false;
+    int  dense_k = 0;  // >= 3: fold the gate stream into dense k-qubit blocks (FP64 tensor pipe)  // never swap registers: an X-type op that cannot be hoisted ends the stage
     double snap_tol = 1e-15;
 };
 

@@ -15,6 +15,12 @@
 #pragma once
 #include <cstdint>
 
+#ifdef __CUDACC__
+#define QSX_HD __host__ __device__
+#else
+#define QSX_HD
+#endif
+
 namespace qsx {
 
 constexpr int kMaxRegBits  = 4;
@@ -23,7 +29,7 @@ constexpr int kMaxRowBits  = 26;
 
 // CTA size limit of sweep_kernel<R>: 2^R complex128 live in registers per thread, so the
 // R >= 3 instantiations are compiled for <= 512 threads (128 registers), the others for 1024.
-constexpr int max_threads_log2(int R) { return R >= 3 ? 9 : 10; }
+QSX_HD constexpr int max_threads_log2(int R) { return R >= 3 ? 9 : 10; }
 
 // semantic kinds of lowered gates (host side, planner + dumps)
 enum OpKind : int32_t {
@@ -129,10 +135,16 @@ struct alignas(16) DevSweep {
     int32_t  n_perms;
     int32_t  sp[kMaxTileBits];    // global row-bit position of tile-local bit l, ascending
     int32_t  outer[kMaxRowBits];  // global positions of the enumerated outer bits, ascending
-    int32_t  pad2[3];
-    // followed in memory by: DevStage stages[n_stages]; DevOp ops[n_ops]; DevPerm perms[n_perms];
-    // double pool[pool_doubles]
+    int32_t  dense_k;             // 0: interpreted sweep.  k >= 3: ONE dense 2^k x 2^k block (dense_kernel<k>)
+    int32_t  pad2[2];
+    // interpreted sweep: followed by DevStage stages[n_stages]; DevOp ops[n_ops]; DevPerm perms[n_perms];
+    //                    double pool[pool_doubles]
+    // dense sweep:       followed by int32 block_local[8] (tile-local position of block bit i = bit i of the
+    //                    component index); then the REAL form of the block matrix,
+    //                    A[(2c'+p')][(2c+p)] with p = 0 re / 1 im, 2^(k+1) rows of dense_lda(k) doubles
 };
+constexpr int kMaxDenseK = 5;
+QSX_HD constexpr int dense_lda(int k) { return (2 << k) + 2; }  // +2 doubles: conflict-free A fragments
 static_assert(sizeof(DevSweep) % 16 == 0, "DevSweep layout");
 
 }  // namespace qsx

@@ -32,18 +32,22 @@ def main():
         (1, 4, 10, 3, 8), (1, 4, 10, 3, 16), (1, 4, 10, 3, 48), (1, 4, 10, 3, 200),
         (1, 4, 9, 3, 48), (1, 4, 8, 3, 48), (1, 3, 9, 3, 48), (1, 3, 8, 3, 48), (1, 4, 6, 3, 48), (1, 3, 7, 4, 48),
     ]
-    qc = O.qcir_from_qasm_text(O.random_clifford_t_qasm(n, g, 20261019))
+    workload = sys.argv[4] if len(sys.argv) > 4 else "clifford_t"
+    text = O.random_rotation_qasm(n, g, 20261019) if workload == "rot" else O.random_clifford_t_qasm(n, g, 20261019)
+    qc = O.qcir_from_qasm_text(text)
     gs = O.gate_stream(qc)
-    print("n", n, "gates", g, flush=True)
+    print("n", n, "gates", g, workload, flush=True)
     for cfg in configs:
         fuse, R, tile, w, cap = cfg[:5]
         pol = cfg[5] if len(cfg) > 5 else 0
-        opt = Q.PlanOptions(fuse=fuse, reg_qubits=R, tile_qubits=tile, log2_tile_cols=w, max_ops_per_sweep=cap, no_perm_folding=pol)
+        dense = cfg[6] if len(cfg) > 6 else 0
+        opt = Q.PlanOptions(fuse=fuse, reg_qubits=R, tile_qubits=tile, log2_tile_cols=w, max_ops_per_sweep=cap, no_perm_folding=pol,
+                            dense_block=dense)
         try:
             r = time_plan(n, gs, opt)
         except Exception as e:  # noqa
             r = {"error": str(e)}
-        r.update(fuse=fuse, R=R, tile=tile, log2w=w, cap=cap, pol=pol)
+        r.update(fuse=fuse, R=R, tile=tile, log2w=w, cap=cap, pol=pol, dense=dense)
         print(json.dumps(r), flush=True)
     qft = O.gate_stream(O.qcir_from_qasm_text(O.qft_qasm(n)))
     print("qft", json.dumps(time_plan(n, qft, Q.PlanOptions(max_ops_per_sweep=128))), flush=True)

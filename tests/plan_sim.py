@@ -61,10 +61,32 @@ def apply_op(u, n, op):
     raise ValueError(kind)
 
 
+def apply_dense(u, n, bits, mat):
+    """Dense block: component-index bit i <-> global row bit bits[i]; mat = complex D x D row-major."""
+    k = len(bits)
+    D = 2**k
+    m = np.array(mat).reshape(D, D, 2)
+    m = m[..., 0] + 1j * m[..., 1]
+    rows = np.arange(2**n)
+    mask = sum(1 << b for b in bits)
+    base = rows[(rows & mask) == 0]
+    idx = []
+    for c in range(D):
+        off = sum(((c >> i) & 1) << bits[i] for i in range(k))
+        idx.append(base | off)
+    v = np.stack([u[i] for i in idx])  # (D, nbase, cols)
+    w = np.einsum("rc,cbn->rbn", m, v)
+    for c in range(D):
+        u[idx[c]] = w[c]
+
+
 def run_plan(dump, u):
     """Executes the SEMANTIC ops in scheduled order."""
     n = dump["n"]
     for sw in dump["sweeps"]:
+        if sw["dense"]["bits"]:
+            apply_dense(u, n, sw["dense"]["bits"], sw["dense"]["mat"])
+            continue
         for st in sw["stages"]:
             for op in st["pre"] + st["ops"] + st["post"]:
                 apply_op(u, n, op)
@@ -78,6 +100,9 @@ def run_plan_uops(dump, u):
     n = dump["n"]
     rows = np.arange(2**n)
     for sw in dump["sweeps"]:
+        if sw["dense"]["bits"]:
+            apply_dense(u, n, sw["dense"]["bits"], sw["dense"]["mat"])
+            continue
         for st in sw["stages"]:
             rb = st["reg_bits"]
             regidx = np.zeros(2**n, dtype=np.int64)
@@ -158,6 +183,12 @@ def check_invariants(dump, n_ops_expected=None):
     for sw in dump["sweeps"]:
         tb = sw["tile_bits"]
         assert tb == sorted(set(tb)) and all(0 <= b < n for b in tb)
+        if sw["dense"]["bits"]:
+            bits = sw["dense"]["bits"]
+            assert set(bits) <= set(tb) and len(set(bits)) == len(bits) and not sw["stages"]
+            assert len(sw["dense"]["mat"]) == 2 * 4 ** len(bits)
+            seen.extend(sw["dense"]["gates"])
+            continue
         assert len(tb) >= min(R, n)
         assert len(sw["stages"]) >= 1
         common = ~0

@@ -91,6 +91,25 @@ def test_schedule_preserves_the_unitary(n, g, seed, fuse):
         assert err < 1e-13, err
 
 
+@pytest.mark.parametrize("k", [3, 4, 5])
+def test_dense_block_folding_preserves_the_unitary(k):
+    """dense_block = k: the whole gate stream becomes dense 2^k x 2^k blocks (host products)."""
+    for n, g, seed in [(5, 120, 4), (7, 150, 6), (9, 300, 16)]:
+        qc = _rand_circuit(n, g, seed)  # seed 16 contains cccx / ccswap: wider than a k = 3 / 4 block
+        want = O.to_matrix_rowform(qc)
+        plan = Q.Plan(n, 2**n, O.gate_stream(qc), Q.PlanOptions(dense_block=k))
+        d, st = plan.dump(), plan.stats()
+        assert 0 < st.n_dense_blocks <= st.n_sweeps == len(d["sweeps"])
+        seen = plan_sim.check_invariants(d)
+        assert len(seen) == st.n_ops
+        got = plan_sim.run_plan_uops(d, np.eye(2**n, dtype=np.complex128))
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-13
+    with pytest.raises(Q.QsxError):
+        Q.Plan(5, 32, [], Q.PlanOptions(dense_block=2))
+    with pytest.raises(Q.QsxError):
+        Q.Plan(4, 16, [], Q.PlanOptions(dense_block=5))
+
+
 def test_snapping_is_optional_and_small():
     qc = O.qcir_from_qasm_text(O.random_clifford_t_qasm(4, 300, 9))
     want = O.to_matrix_rowform(qc)

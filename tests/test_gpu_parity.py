@@ -267,6 +267,21 @@ def test_inverse_circuit_roundtrip_at_full_size():
     assert np.max(np.abs(band - want)) < 1e-12
 
 
+@pytest.mark.parametrize("k", [3, 4, 5])
+def test_dense_blocks_on_the_tensor_pipe(k):
+    """dense_block = k: every sweep is one dense 2^k x 2^k block applied with DMMA (dense_kernel<k>)."""
+    for n, g, seed in [(5, 120, 4), (7, 200, 6), (9, 300, 16), (10, 200, 3)]:
+        qc = _rand_circuit(n, g, seed)
+        want = O.to_matrix_rowform(qc)
+        got = run_device(qc, Q.PlanOptions(dense_block=k))
+        assert frob_rel(got, want) < TOL, (k, n)
+    # column shard
+    qc = _rand_circuit(8, 150, 9)
+    want = O.to_matrix_rowform(qc)
+    got = run_device(qc, Q.PlanOptions(dense_block=k), 64, 64)
+    assert frob_rel(got, want[:, 64:128]) < TOL
+
+
 def test_n10_against_oracle_default_schedule():
     n = 10
     qc = O.qcir_from_qasm_text(O.random_clifford_t_qasm(n, 600, 123))
