@@ -563,6 +563,18 @@ __global__ void __launch_bounds__(256, 2)
     int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     int const g = lane >> 2, t = lane & 3;
     double* const tile_d = reinterpret_cast<double*>(tile);
+    // per-lane fragment offsets (in doubles, relative to the j base row), fixed for the whole launch
+    uint32_t boff[KB], ooff[RB];
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) {
+        int const kidx = 4 * kb + t;  // real component index = 2*c + part
+        boff[kb]       = (((comp_row[kidx >> 1] << 3) + g) << 1) + (kidx & 1);
+    }
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) {
+        int const ridx = rb * 8 + g;  // output real component = 2*c' + part'
+        ooff[rb]       = (((comp_row[ridx >> 1] << 3) + 2 * t) << 1) + (ridx & 1);
+    }
 
     for (uint32_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
         uint64_t const cb  = tile_id & ((1u << log2_ncb) - 1u);
@@ -571,9 +583,14 @@ __global__ void __launch_bounds__(256, 2)
         for (int k = 0; k < sw.n_outer; ++k) row_outer |= ((rc >> k) & 1u) << sw.outer[k];
         uint64_t const col = (cb << 3) + cw;
 
-        // ---- load the tile: 8 columns x 2^m rows, 128 B per row ----
-        for (int l = threadIdx.x >> 3; l < rows; l += blockDim.x >> 3)
-            tile[(l << 3) + cw] = __ldcg(u + ((size_t)(row_outer | growl[l]) << log2_ncols) + col);
+        // ---- load the tile: 8 columns x 2^m rows, 128 B per row; cp.async keeps every row of the
+        //      thread in flight at once without staging registers ----
+        for (int l = threadIdx.x >> 3; l < rows; l += blockDim.x >> 3) {
+            const double2* const src = u + ((size_t)(row_outer | growl[l]) << log2_ncols) + col;
+            uint32_t const dst       = (uint32_t)__cvta_generic_to_shared(tile + (l << 3) + cw);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
         __syncthreads();
 
         // ---- GEMM: each warp owns whole j's ----
@@ -587,12 +604,10 @@ __global__ void __launch_bounds__(256, 2)
                         jj >>= 1;
                     }
             }
+            double* const jbase = tile_d + ((size_t)base << 4);  // (row * 8 columns) * 2 doubles
             double bfrag[KB];
 #pragma unroll
-            for (int kb = 0; kb < KB; ++kb) {
-                int const kidx = 4 * kb + t;  // real component index = 2*c + part
-                bfrag[kb]      = tile_d[(((size_t)(base | comp_row[kidx >> 1]) << 3) + g) * 2 + (kidx & 1)];
-            }
+            for (int kb = 0; kb < KB; ++kb) bfrag[kb] = jbase[boff[kb]];
             double out[RB][2];
 #pragma unroll
             for (int rb = 0; rb < RB; ++rb) {
@@ -606,14 +621,13 @@ __global__ void __launch_bounds__(256, 2)
             __syncwarp();  // every lane has read its B fragments of this j
 #pragma unroll
             for (int rb = 0; rb < RB; ++rb) {
-                int const ridx    = rb * 8 + g;  // output real component = 2*c' + part'
-                double* const dst = tile_d + (((size_t)(base | comp_row[ridx >> 1]) << 3) + 2 * t) * 2 + (ridx & 1);
-                dst[0]            = out[rb][0];  // column 2t
-                dst[2]            = out[rb][1];  // column 2t + 1
+                jbase[ooff[rb]]     = out[rb][0];  // column 2t
+                jbase[ooff[rb] + 2] = out[rb][1];  // column 2t + 1
             }
         }
         __syncthreads();
 
+#pragma unroll 8
         for (int l = threadIdx.x >> 3; l < rows; l += blockDim.x >> 3)
             __stcg(u + ((size_t)(row_outer | growl[l]) << log2_ncols) + col, tile[(l << 3) + cw]);
         __syncthreads();  // the tile buffer is reused by the next iteration
