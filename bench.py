@@ -127,7 +127,8 @@ def run_ours(args):
     n, desc, qc_a, qc_b, gs_a, gs_b = build_workload(args.workload)
     dim = 2**n
     col0, ncols = sharding.shard_columns(n, rank, world)
-    opt = Q.PlanOptions(max_ops_per_sweep=args.cap, tile_qubits=args.tile, reg_qubits=args.reg, log2_tile_cols=args.log2w)
+    opt = Q.PlanOptions(max_ops_per_sweep=args.cap, tile_qubits=args.tile, reg_qubits=args.reg, log2_tile_cols=args.log2w,
+                        dense_block=args.dense)
 
     stream = torch.cuda.ExternalStream(abi.device_stream(local), device=torch.device("cuda", local))
     ua = Q.Unitary(n, local, col0, ncols)
@@ -276,7 +277,8 @@ def run_ours(args):
                 "l2": "unitary shard per GPU is %.0f MiB; L2 is 126 MB: %s" % (
                     16 * dim * ncols / 2**20, "inputs larger than L2" if 16 * dim * ncols > 126e6 else "shard fits in L2 (strong scaling), no flush"),
                 "schedule": {"sweeps_A": st_a.n_sweeps, "stages_A": st_a.n_stages, "micro_ops_A": st_a.n_micro_ops,
-                             "max_ops_per_sweep": args.cap, "tile_qubits": args.tile, "reg_qubits": args.reg},
+                             "max_ops_per_sweep": args.cap, "tile_qubits": args.tile, "reg_qubits": args.reg,
+                             "dense_block": args.dense, "dense_blocks_A": st_a.n_dense_blocks},
             },
             "construct_ms_A": round(sweep_ms, 4),
             "equiv_ms": round(equiv_ms, 4),
@@ -286,7 +288,7 @@ def run_ours(args):
             "e2e": {"value": round(e2e_value, 2), "unit": "GB/s", "ms_per_step": round(e2e_s * 1e3, 4),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64,
                     "note": "host gate arrays -> qsx_apply_gates (schedule + program upload + sweeps) x2 -> qsx_equiv_partial -> verdict"},
-            "roofline": {"bound": "hbm", "kernel": "sweep_kernel<%d>" % args.reg, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": ("dense_kernel<%d>" % args.dense) if args.dense else ("sweep_kernel<%d>" % args.reg), "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": st_a.alg_bytes_per_run / max(st_a.n_sweeps, 1),
                          "launches": st_a.n_sweeps, "avg_launch_us": round(sweep_ms * 1e3 / max(st_a.n_sweeps, 1), 2)},
@@ -415,6 +417,7 @@ def main():
     ap.add_argument("--tile", type=int, default=9)
     ap.add_argument("--reg", type=int, default=4)
     ap.add_argument("--log2w", type=int, default=3)
+    ap.add_argument("--dense", type=int, default=0, help="fold the gate stream into dense k-qubit blocks on the FP64 tensor pipe (3..5)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
