@@ -21,8 +21,13 @@ SHIM      := bin/qsyn-b200
 HOSTHDRS  := $(wildcard $(HOST)/*/*.hpp) include/qsx.h
 
 FP64PEAK  := bin/fp64_peak
+BCAST     := bin/bcast_probe
 
-all: $(LIBQSX) $(SHIM) $(FP64PEAK)
+all: $(LIBQSX) $(SHIM) $(FP64PEAK) $(BCAST)
+
+$(BCAST): $(CSRC)/tools/bcast_probe.cu
+	@mkdir -p bin
+	$(NVCC) -O3 -std=c++20 -lineinfo $(ARCH) -o $@ $<
 
 $(FP64PEAK): $(CSRC)/tools/fp64_peak.cu
 	@mkdir -p bin
