@@ -303,13 +303,18 @@ def run_ours(args):
 
 
 def _plan_blob_bytes(plan):
-    # program bytes uploaded per qsx_apply_gates call: 192 B header + 80 B/stage + 96 B/micro-op (+ tables)
+    # program bytes uploaded per qsx_apply_gates call (program.hpp): 192 B header + 160 B/stage +
+    # 96 B/micro-op (+ tables, 48 B per scalar entry) + 16 B per folded permutation step
     d = plan.dump()
     total = 0
     for sw in d["sweeps"]:
         total += 192
+        if sw["dense"]["bits"]:
+            k = len(sw["dense"]["bits"])
+            total += 32 + 8 * (2 << k) * ((2 << k) + 2)
         for st in sw["stages"]:
-            total += 80 + sum(96 + 8 * len(u["table"]) for u in st["uops"])
+            total += 160 + sum(96 + 8 * len(u["table"]) + 48 * len(u["scalars"]) for u in st["uops"])
+            total += 16 * sum(3 if op["kind"] == "SWAP" else 1 for op in st["pre"] + st["post"])
         total = (total + 255) // 256 * 256
     return total
 

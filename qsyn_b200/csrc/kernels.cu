@@ -189,7 +189,8 @@ __device__ __forceinline__ void op_dtab_half(double2 (&e)[1 << R], const double2
 // stall reason).  A sweep that needs any other handler runs in the LEAN = false instantiation.
 __host__ __device__ constexpr bool is_common_handler(int h) {
     return (h >= H_H && h < H_H + 4) || (h >= H_X && h < H_X + 4) || (h >= H_XC && h < H_XC + 16) ||
-           (h >= H_U1 && h < H_U1 + 4) || (h >= H_DTABH && h < H_DTABH + 4) || h == H_DTABF || h == H_SCALN;
+           (h >= H_U1 && h < H_U1 + 4) || (h >= H_DTABH && h < H_DTABH + 4) || h == H_DTABF || h == H_SCALN ||
+           (h >= H_PHJ && h < H_PHJ + 4);
 }
 
 // One handler = one straight-line body; everything about it is known at compile time.
@@ -224,6 +225,14 @@ __device__ __forceinline__ void run_handler(double2 (&e)[1 << R], double2& scal,
     } else if constexpr (H >= H_DTABH && H < H_DTABH + 4) {
         constexpr int J = H - H_DTABH;
         if constexpr (J < R) op_dtab_half<R, J>(e, reinterpret_cast<const double2*>(pool + pool_off));
+    } else if constexpr (H >= H_PHJ && H < H_PHJ + 4) {
+        constexpr int J = H - H_PHJ;
+        if constexpr (J < R) {
+            double2 const w = make_double2(c[0], c[1]);
+#pragma unroll
+            for (int i = 0; i < (1 << R); ++i)
+                if ((i >> J) & 1) e[i] = cmul(e[i], w);
+        }
     } else if constexpr (H == H_DTABF) {
         const double2* const tab = reinterpret_cast<const double2*>(pool + pool_off);
 #pragma unroll
@@ -279,6 +288,10 @@ __device__ __forceinline__ void apply_op(double2 (&e)[1 << R], double2& scal, co
         QSX_CASE8(72)
         QSX_CASE8(80)
         QSX_CASE(88)
+        QSX_CASE(89)
+        QSX_CASE(90)
+        QSX_CASE(91)
+        QSX_CASE(92)
         default: break;
     }
 }
@@ -358,17 +371,22 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), 1)
         // this thread's rows: tile-local index (register bits = 0) and the global row it maps to
         uint32_t lbase = 0, grow = row_outer;
         {
+            // fixed trip count, independent loads (positions precomputed by the scheduler): one
+            // shared-memory latency per stage instead of a chain of dependent ones
             int const n_t = st->n_t;
-            for (int k = 0; k < n_t; ++k) {
-                int const l      = st->tl[k];
-                uint32_t const b = (trow >> k) & 1u;
-                lbase |= b << l;
-                grow |= b << sw->sp[l];
+#pragma unroll
+            for (int k = 0; k < kMaxTileBits; ++k) {
+                uint32_t const b = k < n_t ? ((trow >> k) & 1u) : 0u;
+                lbase |= b << st->tl[k];
+                grow |= b << st->tg[k];
             }
         }
-        int rl[R];
+        int rl[R], rg[R];
 #pragma unroll
-        for (int j = 0; j < R; ++j) rl[j] = st->rl[j];
+        for (int j = 0; j < R; ++j) {
+            rl[j] = st->rl[j];
+            rg[j] = st->rg[j];
+        }
 
         if (s == 0) {
             // global load; X-type ops scheduled before the first register op are folded into the addresses
@@ -376,7 +394,7 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), 1)
             int const pb = st->pre_begin, pe = st->pre_end;
             if (pb == pe) {
 #pragma unroll
-                for (int j = 0; j < R; ++j) gc[j] = 1u << sw->sp[rl[j]];
+                for (int j = 0; j < R; ++j) gc[j] = 1u << rg[j];
             } else {
                 uint32_t rows[R + 1];
                 rows[0] = lbase;
@@ -436,7 +454,7 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), 1)
             if (qb == qe) {
                 gb = grow;
 #pragma unroll
-                for (int j = 0; j < R; ++j) gc[j] = 1u << sw->sp[rl[j]];
+                for (int j = 0; j < R; ++j) gc[j] = 1u << rg[j];
             } else {
                 gb = row_outer | deposit_tile_bits(rows[0], sw->sp, m);
 #pragma unroll

@@ -439,7 +439,16 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
                     if (((active >> i) & 1u) && !((i >> j) & 1)) ok = false;
                 if (ok) half = j;
             }
-            if (half >= 0) {
+            bool uniform = half >= 0;  // every entry of the half-table equal -> one scalar instead of a table
+            for (int i = 0; uniform && i < E; ++i)
+                if ((i >> half) & 1)
+                    uniform = g.tab[i].re == g.tab[1 << half].re && g.tab[i].im == g.tab[1 << half].im;
+            if (uniform) {
+                u.kind = K_PHJ;
+                u.j0   = half;
+                u.c[0] = g.tab[1 << half].re;
+                u.c[1] = g.tab[1 << half].im;
+            } else if (half >= 0) {
                 u.kind = K_DTABH;
                 u.j0   = half;
                 for (int i = 0; i < E; ++i)
@@ -737,6 +746,7 @@ int handler_of(MicroOp const& u) {
         case K_DTABH: return H_DTABH + u.j0;
         case K_DTABF: return H_DTABF;
         case K_SCALN: return H_SCALN;
+        case K_PHJ: return H_PHJ + u.j0;
         default: return H_SAPPLY;
     }
 }
@@ -842,8 +852,12 @@ void serialize(Plan& plan) {
             }
             int nt = 0;
             for (int l = 0; l < m; ++l)
-                if (!((regmask_local >> l) & 1u)) ds.tl[nt++] = l;
+                if (!((regmask_local >> l) & 1u)) {
+                    ds.tg[nt]   = sw.tile_bits[l];
+                    ds.tl[nt++] = l;
+                }
             ds.n_t = nt;
+            for (int j = 0; j < ds.r; ++j) ds.rg[j] = st.reg_bits[j];
             for (MicroOp const& mo : st.uops) {
                 DevOp d;
                 std::memset(&d, 0, sizeof(d));
@@ -1021,7 +1035,7 @@ std::string dump_plan_json(const Plan& plan) {
                 for (size_t k = 0; k < op.mat.size(); ++k) os << (k ? "," : "") << op.mat[k];
                 os << "]}";
             }
-            static char const* const kMicro[] = {"U1", "H", "X", "AD", "XC", "SWAP", "U2", "DSCAL", "DTABH", "DTABF", "SAPPLY", "SCALN"};
+            static char const* const kMicro[] = {"U1", "H", "X", "AD", "XC", "SWAP", "U2", "DSCAL", "DTABH", "DTABF", "SAPPLY", "SCALN", "PHJ"};
             os << "],\"uops\":[";
             for (size_t i = 0; i < st.uops.size(); ++i) {
                 MicroOp const& u = st.uops[i];

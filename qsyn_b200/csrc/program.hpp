@@ -58,6 +58,7 @@ enum MicroKind : int32_t {
     K_DTABH  = 8,   // e[i] *= tab[i without bit j0] for the 8 (2^(R-1)) elements with bit j0 set; table at pool
     K_DTABF  = 9,   // e[i] *= tab[i] for all 2^R elements; table at pool
     K_SAPPLY = 10,  // e[i] *= s for all i ; s = 1
+    K_PHJ    = 12,  // e[i] *= w for the elements with register bit j0 set (a K_DTABH whose entries are all equal)
     K_SCALN  = 11,  // all per-thread scalars of a stage in one micro-op: for k < j0 entries at pool
                     // {cother, czero, sel, pad, d0.re, d0.im, d1.re, d1.im} (48 B each):
                     //   s *= pass ? (sel >= 0 && row bit sel ? d1 : d0) : 1 ; then e[i] *= s
@@ -84,7 +85,8 @@ enum Handler : int32_t {
     H_DTABF  = 86,
     H_SAPPLY = 87,
     H_SCALN  = 88,
-    H_COUNT  = 89,
+    H_PHJ    = 89,  // +J
+    H_COUNT  = 93,
 };
 
 // Thread-level predicate of every micro-op: (row & cother) == cother && (row & czero) == 0, where
@@ -121,6 +123,8 @@ struct alignas(16) DevStage {
     int32_t pad;
     int32_t pre_begin, pre_end;   // permutation steps applied at this stage's LOAD (stage 0 only: global load)
     int32_t post_begin, post_end; // permutation steps applied at this stage's STORE
+    int32_t rg[kMaxRegBits];      // GLOBAL row-bit position of register bit j   (= sp[rl[j]], precomputed)
+    int32_t tg[kMaxTileBits + 1]; // GLOBAL row-bit position of thread-row bit k (= sp[tl[k]], precomputed)
 };
 static_assert(sizeof(DevStage) % 16 == 0, "DevStage layout");
 

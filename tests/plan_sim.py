@@ -145,6 +145,10 @@ def run_plan_uops(dump, u):
                     tab = tab[:, 0] + 1j * tab[:, 1]
                     assert len(tab) == 2 ** len(rb)
                     u[tsel] *= tab[regidx[tsel]][:, None]
+                elif k == "PHJ":
+                    j = uop["j0"]
+                    sel = tsel & (((regidx >> j) & 1) == 1)
+                    u[sel] *= complex(c[0], c[1])
                 elif k == "DTABH":
                     j = uop["j0"]
                     tab = np.array(uop["table"]).reshape(-1, 2)
