@@ -23,7 +23,18 @@ HOSTHDRS  := $(wildcard $(HOST)/*/*.hpp) include/qsx.h
 FP64PEAK  := bin/fp64_peak
 BCAST     := bin/bcast_probe
 
-all: $(LIBQSX) $(SHIM) $(FP64PEAK) $(BCAST)
+LIBHOST   := $(LIBDIR)/libqsxhost.so
+
+all: $(LIBQSX) $(LIBHOST) $(SHIM) $(FP64PEAK) $(BCAST)
+
+$(OBJDIR)/host_%.o: $(HOST)/capi/%.cpp $(HOSTHDRS) include/qsx_host.h
+	@mkdir -p $(OBJDIR)
+	$(CXX) $(HOSTFLAGS) -c $< -o $@
+
+# C ABI of the host layer (include/qsx_host.h) for non-C++ callers (tests, bench.py)
+$(LIBHOST): $(OBJDIR)/host_qcir_io.o $(OBJDIR)/host_qcir_to_tensor.o $(OBJDIR)/host_qsx_host.o $(LIBQSX)
+	$(CXX) -shared -o $@ $(OBJDIR)/host_qcir_io.o $(OBJDIR)/host_qcir_to_tensor.o $(OBJDIR)/host_qsx_host.o \
+	    -L$(LIBDIR) -lqsx -Wl,-rpath,'$$ORIGIN'
 
 $(BCAST): $(CSRC)/tools/bcast_probe.cu
 	@mkdir -p bin

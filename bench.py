@@ -33,29 +33,19 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = {
-    # name: (n_qubits, generator, n_gates, seed, description)   -- SURVEY.md 8(d) C2..C5
-    "c2": (12, "clifford_t", 2000, 20261019, "C2: 12-qubit random Clifford+T, 2000 gates (256 MiB unitary)"),
-    "c3": (14, "qft", 105, 0, "C3: 14-qubit QFT (benchmark/qft generator), 105 gates (4 GiB unitary)"),
-    "c4": (15, "clifford_t", 10000, 20261020, "C4: 15-qubit random Clifford+T, 10000 gates (16 GiB unitary)"),
-    "c5": (16, "clifford_t", 10000, 20261021, "C5: 16-qubit random Clifford+T, 10000 gates (64 GiB unitary)"),
-    "tiny": (8, "clifford_t", 400, 7, "tiny: 8-qubit random Clifford+T, 400 gates (smoke)"),
-}
-
-
 def build_workload(name):
-    """Circuits A and B as gate streams.  Uses the oracle ONLY as the synthetic-input generator +
-    QASM/gate-matrix front end of the checker side; the timed product path receives plain
-    (n_ctrls, qubits, matrix) arrays through the C ABI."""
-    from oracle import oracle as O
+    """Circuits A and B of the verification job through the PRODUCT's own front end: the synthetic
+    QASM text (qsyn_b200.workloads) is parsed and lowered by the C++ host layer (libqsxhost.so:
+    qsyn-shaped QASM reader, QCir, per-gate matrices with the reference formulas).  B = A followed
+    by t,x,t,x on qubit 0 (Equivalent, global phase pi/4).  Nothing here touches oracle/."""
+    from qsyn_b200 import host, workloads
 
-    n, gen, g, seed, desc = WORKLOADS[name]
-    text = O.random_clifford_t_qasm(n, g, seed) if gen == "clifford_t" else O.qft_qasm(n)
-    qc_a = O.qcir_from_qasm_text(text)
-    qc_b = O.qcir_from_qasm_text(text)
+    n, desc, text = workloads.workload_qasm(name)
+    ca = host.Circuit(qasm_text=text)
+    cb = host.Circuit(qasm_text=text)
     for nm in "txtx":
-        qc_b.append(O.str_to_operation(nm), [0])
-    return n, desc, qc_a, qc_b, O.gate_stream(qc_a), O.gate_stream(qc_b)
+        cb.append(nm, [0])
+    return n, desc, ca, cb
 
 
 # ------------------------------------------------------------------------------------------
@@ -124,7 +114,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    n, desc, qc_a, qc_b, gs_a, gs_b = build_workload(args.workload)
+    n, desc, circ_a, circ_b = build_workload(args.workload)
+    gs_a, gs_b = circ_a.gate_array(), circ_b.gate_array()  # (qsx_gate*, count): host buffers of the C ABI
     dim = 2**n
     col0, ncols = sharding.shard_columns(n, rank, world)
     opt = Q.PlanOptions(max_ops_per_sweep=args.cap, tile_qubits=args.tile, reg_qubits=args.reg, log2_tile_cols=args.log2w,
@@ -153,10 +144,9 @@ def run_ours(args):
         launches["n"] += 2 + ra.launches + rb.launches + 2
         return Q.equiv_finish(sums, 1e-6, False)
 
-    # host-side input buffers of the C ABI (array of qsx_gate + matrices), built once
+    # host-side input buffers of the C ABI (array of qsx_gate + matrices, owned by the host-layer circuits)
     import ctypes as C
-    arr_a, keep_a, na = abi.pack_gates(gs_a)
-    arr_b, keep_b, nb = abi.pack_gates(gs_b)
+    (arr_a, na), (arr_b, nb) = gs_a, gs_b
     null_stop = C.cast(None, abi.STOP_FN)
 
     def step_e2e():
@@ -271,7 +261,7 @@ def run_ours(args):
             "config": {
                 "workload": desc,
                 "n_qubits": n,
-                "gates_A": len(gs_a), "gates_B": len(gs_b),
+                "gates_A": na, "gates_B": nb,
                 "columns_per_gpu": ncols,
                 "step": "identity+construct A, identity+construct B, fused equiv + host finish (verdict Equivalent, phase pi/4)",
                 "l2": "unitary shard per GPU is %.0f MiB; L2 is 126 MB: %s" % (
@@ -341,7 +331,10 @@ def cpu_reference_sample(workload: str, n_gates: int):
     from oracle import oracle as O
     from oracle import oracle_c
 
-    n, desc, qc_a, _, _, _ = build_workload(workload)
+    from qsyn_b200 import workloads
+
+    n, desc, text = workloads.workload_qasm(workload)
+    qc_a = O.qcir_from_qasm_text(text)
     sub = O.QCir(n)
     for g in qc_a.topological_order()[:n_gates]:
         sub.append(g.op, g.qubits)
@@ -359,6 +352,8 @@ def cpu_reference_sample(workload: str, n_gates: int):
 
 
 def cpu_baseline(workload: str, budget_s: float = 20.0):
+    from qsyn_b200.workloads import WORKLOADS
+
     n = WORKLOADS[workload][0]
     # measured ballpark: ~0.18 s per gate at n=12, x4 per extra qubit
     per_gate = 0.18 * 4.0 ** (n - 12)
@@ -378,6 +373,8 @@ def cpu_baseline(workload: str, budget_s: float = 20.0):
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm (oracle port; the reference binary cannot be
     built here: xtensor/xtensor-blas/OpenBLAS are not vendored) on the host cores."""
+    from qsyn_b200.workloads import WORKLOADS
+
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -416,7 +413,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "tiny"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cap", type=int, default=96, help="max ops per sweep")
     ap.add_argument("--tile", type=int, default=9)

@@ -151,8 +151,13 @@ def pack_gates(gates: Iterable[tuple]):
 
 
 class Plan:
-    def __init__(self, n_qubits: int, ncols: int, gates: Iterable[tuple], options: PlanOptions | None = None):
-        arr, keep, n = pack_gates(gates)
+    def __init__(self, n_qubits: int, ncols: int, gates, options: PlanOptions | None = None):
+        """gates: iterable of (n_ctrls, qubits, matrix) tuples, or a (qsx_gate pointer, count) pair
+        as returned by qsyn_b200.host.Circuit.gate_array()."""
+        if isinstance(gates, tuple) and len(gates) == 2 and isinstance(gates[1], int):
+            arr, n = gates
+        else:
+            arr, keep, n = pack_gates(gates)
         self._h = C.c_void_p()
         _check(lib().qsx_plan_create(n_qubits, ncols, arr, n, C.byref(options) if options is not None else None,
                                      C.byref(self._h)))

@@ -1,0 +1,216 @@
+// qsx_host.cpp -- C ABI over the C++ host layer (include/qsx_host.h).
+#include "../../../include/qsx_host.h"
+
+#include <cstring>
+#include <format>
+#include <sstream>
+#include <string>
+
+#include "../convert/qcir_to_tensor.hpp"
+#include "../qcir/qcir.hpp"
+#include "../tensor/qtensor.hpp"
+
+// the embedding application owns cancellation (qsyn: SIGINT -> jthread stop token); a library user
+// that has none links this weak default
+__attribute__((weak)) bool stop_requested() { return false; }
+
+struct qsxh_circuit {
+    qsyn::qcir::QCir qcir;
+    std::optional<qsyn::GateStream> stream;  // rebuilt lazily after a modification
+};
+struct qsxh_tensor {
+    qsyn::tensor::QTensor<double> tensor;
+};
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, std::string msg) {
+    g_err = std::move(msg);
+    return code;
+}
+template <typename F>
+int guarded(F f) {
+    try {
+        return f();
+    } catch (std::bad_alloc const&) {
+        return fail(QSX_ERR_OOM, "Memory allocation failed!!");
+    } catch (std::invalid_argument const& e) {
+        return fail(QSX_ERR_SHAPE, e.what());
+    } catch (std::exception const& e) {
+        return fail(QSX_ERR_CUDA, e.what());
+    }
+}
+}  // namespace
+
+extern "C" {
+
+const char* qsxh_last_error(void) { return g_err.c_str(); }
+
+int qsxh_circuit_new(size_t n_qubits, qsxh_circuit** out) {
+    if (out == nullptr) return fail(QSX_ERR_BAD_ARG, "null out-pointer");
+    *out = new qsxh_circuit{qsyn::qcir::QCir(n_qubits), std::nullopt};
+    return QSX_OK;
+}
+
+int qsxh_circuit_from_qasm_text(const char* text, qsxh_circuit** out) {
+    if (text == nullptr || out == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    return guarded([&] {
+        std::istringstream in{std::string(text)};
+        auto qc = qsyn::qcir::from_qasm_stream(in, "<text>");
+        if (!qc.has_value()) return fail(QSX_ERR_BAD_ARG, "the QASM text has something wrong!!");
+        *out = new qsxh_circuit{std::move(*qc), std::nullopt};
+        return (int)QSX_OK;
+    });
+}
+
+int qsxh_circuit_from_qasm_file(const char* path, qsxh_circuit** out) {
+    if (path == nullptr || out == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    return guarded([&] {
+        auto qc = qsyn::qcir::from_qasm(path);
+        if (!qc.has_value()) return fail(QSX_ERR_BAD_ARG, std::format("the format in \"{}\" has something wrong!!", path));
+        *out = new qsxh_circuit{std::move(*qc), std::nullopt};
+        return (int)QSX_OK;
+    });
+}
+
+int qsxh_circuit_append(qsxh_circuit* c, const char* gate, const char* phase, const size_t* qubits, size_t n_qubits) {
+    if (c == nullptr || gate == nullptr || (n_qubits > 0 && qubits == nullptr)) return fail(QSX_ERR_BAD_ARG, "null argument");
+    return guarded([&] {
+        std::vector<dvlab::Phase> params;
+        if (phase != nullptr) {
+            auto const ph = dvlab::Phase::from_string(phase);
+            if (!ph.has_value()) return fail(QSX_ERR_BAD_ARG, std::format("invalid phase \"{}\"!!", phase));
+            params.push_back(*ph);
+        }
+        auto const op = qsyn::qcir::str_to_operation(gate, params);
+        if (!op.has_value()) return fail(QSX_ERR_BAD_ARG, std::format("Invalid gate type {}!!", gate));
+        qsyn::QubitIdList ids(qubits, qubits + n_qubits);
+        if (op->get_num_qubits() != ids.size() || !qsyn::qcir::QCirGate::qubit_id_is_unique(ids))
+            return fail(QSX_ERR_BAD_ARG, std::format("Gate {} requires {} distinct qubits", gate, op->get_num_qubits()));
+        for (auto q : ids)
+            if (q >= c->qcir.get_num_qubits()) return fail(QSX_ERR_BAD_ARG, std::format("Qubit ID {} does not exist!!", q));
+        c->qcir.append(*op, ids);
+        c->stream.reset();
+        return (int)QSX_OK;
+    });
+}
+
+int qsxh_circuit_info(const qsxh_circuit* c, size_t* n_qubits, size_t* n_gates) {
+    if (c == nullptr) return fail(QSX_ERR_BAD_ARG, "null circuit");
+    if (n_qubits != nullptr) *n_qubits = c->qcir.get_num_qubits();
+    if (n_gates != nullptr) *n_gates = c->qcir.get_num_gates();
+    return QSX_OK;
+}
+
+int qsxh_circuit_gate_repr(qsxh_circuit* c, size_t i, char* buf, size_t buf_size, size_t* gate_id) {
+    if (c == nullptr) return fail(QSX_ERR_BAD_ARG, "null circuit");
+    auto const& gates = c->qcir.get_gates();
+    if (i >= gates.size()) return fail(QSX_ERR_BAD_ARG, "gate index out of range");
+    std::string const r = gates[i]->get_operation().get_repr();
+    if (buf != nullptr && buf_size > 0) {
+        size_t const k = std::min(buf_size - 1, r.size());
+        std::memcpy(buf, r.data(), k);
+        buf[k] = '\0';
+    }
+    if (gate_id != nullptr) *gate_id = gates[i]->get_id();
+    return QSX_OK;
+}
+
+int qsxh_circuit_gate_stream(qsxh_circuit* c, const qsx_gate** gates, size_t* n_gates) {
+    if (c == nullptr || gates == nullptr || n_gates == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    return guarded([&] {
+        if (!c->stream.has_value()) {
+            c->stream = qsyn::to_gate_stream(c->qcir);
+            if (!c->stream.has_value()) return fail(QSX_ERR_UNSUPPORTED, "Conversion of a gate to Tensor is not supported yet!!");
+        }
+        *gates   = c->stream->gates.data();
+        *n_gates = c->stream->gates.size();
+        return (int)QSX_OK;
+    });
+}
+
+int qsxh_circuit_destroy(qsxh_circuit* c) {
+    delete c;
+    return QSX_OK;
+}
+
+int qsxh_qc2ts(const qsxh_circuit* c, qsxh_tensor** out) {
+    if (c == nullptr || out == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    return guarded([&] {
+        if (c->qcir.get_num_qubits() == 0) return fail(QSX_ERR_BAD_ARG, "QCir is empty!!");
+        auto t = qsyn::to_tensor(c->qcir);  // conversion_cmd.cpp:86
+        if (!t.has_value()) return fail(QSX_ERR_UNSUPPORTED, "conversion failed (see the log)");
+        *t   = t->to_matrix();              // conversion_cmd.cpp:89
+        t->set_filename(c->qcir.get_filename());
+        t->add_procedures(c->qcir.get_procedures());
+        t->add_procedure("QC2TS");
+        *out = new qsxh_tensor{std::move(*t)};
+        return (int)QSX_OK;
+    });
+}
+
+int qsxh_tensor_shape(const qsxh_tensor* t, size_t* dims, size_t max_dims, size_t* n_dims) {
+    if (t == nullptr || n_dims == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    auto const s = t->tensor.shape();
+    *n_dims      = s.size();
+    for (size_t i = 0; i < s.size() && i < max_dims && dims != nullptr; ++i) dims[i] = s[i];
+    return QSX_OK;
+}
+
+int qsxh_tensor_download(const qsxh_tensor* t, double* out, size_t n_doubles) {
+    if (t == nullptr || out == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    return guarded([&] {
+        auto const v = t->tensor.host_elements();
+        if (n_doubles != 2 * v.size()) return fail(QSX_ERR_BAD_ARG, "buffer size mismatch");
+        std::memcpy(out, v.data(), sizeof(double) * n_doubles);
+        return (int)QSX_OK;
+    });
+}
+
+int qsxh_tensor_adjoint_inplace(qsxh_tensor* t) {
+    if (t == nullptr) return fail(QSX_ERR_BAD_ARG, "null tensor");
+    return guarded([&] {
+        t->tensor.adjoint_inplace();
+        return (int)QSX_OK;
+    });
+}
+
+int qsxh_tensor_equiv(const qsxh_tensor* t1, const qsxh_tensor* t2, double eps, int strict, qsx_equiv_result* result, char* text,
+                      size_t text_size) {
+    if (t1 == nullptr || t2 == nullptr) return fail(QSX_ERR_BAD_ARG, "null tensor");
+    return guarded([&] {
+        using namespace qsyn::tensor;
+        std::string msg;
+        qsx_equiv_result r{};
+        double s[8];
+        if (!equivalence_sums(t1->tensor, t2->tensor, s)) {
+            auto fmt_shape = [](std::vector<size_t> const& sh) {
+                std::string o = "[";
+                for (size_t i = 0; i < sh.size(); ++i) o += (i ? ", " : "") + std::to_string(sh[i]);
+                return o + "]";
+            };
+            msg = std::format("Not Equivalent\n- Shape Mismatch: {} vs {}\n", fmt_shape(t1->tensor.shape()), fmt_shape(t2->tensor.shape()));
+        } else {
+            qsx_equiv_finish(s, eps, strict, &r);
+            if (r.equivalent)
+                msg = std::format("Equivalent\n- Global Norm : {:.6}\n- Global Phase: {}\n", r.norm,
+                                  dvlab::Phase(r.phase_num, r.phase_den).get_print_string());
+            else
+                msg = std::format("Not Equivalent\n- Cosine Similarity: {:.6}\n", r.cosine);
+        }
+        if (result != nullptr) *result = r;
+        if (text != nullptr && text_size > 0) {
+            size_t const k = std::min(text_size - 1, msg.size());
+            std::memcpy(text, msg.data(), k);
+            text[k] = '\0';
+        }
+        return (int)QSX_OK;
+    });
+}
+
+int qsxh_tensor_destroy(qsxh_tensor* t) {
+    delete t;
+    return QSX_OK;
+}
+
+}  // extern "C"

@@ -123,6 +123,27 @@ int stop_trampoline(void*) { return stop_requested() ? 1 : 0; }
 
 }  // namespace
 
+std::optional<GateStream> to_gate_stream(QCir const& qcir) {
+    GateStream gs;
+    gs.gates.reserve(qcir.get_num_gates());
+    gs.matrices.reserve(qcir.get_num_gates());
+    for (auto const& gate : qcir.get_gates()) {
+        auto g = lower_to_stream(gate->get_operation());
+        if (!g.has_value() || gate->get_num_qubits() > QSX_MAX_GATE_QUBITS) {
+            spdlog::error("Conversion of Gate {} ({}) to Tensor is not supported yet!!", gate->get_id(), gate->get_operation().get_repr());
+            return std::nullopt;
+        }
+        gs.matrices.push_back(std::move(g->matrix));
+        qsx_gate d{};
+        d.n_ctrls   = static_cast<int32_t>(g->n_ctrls);
+        d.n_targets = static_cast<int32_t>(g->n_targets);
+        for (size_t p = 0; p < gate->get_num_qubits(); ++p) d.qubits[p] = static_cast<int32_t>(gate->get_qubit(p));
+        d.matrix = gs.matrices.back().data();  // heap storage: stable when the outer vector grows
+        gs.gates.push_back(d);
+    }
+    return gs;
+}
+
 template <>
 std::optional<QTensor<double>> to_tensor(QCir const& qcir) try {
     if (qcir.get_num_qubits() == 0) {

@@ -9,6 +9,16 @@ using namespace qsyn::qcir;
 
 namespace qsyn {
 
+// The ordered gate stream the device consumes (include/qsx.h): one entry per gate of
+// QCir::get_gates(), controls peeled off so that only the 2^t x 2^t TARGET matrix (built with the
+// reference formulas) crosses the ABI.  `gates[i].matrix` points into `matrices[i]`.
+struct GateStream {
+    std::vector<qsx_gate> gates;
+    std::vector<std::vector<double>> matrices;
+};
+// nullopt + error log if a gate has no tensor form (qcir_to_tensor.cpp:180-183 of the reference)
+std::optional<GateStream> to_gate_stream(qsyn::qcir::QCir const& qcir);
+
 std::optional<qsyn::tensor::QTensor<double>> to_tensor(QCirGate const& gate);
 template <>
 std::optional<qsyn::tensor::QTensor<double>> to_tensor(QCir const& qcir);

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstddef>
 #include <filesystem>
+#include <istream>
 #include <format>
 #include <memory>
 #include <optional>
@@ -417,6 +418,7 @@ private:
 
 // QASM 2.0 reader with the reference's behaviour (qcir_reader.cpp:47-120)
 std::optional<QCir> from_qasm(std::filesystem::path const& filepath);
+std::optional<QCir> from_qasm_stream(std::istream& in, std::string const& name_for_messages);
 std::optional<QCir> from_file(std::filesystem::path const& filepath);
 
 }  // namespace qcir

@@ -91,13 +91,18 @@ std::optional<QCir> from_qasm(std::filesystem::path const& filepath) {
         spdlog::error("Cannot open the QASM file \"{}\"!!", filepath.string());
         return std::nullopt;
     }
+    auto qc = from_qasm_stream(file, filepath.string());
+    if (qc.has_value()) qc->set_filename(filepath.string());
+    return qc;
+}
+
+std::optional<QCir> from_qasm_stream(std::istream& file, std::string const& /*name_for_messages*/) {
     // OPENQASM 2.0; include "qelib1.inc"; qreg q[N];  -- six whitespace separated tokens
     std::string word;
     for (int i = 0; i < 6; ++i) file >> word;
     size_t const lb     = word.find('[');
     size_t const nqubit = std::stoul(word.substr(lb + 1, word.size() - lb - 3));
     QCir qcir{nqubit};
-    qcir.set_filename(filepath.string());
 
     std::string line;
     std::getline(file, line);  // rest of the qreg line

@@ -574,7 +574,6 @@ Tensor<U> tensordot(Tensor<U> const& t1, Tensor<U> const& t2, TensorAxisList con
     for (size_t i = 0; i < m; ++i)
         for (size_t p = 0; p < k; ++p) {
             U const av = a._data[i * k + p];
-            if (av == U{}) continue;
             for (size_t j = 0; j < n; ++j) t._data[i * n + j] += av * b._data[p * n + j];
         }
     size_t tmp_axis_id = 0;

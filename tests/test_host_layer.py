@@ -1,0 +1,122 @@
+"""The C++ host layer (qsyn_b200/host: reference-shaped QCir / QASM reader / to_tensor / QTensor /
+`tensor equiv`) through its C ABI (include/qsx_host.h), against the oracle."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import qsyn_b200 as Q
+from oracle import oracle as O
+from qsyn_b200 import host, workloads
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_host_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "qsx_host.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(qsxh_[a-z_0-9]+)\s*\(", hdr))
+    assert len(names) >= 14
+    for nm in sorted(names):
+        assert hasattr(host.lib(), nm), nm
+
+
+def test_workload_generators_match_the_oracle():
+    """bench.py's product arm (qsyn_b200.workloads) and the CPU arm (oracle) see the same circuits."""
+    assert workloads.random_clifford_t_qasm(12, 2000, 20261019) == O.random_clifford_t_qasm(12, 2000, 20261019)
+    assert workloads.random_clifford_t_qasm(1, 20, 3) == O.random_clifford_t_qasm(1, 20, 3)
+    assert workloads.qft_qasm(14) == O.qft_qasm(14)
+    assert workloads.random_rotation_qasm(7, 90, 5) == O.random_rotation_qasm(7, 90, 5)
+
+
+def test_qasm_reader_gate_order_and_matrices_match_oracle(goldens):
+    """Every golden input circuit: same gate order (non-monotone ids), same reprs (float angle ->
+    rational), and gate matrices equal to the oracle's reference formulas to the last ulp or two
+    (libm vs numpy complex exp / product rounding)."""
+    for path, text in goldens["inputs"].items():
+        c = host.Circuit(qasm_text=text)
+        qc = O.qcir_from_qasm_text(text)
+        assert (c.n_qubits, c.n_gates) == (qc.n_qubits, len(qc.gates)), path
+        order = qc.topological_order()
+        assert c.gate_reprs() == [(g.gid, g.op.repr()) for g in order], path
+        for (nc, qs, m), (onc, oqs, om) in zip(c.gate_stream(), O.gate_stream(qc)):
+            assert nc == onc and qs == oqs and np.allclose(m, om, rtol=0, atol=5e-16), path
+
+
+def test_whole_gate_table_and_phase_strings():
+    cases = [("h", None), ("x", None), ("y", None), ("z", None), ("s", None), ("sdg", None), ("t", None), ("tdg", None),
+             ("sx", None), ("sxdg", None), ("sy", None), ("sydg", None), ("tx", None), ("ty", None), ("id", None), ("not", None),
+             ("x_1_2", None), ("rz", "pi/3"), ("rx", "6.28*0.46181601443868003"), ("ry", "-3*pi/7"), ("p", "0.001"),
+             ("px", "2.3145031"), ("py", "pi"), ("pz", "-pi/4")]
+    for name, ph in cases:
+        c = host.Circuit(3).append(name, [1], ph)
+        op = O.str_to_operation(name, [O.str_to_phase(ph)] if ph else [])
+        assert c.gate_reprs()[0][1] == op.repr(), (name, ph)
+        assert np.allclose(c.gate_stream()[0][2], op.target_matrix(), rtol=0, atol=5e-16), (name, ph)
+    for name, qs, ph in [("cx", [0, 2], None), ("ccz", [2, 0, 1], None), ("cswap", [1, 0, 2], None), ("swap", [0, 1], None),
+                         ("ecr", [2, 1], None), ("crz", [0, 1], "pi/8"), ("cccx", [3, 0, 1, 2], None), ("cecr", [0, 1, 2], None)]:
+        c = host.Circuit(4).append(name, qs, ph)
+        op = O.str_to_operation(name, [O.str_to_phase(ph)] if ph else [])
+        nc, q, m = c.gate_stream()[0]
+        assert (nc, q) == (op.n_ctrls, qs) and np.allclose(m, op.target_matrix(), rtol=0, atol=5e-16)
+        assert c.gate_reprs()[0][1] == op.repr()
+    for bad in [("foo", [0], None), ("rz", [0], None), ("h", [0], "pi"), ("cx", [0, 0], None), ("h", [9], None), ("rz", [0], "abc")]:
+        with pytest.raises(Q.QsxError):
+            host.Circuit(2).append(bad[0], bad[1], bad[2])
+    with pytest.raises(Q.QsxError):
+        host.Circuit(qasm_text="OPENQASM 2.0;\ninclude \"qelib1.inc\";\nqreg q[2];\nh q[5];\n")
+
+
+def test_reader_quirks_match_oracle():
+    text = ("OPENQASM 2.0;\ninclude \"qelib1.inc\";\nqreg q[3];\ncreg c[3];\n// a comment\n  h q[0]; // trailing\n"
+            "mcx q[0],q[1],q[2];\nCX q[0] , q[1];\nrz(pi/2) q[2];\nbarrier q[0];\nt q[2];\n")
+    c, qc = host.Circuit(qasm_text=text), O.qcir_from_qasm_text(text)
+    assert c.gate_reprs() == [(g.gid, g.op.repr()) for g in qc.topological_order()]
+    assert c.n_gates == len(qc.gates) == 4  # mcx and barrier are skipped silently (Appendix C trap 7)
+    # a phase expression with blanks is "invalid phase on line" for the reference reader: both reject it
+    bad = text.replace("rz(pi/2)", "rz(pi / 2)")
+    assert O.qcir_from_qasm_text(bad) is None
+    with pytest.raises(Q.QsxError):
+        host.Circuit(qasm_text=bad)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["benchmark/qft/qft_5.qasm", "benchmark/qasm/qc2ts/toffoli_qiskit.qasm",
+                                  "benchmark/SABRE/small/3_17_13.qasm", "benchmark/qft/qft_8crz.qasm"])
+def test_qc2ts_through_the_host_layer(goldens, name):
+    """qsyn::to_tensor(QCir) + to_matrix() of the C++ host layer == the reference's literal algorithm."""
+    text = goldens["inputs"][name]
+    t = host.Circuit(qasm_text=text).qc2ts()
+    want = O.qc2ts(O.qcir_from_qasm_text(text))
+    assert t.shape == list(want.shape)
+    got = t.to_numpy()
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-12
+
+
+@pytest.mark.gpu
+def test_tensor_equiv_text_through_the_host_layer(goldens):
+    ins = goldens["inputs"]
+    a = host.Circuit(qasm_text=ins["benchmark/qft/qft_8.qasm"]).qc2ts()
+    b = host.Circuit(qasm_text=ins["benchmark/qft/qft_8dec.qasm"]).qc2ts()
+    c = host.Circuit(qasm_text=ins["benchmark/qft/qft_8crz.qasm"]).qc2ts()
+    r, text = a.equiv(b, 1e-6, True)
+    assert text == "Equivalent\n- Global Norm : 1\n- Global Phase: 0\n" and r.equivalent == 1
+    r, text = a.equiv(c)
+    assert text == "Equivalent\n- Global Norm : 1\n- Global Phase: 126π/253\n"
+    one = host.Circuit(1).qc2ts()
+    txtx = host.Circuit(1)
+    for g in "txtx":
+        txtx.append(g, [0])
+    r, text = one.equiv(txtx.qc2ts())
+    assert text == "Equivalent\n- Global Norm : 1\n- Global Phase: π/4\n"
+    r, text = one.equiv(txtx.qc2ts(), 1e-6, True)
+    assert text == "Not Equivalent\n- Cosine Similarity: 1\n"
+    r, text = one.equiv(host.Circuit(2).qc2ts())
+    assert text == "Not Equivalent\n- Shape Mismatch: [2, 2] vs [4, 4]\n"
+    with pytest.raises(Q.QsxError) as ei:
+        host.Circuit(0).qc2ts()
+    assert "QCir is empty!!" in str(ei.value)
+    b.adjoint_inplace()
+    r, text = a.equiv(b)
+    assert text.startswith("Not Equivalent\n- Cosine Similarity: ")
