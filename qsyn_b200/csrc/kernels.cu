@@ -187,29 +187,28 @@ __device__ __forceinline__ void op_dtab_half(double2 (&e)[1 << R], const double2
 // kernel is an interpreter whose hot loop jumps between handler bodies, and the full set is
 // ~160 KB of SASS -- far beyond the instruction caches ("no_instruction" was the third largest
 // stall reason).  A sweep that needs any other handler runs in the LEAN = false instantiation.
-__host__ __device__ constexpr bool is_common_handler(int h) {
-    return (h >= H_H && h < H_H + 4) || (h >= H_X && h < H_X + 4) || (h >= H_XC && h < H_XC + 16) ||
-           (h >= H_U1 && h < H_U1 + 4) || (h >= H_DTABH && h < H_DTABH + 4) || h == H_DTABF || h == H_SCALN ||
-           (h >= H_PHJ && h < H_PHJ + 4);
-}
+__host__ __device__ constexpr bool is_common_handler(int h) { return h >= 0 && h < H_COMMON; }
 
 // One handler = one straight-line body; everything about it is known at compile time.
 template <int R, int H>
 __device__ __forceinline__ void run_handler(double2 (&e)[1 << R], double2& scal, const DevOp* __restrict__ op, uint32_t creg,
                                             int pool_off, int sel, uint32_t grow, const double* __restrict__ pool) {
     const double* const c = op->c;
-    if constexpr (H >= H_H && H < H_HG + 4) {
-        constexpr int J = (H - H_H) & 3;
-        if constexpr (J < R) op_h<R, J, (H < H_HG)>(e, c[0], creg);
-    } else if constexpr (H >= H_X && H < H_XG + 4) {
-        constexpr int J = (H - H_X) & 3;
-        if constexpr (J < R) op_x<R, J, (H < H_XG)>(e, creg);
+    if constexpr ((H >= H_H && H < H_H + 4) || (H >= H_HG && H < H_HG + 4)) {
+        constexpr bool all = H < H_H + 4;
+        constexpr int J    = all ? H - H_H : H - H_HG;
+        if constexpr (J < R) op_h<R, J, all>(e, c[0], creg);
+    } else if constexpr ((H >= H_X && H < H_X + 4) || (H >= H_XG && H < H_XG + 4)) {
+        constexpr bool all = H < H_X + 4;
+        constexpr int J    = all ? H - H_X : H - H_XG;
+        if constexpr (J < R) op_x<R, J, all>(e, creg);
     } else if constexpr (H >= H_XC && H < H_XC + 16) {
         constexpr int J = (H - H_XC) >> 2, JC = (H - H_XC) & 3;
         if constexpr (J < R && JC < R && J != JC) op_xc<R, J, JC>(e);
-    } else if constexpr (H >= H_U1 && H < H_U1G + 4) {
-        constexpr int J = (H - H_U1) & 3;
-        if constexpr (J < R) op_u1<R, J, (H < H_U1G)>(e, c, creg);
+    } else if constexpr ((H >= H_U1 && H < H_U1 + 4) || (H >= H_U1G && H < H_U1G + 4)) {
+        constexpr bool all = H < H_U1 + 4;
+        constexpr int J    = all ? H - H_U1 : H - H_U1G;
+        if constexpr (J < R) op_u1<R, J, all>(e, c, creg);
     } else if constexpr (H >= H_AD && H < H_ADG + 4) {
         constexpr int J = (H - H_AD) & 3;
         if constexpr (J < R) op_ad<R, J, (H < H_ADG)>(e, c, creg);
@@ -261,10 +260,8 @@ __device__ __forceinline__ void run_handler(double2 (&e)[1 << R], double2& scal,
     }
 }
 
-#define QSX_CASE(h)                                                                \
-    case h:                                                                        \
-        if constexpr (!LEAN || is_common_handler(h)) run_handler<R, h>(e, scal, op, creg, pool_off, sel, grow, pool); \
-        break;
+#define QSX_CASE(h) \
+    case h: run_handler<R, h>(e, scal, op, creg, pool_off, sel, grow, pool); break;
 #define QSX_CASE8(b) QSX_CASE(b) QSX_CASE(b + 1) QSX_CASE(b + 2) QSX_CASE(b + 3) QSX_CASE(b + 4) QSX_CASE(b + 5) QSX_CASE(b + 6) QSX_CASE(b + 7)
 
 // hdr = {handler, j0, j1, creg}, hdr2 = {cother, czero, pool, sel}: already loaded (prefetched) by the caller
@@ -275,24 +272,40 @@ __device__ __forceinline__ void apply_op(double2 (&e)[1 << R], double2& scal, co
     uint32_t const cother = (uint32_t)hdr2.x, czero = (uint32_t)hdr2.y;
     if ((grow & cother) != cother || (grow & czero) != 0u) return;
     int const pool_off = hdr2.z, sel = hdr2.w;
-    switch (hdr.x) {
-        QSX_CASE8(0)
-        QSX_CASE8(8)
-        QSX_CASE8(16)
-        QSX_CASE8(24)
-        QSX_CASE8(32)
-        QSX_CASE8(40)
-        QSX_CASE8(48)
-        QSX_CASE8(56)
-        QSX_CASE8(64)
-        QSX_CASE8(72)
-        QSX_CASE8(80)
-        QSX_CASE(88)
-        QSX_CASE(89)
-        QSX_CASE(90)
-        QSX_CASE(91)
-        QSX_CASE(92)
-        default: break;
+    if constexpr (LEAN) {
+        switch (hdr.x) {  // dense 0..H_COMMON-1: one jump table
+            QSX_CASE8(0)
+            QSX_CASE8(8)
+            QSX_CASE8(16)
+            QSX_CASE8(24)
+            QSX_CASE(32)
+            QSX_CASE(33)
+            QSX_CASE(34)
+            QSX_CASE(35)
+            QSX_CASE(36)
+            QSX_CASE(37)
+            default: break;
+        }
+    } else {
+        switch (hdr.x) {
+            QSX_CASE8(0)
+            QSX_CASE8(8)
+            QSX_CASE8(16)
+            QSX_CASE8(24)
+            QSX_CASE8(32)
+            QSX_CASE8(40)
+            QSX_CASE8(48)
+            QSX_CASE8(56)
+            QSX_CASE8(64)
+            QSX_CASE8(72)
+            QSX_CASE8(80)
+            QSX_CASE(88)
+            QSX_CASE(89)
+            QSX_CASE(90)
+            QSX_CASE(91)
+            QSX_CASE(92)
+            default: break;
+        }
     }
 }
 #undef QSX_CASE8

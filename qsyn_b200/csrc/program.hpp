@@ -68,24 +68,27 @@ enum MicroKind : int32_t {
 // is a (kind, register bit(s), "has in-register controls") combination, numbered for the
 // maximum R = 4; combinations that do not exist for a smaller R are never emitted.
 enum Handler : int32_t {
+    // -- common handlers, numbered densely from 0 so that the lean kernel's switch is ONE jump table --
     H_H      = 0,   // +J          uncontrolled inside the registers (no per-element tests)
-    H_HG     = 4,   // +J          generic: runtime creg
-    H_X      = 8,   // +J
-    H_XG     = 12,  // +J
-    H_XC     = 16,  // +J*4+JC
-    H_U1     = 32,  // +J
-    H_U1G    = 36,  // +J
-    H_AD     = 40,  // +J
-    H_ADG    = 44,  // +J
-    H_SWAP   = 48,  // +JA*4+JB  (JA > JB)
-    H_SWAPG  = 64,  // +JA*4+JB
-    H_U2     = 80,
-    H_DSCAL  = 81,
-    H_DTABH  = 82,  // +J
-    H_DTABF  = 86,
-    H_SAPPLY = 87,
-    H_SCALN  = 88,
-    H_PHJ    = 89,  // +J
+    H_X      = 4,   // +J
+    H_XC     = 8,   // +J*4+JC
+    H_U1     = 24,  // +J
+    H_DTABH  = 28,  // +J
+    H_DTABF  = 32,
+    H_SCALN  = 33,
+    H_PHJ    = 34,  // +J
+    H_COMMON = 38,  // number of common handlers
+    // -- rare handlers (full kernel only) --
+    H_HG     = 38,  // +J          generic: runtime creg
+    H_XG     = 42,  // +J
+    H_U1G    = 46,  // +J
+    H_AD     = 50,  // +J
+    H_ADG    = 54,  // +J
+    H_SWAP   = 58,  // +JA*4+JB  (JA > JB)
+    H_SWAPG  = 74,  // +JA*4+JB
+    H_U2     = 90,
+    H_DSCAL  = 91,
+    H_SAPPLY = 92,
     H_COUNT  = 93,
 };
 

@@ -5,7 +5,7 @@ import time
 
 sys.path.insert(0, ".")
 import qsyn_b200 as Q
-from oracle import oracle as O
+from qsyn_b200 import host, workloads as W
 
 
 def time_plan(n, gs, opt, reps=3):
@@ -33,9 +33,9 @@ def main():
         (1, 4, 9, 3, 48), (1, 4, 8, 3, 48), (1, 3, 9, 3, 48), (1, 3, 8, 3, 48), (1, 4, 6, 3, 48), (1, 3, 7, 4, 48),
     ]
     workload = sys.argv[4] if len(sys.argv) > 4 else "clifford_t"
-    text = O.random_rotation_qasm(n, g, 20261019) if workload == "rot" else O.random_clifford_t_qasm(n, g, 20261019)
-    qc = O.qcir_from_qasm_text(text)
-    gs = O.gate_stream(qc)
+    text = W.random_rotation_qasm(n, g, 20261019) if workload == "rot" else W.random_clifford_t_qasm(n, g, 20261019)
+    qc = host.Circuit(qasm_text=text)
+    gs = qc.gate_array()
     print("n", n, "gates", g, workload, flush=True)
     for cfg in configs:
         fuse, R, tile, w, cap = cfg[:5]
@@ -49,7 +49,8 @@ def main():
             r = {"error": str(e)}
         r.update(fuse=fuse, R=R, tile=tile, log2w=w, cap=cap, pol=pol, dense=dense)
         print(json.dumps(r), flush=True)
-    qft = O.gate_stream(O.qcir_from_qasm_text(O.qft_qasm(n)))
+    qft_c = host.Circuit(qasm_text=W.qft_qasm(n))
+    qft = qft_c.gate_array()
     print("qft", json.dumps(time_plan(n, qft, Q.PlanOptions(max_ops_per_sweep=128))), flush=True)
     a, b = Q.Unitary(n), Q.Unitary(n)
     a.equiv_partial(b)

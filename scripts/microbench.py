@@ -8,12 +8,12 @@ import numpy as np
 
 sys.path.insert(0, ".")
 import qsyn_b200 as Q
-from oracle import oracle as O
 
-H = O.mat_h()
-T = O.mat_pz(O.Phase(1, 4))
+H = np.array([[1, 1], [1, -1]], dtype=complex) / np.sqrt(2.0)
+T = np.diag([1.0, np.exp(0.25j * np.pi)])
 X = np.array([[0, 1], [1, 0]], dtype=complex)
-RX = O.mat_rx(O.Phase(1, 3))
+_c, _s = np.cos(np.pi / 6), np.sin(np.pi / 6)
+RX = np.array([[_c, -1j * _s], [-1j * _s, _c]], dtype=complex)
 
 
 def run(n, gates, opt, reps=5):

@@ -3,14 +3,14 @@ import sys
 
 sys.path.insert(0, ".")
 import qsyn_b200 as Q
-from oracle import oracle as O
+from qsyn_b200 import host, workloads
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 g = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
 fuse = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 dense = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-qc = O.qcir_from_qasm_text(O.random_clifford_t_qasm(n, g, 20261019))
-plan = Q.Plan(n, 2**n, O.gate_stream(qc), Q.PlanOptions(fuse=fuse, dense_block=dense, max_ops_per_sweep=96, tile_qubits=9))
+qc = host.Circuit(qasm_text=workloads.random_clifford_t_qasm(n, g, 20261019))
+plan = Q.Plan(n, 2**n, qc.gate_array(), Q.PlanOptions(fuse=fuse, dense_block=dense, max_ops_per_sweep=96, tile_qubits=9))
 u = Q.Unitary(n)
 for _ in range(2):
     r = plan.run(u)
