@@ -47,6 +47,67 @@ __device__ __forceinline__ void swap_inplace(double2& a, double2& b) {
         : "+d"(a.x), "+d"(a.y), "+d"(b.x), "+d"(b.y));
 }
 
+// In-place arithmetic on register-resident elements, also PTX with tied ("+d") operands.  With
+// C++ value semantics every handler of the interpreter switch defines NEW values for e[i] while
+// the old ones are still live; the phi elimination at the head of the op loop then copies half of
+// the register tile on EVERY micro-op (measured: 32 IMAD.MOV per op, 30 % of all executed
+// instructions).  Tied operands keep each element in one virtual register for the whole stage.
+// The operation order (and therefore every rounding) is the one of cmul()/cfma() above.
+__device__ __forceinline__ void cmul_inplace(double2& a, double wx, double wy) {
+    asm("{\n\t.reg .f64 t, u;\n\t"
+        "mul.f64 t, %1, %3;\n\t"
+        "neg.f64 t, t;\n\t"
+        "mul.f64 u, %1, %2;\n\t"
+        "fma.rn.f64 %1, %0, %3, u;\n\t"
+        "fma.rn.f64 %0, %0, %2, t;\n\t}"
+        : "+d"(a.x), "+d"(a.y)
+        : "d"(wx), "d"(wy));
+}
+__device__ __forceinline__ void cmul_inplace(double2& a, double2 w) { cmul_inplace(a, w.x, w.y); }
+
+// (a, b) <- (s*(a+b), s*(a-b)) as DMUL + 2 DFMA per component
+__device__ __forceinline__ void hadamard_inplace(double2& a, double2& b, double s) {
+    asm("{\n\t.reg .f64 t, n;\n\t"
+        "mul.f64 t, %2, %4;\n\t"
+        "neg.f64 n, t;\n\t"
+        "fma.rn.f64 %2, %4, %0, n;\n\t"
+        "fma.rn.f64 %0, %4, %0, t;\n\t"
+        "mul.f64 t, %3, %4;\n\t"
+        "neg.f64 n, t;\n\t"
+        "fma.rn.f64 %3, %4, %1, n;\n\t"
+        "fma.rn.f64 %1, %4, %1, t;\n\t}"
+        : "+d"(a.x), "+d"(a.y), "+d"(b.x), "+d"(b.y)
+        : "d"(s));
+}
+
+// (a, b) <- (m00 a + m01 b, m10 a + m11 b), m = {m00, m01, m10, m11} as re/im pairs
+__device__ __forceinline__ void u1_inplace(double2& a, double2& b, const double* __restrict__ m) {
+    asm("{\n\t.reg .f64 t, p, q, r, s;\n\t"
+        "mul.f64 t, %5, %1;\n\t"  // cmul(m00, a)
+        "neg.f64 t, t;\n\t"
+        "fma.rn.f64 p, %4, %0, t;\n\t"
+        "mul.f64 t, %5, %0;\n\t"
+        "fma.rn.f64 q, %4, %1, t;\n\t"
+        "mul.f64 t, %9, %1;\n\t"  // cmul(m10, a)
+        "neg.f64 t, t;\n\t"
+        "fma.rn.f64 r, %8, %0, t;\n\t"
+        "mul.f64 t, %9, %0;\n\t"
+        "fma.rn.f64 s, %8, %1, t;\n\t"
+        "neg.f64 t, %7;\n\t"  // cfma(m01, b, .)
+        "fma.rn.f64 p, t, %3, p;\n\t"
+        "fma.rn.f64 %0, %6, %2, p;\n\t"
+        "fma.rn.f64 q, %7, %2, q;\n\t"
+        "fma.rn.f64 %1, %6, %3, q;\n\t"
+        "neg.f64 t, %11;\n\t"  // cfma(m11, b, .)
+        "fma.rn.f64 r, t, %3, r;\n\t"
+        "fma.rn.f64 r, %10, %2, r;\n\t"
+        "fma.rn.f64 s, %11, %2, s;\n\t"
+        "fma.rn.f64 %3, %10, %3, s;\n\t"
+        "mov.f64 %2, r;\n\t}"
+        : "+d"(a.x), "+d"(a.y), "+d"(b.x), "+d"(b.y)
+        : "d"(m[0]), "d"(m[1]), "d"(m[2]), "d"(m[3]), "d"(m[4]), "d"(m[5]), "d"(m[6]), "d"(m[7]));
+}
+
 template <int N, int I = 0, class Fn>
 __device__ __forceinline__ void static_switch(int v, Fn&& fn) {
     if constexpr (I < N) {
@@ -64,17 +125,13 @@ __device__ __forceinline__ void static_switch(int v, Fn&& fn) {
 // ---------------------------------------------------------------------------------------
 template <int R, int J, bool ALL>
 __device__ __forceinline__ void op_u1(double2 (&e)[1 << R], const double* __restrict__ c, uint32_t creg) {
-    double2 const m00 = make_double2(c[0], c[1]), m01 = make_double2(c[2], c[3]);
-    double2 const m10 = make_double2(c[4], c[5]), m11 = make_double2(c[6], c[7]);
 #pragma unroll
     for (int i = 0; i < (1 << R); ++i) {
         if ((i >> J) & 1) continue;
         if constexpr (!ALL) {
             if ((i & creg) != creg) continue;
         }
-        double2 const a = e[i], b = e[i | (1 << J)];
-        e[i]            = cfma(m01, b, cmul(m00, a));
-        e[i | (1 << J)] = cfma(m11, b, cmul(m10, a));
+        u1_inplace(e[i], e[i | (1 << J)], c);
     }
 }
 
@@ -87,10 +144,7 @@ __device__ __forceinline__ void op_h(double2 (&e)[1 << R], double s, uint32_t cr
             if ((i & creg) != creg) continue;
         }
         // 3 FP64 instructions per component (DMUL + 2 DFMA) instead of 4 (2 DADD + 2 DMUL)
-        double2 const a = e[i], b = e[i | (1 << J)];
-        double const tx = s * b.x, ty = s * b.y;
-        e[i]            = make_double2(fma(s, a.x, tx), fma(s, a.y, ty));
-        e[i | (1 << J)] = make_double2(fma(s, a.x, -tx), fma(s, a.y, -ty));
+        hadamard_inplace(e[i], e[i | (1 << J)], s);
     }
 }
 
@@ -179,7 +233,7 @@ __device__ __forceinline__ void op_dtab_half(double2 (&e)[1 << R], const double2
         if (!((i >> J) & 1)) continue;
         constexpr int lowmask = (1 << J) - 1;
         int const k           = ((i >> (J + 1)) << J) | (i & lowmask);
-        e[i]                  = cmul(e[i], tab[k]);
+        cmul_inplace(e[i], tab[k]);
     }
 }
 
@@ -230,16 +284,16 @@ __device__ __forceinline__ void run_handler(double2 (&e)[1 << R], double2& scal,
             double2 const w = make_double2(c[0], c[1]);
 #pragma unroll
             for (int i = 0; i < (1 << R); ++i)
-                if ((i >> J) & 1) e[i] = cmul(e[i], w);
+                if ((i >> J) & 1) cmul_inplace(e[i], w);
         }
     } else if constexpr (H == H_DTABF) {
         const double2* const tab = reinterpret_cast<const double2*>(pool + pool_off);
 #pragma unroll
-        for (int i = 0; i < (1 << R); ++i) e[i] = cmul(e[i], tab[i]);
+        for (int i = 0; i < (1 << R); ++i) cmul_inplace(e[i], tab[i]);
     } else if constexpr (H == H_SAPPLY) {
         double2 const sv = scal;
 #pragma unroll
-        for (int i = 0; i < (1 << R); ++i) e[i] = cmul(e[i], sv);
+        for (int i = 0; i < (1 << R); ++i) cmul_inplace(e[i], sv);
         scal = make_double2(1.0, 0.0);
     } else if constexpr (H == H_SCALN) {
         // every per-thread scalar of the stage, without a dispatch per gate
@@ -255,7 +309,7 @@ __device__ __forceinline__ void run_handler(double2 (&e)[1 << R], double2& scal,
             sv               = pass ? nv : sv;
         }
 #pragma unroll
-        for (int i = 0; i < (1 << R); ++i) e[i] = cmul(e[i], sv);
+        for (int i = 0; i < (1 << R); ++i) cmul_inplace(e[i], sv);
         scal = make_double2(1.0, 0.0);
     }
 }
