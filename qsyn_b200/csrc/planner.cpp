@@ -494,6 +494,8 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
                 }
                 break;
         }
+        // the exchange handlers move half of the data through the FP64 pipe as x + (-0.0)
+        if (u.kind == K_X || u.kind == K_XC || u.kind == K_SWAP) u.c[7] = -0.0;
         st.uops.push_back(std::move(u));
     }
     flush(~0u);
@@ -818,10 +820,19 @@ void serialize(Plan& plan) {
         std::vector<DevOp> ops;
         std::vector<DevPerm> perms;
         std::vector<double> pool;
-        auto add_perm_steps = [&](int idx) {
+        // Boundaries to shared memory address the tile (local row bits; controls outside the tile
+        // are a per-CTA test); the two boundaries to global memory are kept in global row bits
+        // so that the kernel needs no local -> global bit deposit.
+        auto add_perm_steps = [&](int idx, bool global_rows) {
             LoweredOp const& lo = plan.ops[idx];
             auto step = [&](uint32_t ctrl_global, int target_global) {
                 DevPerm d{0, 0, 0, 0};
+                if (global_rows) {
+                    d.cml = ctrl_global;
+                    d.tml = 1u << target_global;
+                    perms.push_back(d);
+                    return;
+                }
                 for (int b = 0; b < cfg.n; ++b)
                     if ((ctrl_global >> b) & 1u) {
                         if (local_of[b] >= 0)
@@ -840,7 +851,8 @@ void serialize(Plan& plan) {
                 step(lo.req, lo.t0);
             }
         };
-        for (PlannedStage const& st : sw.stages) {
+        for (size_t si = 0; si < sw.stages.size(); ++si) {
+            PlannedStage const& st = sw.stages[si];
             DevStage ds;
             std::memset(&ds, 0, sizeof(ds));
             ds.op_begin = (int)ops.size();
@@ -878,10 +890,10 @@ void serialize(Plan& plan) {
             }
             ds.op_end   = (int)ops.size();
             ds.pre_begin = (int)perms.size();
-            for (int idx : st.pre) add_perm_steps(idx);
+            for (int idx : st.pre) add_perm_steps(idx, si == 0);
             ds.pre_end    = (int)perms.size();
             ds.post_begin = (int)perms.size();
-            for (int idx : st.post) add_perm_steps(idx);
+            for (int idx : st.post) add_perm_steps(idx, si + 1 == sw.stages.size());
             ds.post_end = (int)perms.size();
             stages.push_back(ds);
         }
