@@ -524,29 +524,59 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
     }
 }
 
-void finish_sweep(Plan& plan, std::vector<int> const& chosen, uint32_t S) {
+// Builds the sweep of `chosen` (tile bits S).  With `trim`, a short trailing stage is not worth
+// its shared-memory transpose (~10 micro-ops of time): its ops are handed back through `returned`
+// and the sweep is rebuilt without them; they are first in line for the next sweep, whose tile
+// and first register set are then chosen around them.
+void finish_sweep(Plan& plan, std::vector<int> chosen, uint32_t S, std::vector<int>* returned = nullptr) {
     PlanConfig const& cfg = plan.cfg;
-    PlannedSweep sw;
-    // pad the tile: at least R bits; one-stage sweeps get enough rows for a full CTA
-    int const m_target = std::min(cfg.n, std::min(cfg.m_cap, cfg.R + 8 - cfg.log2w));
-    int m              = std::max(popc(S), m_target);
-    m                  = std::max(m, std::min(cfg.n, cfg.R));
-    for (int b = 0; b < cfg.n && popc(S) < m; ++b) S |= 1u << b;
-    for (int b = 0; b < cfg.n; ++b)
-        if ((S >> b) & 1u) sw.tile_bits.push_back(b);
-    // tiles whose outer bits fail a control shared by every op are never touched
-    uint32_t common = ~0u;
-    for (int idx : chosen) common &= plan.ops[idx].req;
-    sw.fixed_one = chosen.empty() ? 0u : (common & ~S);
-    build_stages(plan, chosen, sw);
-    for (PlannedStage& st : sw.stages) {
-        emit_uops(plan, st);
-        plan.stats.n_micro_ops += st.uops.size();
+    for (int attempt = 0;; ++attempt) {
+        PlannedSweep sw;
+        // pad the tile: at least R bits; one-stage sweeps get enough rows for a full CTA
+        uint32_t T = S;
+        int const m_target = std::min(cfg.n, std::min(cfg.m_cap, cfg.R + 8 - cfg.log2w));
+        int m              = std::max(popc(T), m_target);
+        m                  = std::max(m, std::min(cfg.n, cfg.R));
+        for (int b = 0; b < cfg.n && popc(T) < m; ++b) T |= 1u << b;
+        for (int b = 0; b < cfg.n; ++b)
+            if ((T >> b) & 1u) sw.tile_bits.push_back(b);
+        // tiles whose outer bits fail a control shared by every op are never touched
+        uint32_t common = ~0u;
+        for (int idx : chosen) common &= plan.ops[idx].req;
+        sw.fixed_one = chosen.empty() ? 0u : (common & ~T);
+        uint64_t const folded0 = plan.stats.n_folded_perms;
+        build_stages(plan, chosen, sw);
+        if (returned != nullptr && cfg.min_tail_ops > 0 && attempt < 4 && sw.stages.size() > 1) {
+            PlannedStage const& tail = sw.stages.back();
+            if ((int)(tail.ops.size() + tail.post.size()) < cfg.min_tail_ops) {
+                std::vector<char> drop(plan.ops.size(), 0);
+                for (int idx : tail.ops) drop[idx] = 1;
+                for (int idx : tail.post) drop[idx] = 1;
+                std::vector<int> keep;
+                S = 0;
+                for (int idx : chosen) {
+                    if (drop[idx]) {
+                        returned->push_back(idx);
+                    } else {
+                        keep.push_back(idx);
+                        S |= plan.ops[idx].tmask();
+                    }
+                }
+                chosen.swap(keep);
+                plan.stats.n_folded_perms = folded0;
+                continue;
+            }
+        }
+        for (PlannedStage& st : sw.stages) {
+            emit_uops(plan, st);
+            plan.stats.n_micro_ops += st.uops.size();
+        }
+        sw.alg_bytes = 32.0 * std::ldexp(1.0, cfg.n - popc(sw.fixed_one)) * (double)cfg.ncols;
+        plan.stats.n_stages += sw.stages.size();
+        plan.stats.alg_bytes_per_run += sw.alg_bytes;
+        plan.sweeps.push_back(std::move(sw));
+        return;
     }
-    sw.alg_bytes = 32.0 * std::ldexp(1.0, cfg.n - popc(sw.fixed_one)) * (double)cfg.ncols;
-    plan.stats.n_stages += sw.stages.size();
-    plan.stats.alg_bytes_per_run += sw.alg_bytes;
-    plan.sweeps.push_back(std::move(sw));
 }
 
 void schedule(Plan& plan) {
@@ -579,7 +609,13 @@ void schedule(Plan& plan) {
                 if (popc(pk.blockedT) >= cfg.n) break;
             }
         }
-        finish_sweep(plan, chosen, S);
+        // trimming pays only if the ops handed back join a sweep that exists anyway
+        bool more = false;
+        for (size_t i = first; i < N && !more; ++i) more = !done[i];
+        std::vector<int> returned;
+        finish_sweep(plan, chosen, S, more ? &returned : nullptr);
+        for (int idx : returned) done[idx] = 0;
+        if (!returned.empty()) first = std::min(first, (size_t)*std::min_element(returned.begin(), returned.end()));
     }
 }
 
@@ -959,12 +995,13 @@ int build_plan(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gat
     cfg.R           = std::min(n_qubits, o.reg_qubits > 0 ? std::min((int)o.reg_qubits, kMaxRegBits) : 4);
     cfg.log2w       = std::min(lc, o.log2_tile_cols > 0 ? std::min((int)o.log2_tile_cols, 5) : 3);
     if (o.log2_tile_cols < 0) cfg.log2w = 0;
-    cfg.m_cap       = o.tile_qubits > 0 ? (int)o.tile_qubits : 10;
+    cfg.m_cap       = o.tile_qubits > 0 ? (int)o.tile_qubits : 9;
     cfg.m_cap       = std::min(cfg.m_cap, kMaxTileBits);
     cfg.m_cap       = std::min(cfg.m_cap, 13 - cfg.log2w);            // 2^m * W * 16 B <= 128 KiB
     cfg.m_cap       = std::min(cfg.m_cap, max_threads_log2(cfg.R) - cfg.log2w + cfg.R);  // CTA size limit
     cfg.m_cap       = std::max(std::min(cfg.m_cap, n_qubits), cfg.R);
-    cfg.max_ops     = o.max_ops_per_sweep > 0 ? (int)o.max_ops_per_sweep : 48;
+    cfg.max_ops     = o.max_ops_per_sweep > 0 ? (int)o.max_ops_per_sweep : 96;
+    cfg.min_tail_ops = o.min_tail_ops > 0 ? (int)o.min_tail_ops : (o.min_tail_ops < 0 ? 0 : 8);
     cfg.lookahead   = o.lookahead > 0 ? (int)o.lookahead : 4096;
 
     plan.stats          = qsx_plan_stats{};

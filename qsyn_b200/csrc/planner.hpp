@@ -64,7 +64,8 @@ struct PlanConfig {
     int  R = 4;          // register bits (kernel template parameter)
     int  log2w = 3;
     int  m_cap = 10;
-    int  max_ops = 48;
+    int  max_ops = 96;
+    int  min_tail_ops = 8;   // a trailing stage with fewer ops is dropped from the sweep
     int  lookahead = 4096;
     bool fuse = true;
     bool fold_perms = true;  // fold X / CX / SWAP into the addressing of stage boundaries
