@@ -416,7 +416,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "tiny"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cap", type=int, default=96, help="max ops per sweep")
-    ap.add_argument("--tile", type=int, default=9)
+    ap.add_argument("--tile", type=int, default=8)
     ap.add_argument("--reg", type=int, default=4)
     ap.add_argument("--log2w", type=int, default=3)
     ap.add_argument("--dense", type=int, default=0, help="fold the gate stream into dense k-qubit blocks on the FP64 tensor pipe (3..5)")

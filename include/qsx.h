@@ -96,7 +96,7 @@ typedef struct qsx_plan_options {
     double  snap_tol;      /* matrix entries within snap_tol of 0 / +-1 / +-i are snapped (default 1e-15);
                               < 0 disables snapping: the host-built matrices are applied as given               */
     int32_t reg_qubits;    /* qubits held in registers per thread (1..4, default 4)                             */
-    int32_t tile_qubits;   /* max row bits staged per shared-memory tile (default 9)                            */
+    int32_t tile_qubits;   /* max row bits staged per shared-memory tile (default 8)                            */
     int32_t log2_tile_cols;/* log2 of tile width in columns (default 3 -> 128 B contiguous per row)             */
     int32_t max_ops_per_sweep; /* cap on ops per sweep (default 96)                                             */
     int32_t lookahead;     /* scheduler scan window in gates (default 4096)                                     */
@@ -106,7 +106,10 @@ typedef struct qsx_plan_options {
                                 registers (an op that cannot be hoisted waits for the next boundary)            */
     int32_t min_tail_ops;  /* a sweep's trailing stage with fewer ops than this is left to the next sweep
                               (default 8; < 0: keep every stage)                                                */
-    int32_t reserved[6];
+    int32_t search;        /* rounds of hill climbing over each sweep's tile bits (0 = first come, first served) */
+    int32_t no_diag_conjugation; /* 1: apply pending diagonal tables before an in-register X / CX / SWAP instead of
+                                    carrying them through it (default 0)                                        */
+    int32_t reserved[4];
 } qsx_plan_options;
 
 typedef struct qsx_plan_stats {

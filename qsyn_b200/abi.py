@@ -54,7 +54,8 @@ class PlanOptions(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("fuse", C.c_int32), ("snap_tol", C.c_double), ("reg_qubits", C.c_int32),
                 ("tile_qubits", C.c_int32), ("log2_tile_cols", C.c_int32), ("max_ops_per_sweep", C.c_int32),
                 ("lookahead", C.c_int32), ("dense_block", C.c_int32), ("no_perm_folding", C.c_int32), ("min_tail_ops", C.c_int32),
-                ("reserved", C.c_int32 * 6)]
+                ("search", C.c_int32), ("no_diag_conjugation", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
 
     def __init__(self, fuse: int = 1, **kw):
         super().__init__()

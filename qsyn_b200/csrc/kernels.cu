@@ -414,7 +414,6 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), 1)
     const double* const pool     = reinterpret_cast<const double*>(perms + sw->n_perms);
 
     int const log2w      = sw->log2w;
-    int const m          = sw->m;
     uint32_t const tid   = threadIdx.x;
     uint32_t const cw    = tid & ((1u << log2w) - 1u);
     uint32_t const trow  = tid >> log2w;
@@ -501,9 +500,17 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), 1)
             double2 scal = make_double2(1.0, 0.0);  // per-thread product of the stage's K_DSCAL ops
             // (prefetching the next header was measured: the 8 extra live registers spill, -12 %)
             for (int o = ob; o < oe; ++o) {
+#if defined(QSX_EXP_DIRECT) && QSX_EXP_DIRECT == 1
+                run_handler<R, H_H>(e, scal, ops + o, 0u, 0, 0, grow, pool);  // timing experiment: no dispatch at all
+#elif defined(QSX_EXP_DIRECT) && QSX_EXP_DIRECT == 2
+                int4 const hdr2 = *(reinterpret_cast<const int4*>(ops + o) + 1);
+                if ((grow & (uint32_t)hdr2.x) != (uint32_t)hdr2.x || (grow & (uint32_t)hdr2.y) != 0u) continue;
+                run_handler<R, H_H>(e, scal, ops + o, 0u, 0, 0, grow, pool);  // timing experiment: control test, no switch
+#else
                 int4 const hdr  = *reinterpret_cast<const int4*>(ops + o);
                 int4 const hdr2 = *(reinterpret_cast<const int4*>(ops + o) + 1);
                 apply_op<R, LEAN>(e, scal, ops + o, hdr, hdr2, grow, pool);
+#endif
             }
         }
 

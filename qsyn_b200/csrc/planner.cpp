@@ -360,114 +360,125 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
         return c;
     };
 
-    std::vector<int> pending;  // positions in st.ops of held-back diagonal ops
     // per-thread scalars commute with every register op of the stage: they are all collected
     // into ONE micro-op at the end of the stage
     std::vector<MicroOp> scalars;
 
+    // The diagonal ops seen so far and not yet applied, multiplied together: one table over the
+    // register index per distinct thread-level condition.  A table stays live across
+    //   * ops that do not act on a register bit it depends on (they commute), and
+    //   * in-register permutations (X / CX / SWAP whose controls are all register bits):
+    //     D then P  ==  P then D',  D'[P(i)] = D[i]  -- the table is permuted instead of applied;
+    // it is applied right before an op that mixes a bit it depends on, or at the end of the stage.
     struct Group {
         uint32_t cother, czero;
         std::vector<Cx> tab;
     };
-
-    auto flush = [&](uint32_t filter) {
-        std::vector<int> keep;
-        std::vector<Group> groups;
-        auto group_for = [&](uint32_t cother, uint32_t czero) -> Group& {
-            for (Group& g : groups)
-                if (g.cother == cother && g.czero == czero) return g;
-            groups.push_back(Group{cother, czero, std::vector<Cx>((size_t)E)});
-            return groups.back();
-        };
-        for (int pos : pending) {
-            LoweredOp const& op = plan.ops[st.ops[pos]];
-            if ((op.dmask() & filter) == 0) {
-                keep.push_back(pos);
-                continue;
-            }
-            uint32_t const creg   = creg_of(op.req);
-            uint32_t const cother = op.req & ~regmask;
-            bool const is_diag2   = op.kind == OP_DIAG;
-            int const dj          = is_diag2 ? regidx_of[op.dbit] : -1;
-            if (creg == 0 && dj < 0) {  // nothing in registers: per-thread scalar
-                MicroOp u;
-                u.kind   = K_DSCAL;
-                u.cother = cother;
-                if (is_diag2) {
-                    u.sel  = op.dbit;
-                    u.c[0] = op.c[0], u.c[1] = op.c[1], u.c[2] = op.c[2], u.c[3] = op.c[3];
-                } else {
-                    Cx const w = phase_of(op);
-                    u.c[0] = w.re, u.c[1] = w.im;
-                }
-                scalars.push_back(std::move(u));
-                continue;
-            }
-            if (!is_diag2) {
-                Group& g   = group_for(cother, 0);
-                Cx const w = phase_of(op);
-                for (int i = 0; i < E; ++i)
-                    if (((uint32_t)i & creg) == creg) g.tab[i] = cmul(g.tab[i], w);
-            } else if (dj >= 0) {
-                Group& g = group_for(cother, 0);
-                Cx const d0{op.c[0], op.c[1]}, d1{op.c[2], op.c[3]};
-                for (int i = 0; i < E; ++i)
-                    if (((uint32_t)i & creg) == creg) g.tab[i] = cmul(g.tab[i], ((i >> dj) & 1) ? d1 : d0);
-            } else {  // selecting bit outside the registers, a control inside
-                Cx const d0{op.c[0], op.c[1]}, d1{op.c[2], op.c[3]};
-                Group& g1 = group_for(cother | (1u << op.dbit), 0);
-                for (int i = 0; i < E; ++i)
-                    if (((uint32_t)i & creg) == creg) g1.tab[i] = cmul(g1.tab[i], d1);
-                Group& g0 = group_for(cother, 1u << op.dbit);
-                for (int i = 0; i < E; ++i)
-                    if (((uint32_t)i & creg) == creg) g0.tab[i] = cmul(g0.tab[i], d0);
-            }
-        }
-        pending.swap(keep);
-        for (Group const& g : groups) {
-            uint32_t active = 0;
-            for (int i = 0; i < E; ++i)
-                if (g.tab[i].re != 1.0 || g.tab[i].im != 0.0) active |= 1u << i;
-            if (active == 0) continue;
+    std::vector<Group> groups;
+    auto group_for = [&](uint32_t cother, uint32_t czero) -> Group& {
+        for (Group& g : groups)
+            if (g.cother == cother && g.czero == czero) return g;
+        groups.push_back(Group{cother, czero, std::vector<Cx>((size_t)E)});
+        return groups.back();
+    };
+    auto add_diagonal = [&](LoweredOp const& op) {
+        uint32_t const creg   = creg_of(op.req);
+        uint32_t const cother = op.req & ~regmask;
+        bool const is_diag2   = op.kind == OP_DIAG;
+        int const dj          = is_diag2 ? regidx_of[op.dbit] : -1;
+        if (creg == 0 && dj < 0) {  // nothing in registers: per-thread scalar
             MicroOp u;
-            u.cother = g.cother;
-            u.czero  = g.czero;
-            int half = -1;
-            for (int j = 0; j < R && half < 0; ++j) {
-                bool ok = true;
-                for (int i = 0; i < E; ++i)
-                    if (((active >> i) & 1u) && !((i >> j) & 1)) ok = false;
-                if (ok) half = j;
-            }
-            bool uniform = half >= 0;  // every entry of the half-table equal -> one scalar instead of a table
-            for (int i = 0; uniform && i < E; ++i)
-                if ((i >> half) & 1)
-                    uniform = g.tab[i].re == g.tab[1 << half].re && g.tab[i].im == g.tab[1 << half].im;
-            if (uniform) {
-                u.kind = K_PHJ;
-                u.j0   = half;
-                u.c[0] = g.tab[1 << half].re;
-                u.c[1] = g.tab[1 << half].im;
-            } else if (half >= 0) {
-                u.kind = K_DTABH;
-                u.j0   = half;
-                for (int i = 0; i < E; ++i)
-                    if ((i >> half) & 1) u.table.push_back(g.tab[i].re), u.table.push_back(g.tab[i].im);
+            u.kind   = K_DSCAL;
+            u.cother = cother;
+            if (is_diag2) {
+                u.sel  = op.dbit;
+                u.c[0] = op.c[0], u.c[1] = op.c[1], u.c[2] = op.c[2], u.c[3] = op.c[3];
             } else {
-                u.kind = K_DTABF;
-                for (int i = 0; i < E; ++i) u.table.push_back(g.tab[i].re), u.table.push_back(g.tab[i].im);
+                Cx const w = phase_of(op);
+                u.c[0] = w.re, u.c[1] = w.im;
             }
-            st.uops.push_back(std::move(u));
+            scalars.push_back(std::move(u));
+            return;
         }
+        if (!is_diag2) {
+            Group& g   = group_for(cother, 0);
+            Cx const w = phase_of(op);
+            for (int i = 0; i < E; ++i)
+                if (((uint32_t)i & creg) == creg) g.tab[i] = cmul(g.tab[i], w);
+        } else if (dj >= 0) {
+            Group& g = group_for(cother, 0);
+            Cx const d0{op.c[0], op.c[1]}, d1{op.c[2], op.c[3]};
+            for (int i = 0; i < E; ++i)
+                if (((uint32_t)i & creg) == creg) g.tab[i] = cmul(g.tab[i], ((i >> dj) & 1) ? d1 : d0);
+        } else {  // selecting bit outside the registers, a control inside
+            Cx const d0{op.c[0], op.c[1]}, d1{op.c[2], op.c[3]};
+            Group& g1 = group_for(cother | (1u << op.dbit), 0);
+            for (int i = 0; i < E; ++i)
+                if (((uint32_t)i & creg) == creg) g1.tab[i] = cmul(g1.tab[i], d1);
+            Group& g0 = group_for(cother, 1u << op.dbit);
+            for (int i = 0; i < E; ++i)
+                if (((uint32_t)i & creg) == creg) g0.tab[i] = cmul(g0.tab[i], d0);
+        }
+    };
+    auto emit_group = [&](Group const& g) {
+        uint32_t active = 0;
+        for (int i = 0; i < E; ++i)
+            if (g.tab[i].re != 1.0 || g.tab[i].im != 0.0) active |= 1u << i;
+        if (active == 0) return;
+        MicroOp u;
+        u.cother = g.cother;
+        u.czero  = g.czero;
+        int half = -1;
+        for (int j = 0; j < R && half < 0; ++j) {
+            bool ok = true;
+            for (int i = 0; i < E; ++i)
+                if (((active >> i) & 1u) && !((i >> j) & 1)) ok = false;
+            if (ok) half = j;
+        }
+        bool uniform = half >= 0;  // every entry of the half-table equal -> one scalar instead of a table
+        for (int i = 0; uniform && i < E; ++i)
+            if ((i >> half) & 1)
+                uniform = g.tab[i].re == g.tab[1 << half].re && g.tab[i].im == g.tab[1 << half].im;
+        if (uniform) {
+            u.kind = K_PHJ;
+            u.j0   = half;
+            u.c[0] = g.tab[1 << half].re;
+            u.c[1] = g.tab[1 << half].im;
+        } else if (half >= 0) {
+            u.kind = K_DTABH;
+            u.j0   = half;
+            for (int i = 0; i < E; ++i)
+                if ((i >> half) & 1) u.table.push_back(g.tab[i].re), u.table.push_back(g.tab[i].im);
+        } else {
+            u.kind = K_DTABF;
+            for (int i = 0; i < E; ++i) u.table.push_back(g.tab[i].re), u.table.push_back(g.tab[i].im);
+        }
+        st.uops.push_back(std::move(u));
+    };
+    // applies (and forgets) every live table that depends on one of the register bits in jmask
+    auto flush = [&](uint32_t jmask) {
+        std::vector<Group> keep;
+        for (Group& g : groups) {
+            bool dep = false;
+            for (int j = 0; j < R && !dep; ++j) {
+                if (!((jmask >> j) & 1u)) continue;
+                for (int i = 0; i < E && !dep; ++i)
+                    dep = g.tab[i].re != g.tab[i ^ (1 << j)].re || g.tab[i].im != g.tab[i ^ (1 << j)].im;
+            }
+            if (dep)
+                emit_group(g);
+            else
+                keep.push_back(std::move(g));
+        }
+        groups.swap(keep);
     };
 
     for (int pos = 0; pos < (int)st.ops.size(); ++pos) {
         LoweredOp const& op = plan.ops[st.ops[pos]];
         if (op.tmask() == 0) {
-            pending.push_back(pos);
+            add_diagonal(op);
             continue;
         }
-        flush(op.tmask());
         MicroOp u;
         u.src    = pos;
         u.creg   = creg_of(op.req);
@@ -475,6 +486,25 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
         u.j0     = regidx_of[op.t0];
         u.j1     = op.t1 >= 0 ? regidx_of[op.t1] : -1;
         std::memcpy(u.c, op.c, sizeof(u.c));
+        uint32_t const jmask = (1u << u.j0) | (u.j1 >= 0 ? 1u << u.j1 : 0u);
+        if (plan.cfg.conjugate_diagonals && (op.kind == OP_X || op.kind == OP_SWAP) && u.cother == 0) {
+            for (Group& g : groups) {
+                std::vector<Cx> t((size_t)E);
+                for (int i = 0; i < E; ++i) {
+                    int pi = i;
+                    if (((uint32_t)i & u.creg) == u.creg) {
+                        if (op.kind == OP_X)
+                            pi = i ^ (1 << u.j0);
+                        else if (((i >> u.j0) & 1) != ((i >> u.j1) & 1))
+                            pi = i ^ (1 << u.j0) ^ (1 << u.j1);
+                    }
+                    t[(size_t)pi] = g.tab[i];
+                }
+                g.tab.swap(t);
+            }
+        } else {
+            flush(jmask);
+        }
         switch (op.kind) {
             case OP_U1: u.kind = K_U1; break;
             case OP_H: u.kind = K_H; break;
@@ -498,7 +528,7 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
         if (u.kind == K_X || u.kind == K_XC || u.kind == K_SWAP) u.c[7] = -0.0;
         st.uops.push_back(std::move(u));
     }
-    flush(~0u);
+    for (Group const& g : groups) emit_group(g);
     if (!scalars.empty()) {
         MicroOp u;
         u.kind = K_SCALN;
@@ -588,27 +618,62 @@ void schedule(Plan& plan) {
     }
     std::vector<char> done(N, 0);
     size_t first = 0;
-    while (true) {
-        while (first < N && done[first]) ++first;
-        if (first >= N) break;
+    // One scan of the pending ops: an op joins the sweep if it commutes past everything skipped
+    // so far and its non-diagonal targets fit the tile.  `allowed` restricts the tile bits
+    // (search); without it the tile grows first come, first served up to m_cap bits.
+    auto scan = [&](uint32_t allowed, bool restricted, std::vector<int>* out, uint32_t& S_out) {
         uint32_t S = 0;
-        std::vector<int> chosen;
+        int count = 0, scanned = 0;
         Picker pk;
-        int scanned = 0;
         for (size_t i = first; i < N && scanned < cfg.lookahead; ++i) {
             if (done[i]) continue;
             ++scanned;
             LoweredOp const& op = plan.ops[i];
-            if (pk.passes(op) && popc(S | op.tmask()) <= cfg.m_cap) {
+            bool const fits     = restricted ? (op.tmask() & ~allowed) == 0 : popc(S | op.tmask()) <= cfg.m_cap;
+            if (pk.passes(op) && fits) {
                 S |= op.tmask();
-                chosen.push_back((int)i);
-                done[i] = 1;
-                if ((int)chosen.size() >= cfg.max_ops) break;
+                if (out != nullptr) out->push_back((int)i);
+                if (++count >= cfg.max_ops) break;
             } else {
                 pk.block(op);
                 if (popc(pk.blockedT) >= cfg.n) break;
             }
         }
+        S_out = S;
+        return count;
+    };
+    while (true) {
+        while (first < N && done[first]) ++first;
+        if (first >= N) break;
+        uint32_t S = 0;
+        std::vector<int> chosen;
+        if (cfg.search > 0 && cfg.n > cfg.m_cap) {
+            // hill climbing over the tile's bit set, seeded with the first-come choice: exchange one
+            // tile bit for one outer bit while that lets the sweep take more ops
+            uint32_t S0  = 0;
+            int best     = scan(0, false, nullptr, S0);
+            uint32_t cur = S0;
+            for (int b = 0; b < cfg.n && popc(cur) < cfg.m_cap; ++b) cur |= 1u << b;
+            best = std::max(best, scan(cur, true, nullptr, S0));
+            for (int round = 0; round < cfg.search; ++round) {
+                uint32_t best_set = cur;
+                for (int a = 0; a < cfg.n; ++a) {
+                    if (!((cur >> a) & 1u)) continue;
+                    for (int b = 0; b < cfg.n; ++b) {
+                        if ((cur >> b) & 1u) continue;
+                        uint32_t const cand = (cur & ~(1u << a)) | (1u << b);
+                        int const c         = scan(cand, true, nullptr, S0);
+                        if (c > best) best = c, best_set = cand;
+                    }
+                }
+                if (best_set == cur) break;
+                cur = best_set;
+            }
+            scan(cur, true, &chosen, S);
+        } else {
+            scan(0, false, &chosen, S);
+        }
+        for (int idx : chosen) done[idx] = 1;
         // trimming pays only if the ops handed back join a sweep that exists anyway
         bool more = false;
         for (size_t i = first; i < N && !more; ++i) more = !done[i];
@@ -995,7 +1060,7 @@ int build_plan(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gat
     cfg.R           = std::min(n_qubits, o.reg_qubits > 0 ? std::min((int)o.reg_qubits, kMaxRegBits) : 4);
     cfg.log2w       = std::min(lc, o.log2_tile_cols > 0 ? std::min((int)o.log2_tile_cols, 5) : 3);
     if (o.log2_tile_cols < 0) cfg.log2w = 0;
-    cfg.m_cap       = o.tile_qubits > 0 ? (int)o.tile_qubits : 9;
+    cfg.m_cap       = o.tile_qubits > 0 ? (int)o.tile_qubits : 8;
     cfg.m_cap       = std::min(cfg.m_cap, kMaxTileBits);
     cfg.m_cap       = std::min(cfg.m_cap, 13 - cfg.log2w);            // 2^m * W * 16 B <= 128 KiB
     cfg.m_cap       = std::min(cfg.m_cap, max_threads_log2(cfg.R) - cfg.log2w + cfg.R);  // CTA size limit
@@ -1003,6 +1068,8 @@ int build_plan(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gat
     cfg.max_ops     = o.max_ops_per_sweep > 0 ? (int)o.max_ops_per_sweep : 96;
     cfg.min_tail_ops = o.min_tail_ops > 0 ? (int)o.min_tail_ops : (o.min_tail_ops < 0 ? 0 : 8);
     cfg.lookahead   = o.lookahead > 0 ? (int)o.lookahead : 4096;
+    cfg.search      = o.search > 0 ? (int)o.search : 0;
+    cfg.conjugate_diagonals = o.no_diag_conjugation == 0;
 
     plan.stats          = qsx_plan_stats{};
     plan.stats.n_gates  = n_gates;

@@ -67,9 +67,11 @@ struct PlanConfig {
     int  max_ops = 96;
     int  min_tail_ops = 8;   // a trailing stage with fewer ops is dropped from the sweep
     int  lookahead = 4096;
+    int  search = 0;         // rounds of hill climbing over each sweep's tile bits
     bool fuse = true;
     bool fold_perms = true;  // fold X / CX / SWAP into the addressing of stage boundaries
     bool defer_perms = false;
+    bool conjugate_diagonals = true;  // carry pending diagonal tables through in-register permutations
     int  dense_k = 0;  // >= 3: fold the gate stream into dense k-qubit blocks (FP64 tensor pipe)  // never swap registers: an X-type op that cannot be hoisted ends the stage
     double snap_tol = 1e-15;
 };

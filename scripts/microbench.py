@@ -29,12 +29,15 @@ def run(n, gates, opt, reps=5):
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 12
     k = 32
-    opt = lambda **kw: Q.PlanOptions(max_ops_per_sweep=1000, tile_qubits=9, **kw)
+    tile = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+    opt = lambda **kw: Q.PlanOptions(max_ops_per_sweep=1000, tile_qubits=tile, min_tail_ops=-1, **kw)
     q = lambda b: n - 1 - b  # row bit -> qubit id
     cases = {}
     # register bits will be the first 4 distinct target bits: use row bits 0..3 as register bits
     cases["1 H (one sweep, one stage)"] = [(0, [q(0)], H)]
     cases["H x%d same bit" % k] = [(0, [q(0)], H)] * k
+    for kk in (4, 8, 16, 64, 128):
+        cases["H x%d same bit" % kk] = [(0, [q(0)], H)] * kk
     cases["H x%d over 4 reg bits" % k] = [(0, [q(i % 4)], H) for i in range(k)]
     cases["(H,T) x%d same reg bit (H + DTABH)" % k] = [(0, [q(0)], m) for _ in range(k) for m in (H, T)]
     cases["(H0,T8) x%d (H + DSCAL outside)" % k] = [g for _ in range(k) for g in ((0, [q(0)], H), (0, [q(8)], T))]

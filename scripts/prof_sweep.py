@@ -10,7 +10,7 @@ g = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
 fuse = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 dense = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 qc = host.Circuit(qasm_text=workloads.random_clifford_t_qasm(n, g, 20261019))
-plan = Q.Plan(n, 2**n, qc.gate_array(), Q.PlanOptions(fuse=fuse, dense_block=dense, max_ops_per_sweep=96, tile_qubits=9))
+plan = Q.Plan(n, 2**n, qc.gate_array(), Q.PlanOptions(fuse=fuse, dense_block=dense))
 u = Q.Unitary(n)
 for _ in range(2):
     r = plan.run(u)
