@@ -106,7 +106,8 @@ typedef struct qsx_plan_options {
                                 registers (an op that cannot be hoisted waits for the next boundary)            */
     int32_t min_tail_ops;  /* a sweep's trailing stage with fewer ops than this is left to the next sweep
                               (default 8; < 0: keep every stage)                                                */
-    int32_t search;        /* rounds of hill climbing over each sweep's tile bits (0 = first come, first served) */
+    int32_t search;        /* rounds of hill climbing over each sweep's tile bits (default 0: 3 rounds when
+                              n >= 13, none below; < 0: never, the tile grows first come, first served)         */
     int32_t no_diag_conjugation; /* 1: apply pending diagonal tables before an in-register X / CX / SWAP instead of
                                     carrying them through it (default 0)                                        */
     int32_t reserved[4];

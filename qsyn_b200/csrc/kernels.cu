@@ -525,6 +525,10 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), 1)
         if (qb != qe) permute_rows<R, true>(rows, perms, qb, qe, last ? 0u : row_outer);
 
         if (last) {
+            // A folded permutation makes a thread load (s == 0) or store (here) rows that another
+            // thread of the CTA stores / loads.  In a multi-stage sweep the transposes' barriers
+            // already separate the global loads from the global stores; a one-stage sweep needs one.
+            if (n_stages == 1 && (qb != qe || st->pre_begin != st->pre_end)) __syncthreads();
             uint32_t const gb = rows[0];
             uint32_t gc[R];
 #pragma unroll

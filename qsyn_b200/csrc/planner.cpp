@@ -1068,7 +1068,8 @@ int build_plan(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gat
     cfg.max_ops     = o.max_ops_per_sweep > 0 ? (int)o.max_ops_per_sweep : 96;
     cfg.min_tail_ops = o.min_tail_ops > 0 ? (int)o.min_tail_ops : (o.min_tail_ops < 0 ? 0 : 8);
     cfg.lookahead   = o.lookahead > 0 ? (int)o.lookahead : 4096;
-    cfg.search      = o.search > 0 ? (int)o.search : 0;
+    // the search costs a few ms of host time: worth it once a sweep takes milliseconds (n >= 13)
+    cfg.search      = o.search > 0 ? (int)o.search : (o.search < 0 || n_qubits < 13 ? 0 : 3);
     cfg.conjugate_diagonals = o.no_diag_conjugation == 0;
 
     plan.stats          = qsx_plan_stats{};

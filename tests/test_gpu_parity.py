@@ -290,3 +290,24 @@ def test_n10_against_oracle_default_schedule():
     assert frob_rel(got, want) < TOL
     got = run_device(qc, Q.PlanOptions(snap_tol=-1.0))
     assert frob_rel(got, want) < TOL
+
+
+@pytest.mark.parametrize("opts", [{}, {"fuse": 0}, {"tile_qubits": 7, "log2_tile_cols": 4}])
+def test_repeated_runs_are_bitwise_identical(opts):
+    """A folded permutation makes threads of a CTA read rows that other threads write: the result
+    must not depend on warp timing (regression: a one-stage sweep lacked the barrier between its
+    global loads and stores and every run of a 600-gate circuit differed)."""
+    n = 10
+    qc = O.qcir_from_qasm_text(O.random_clifford_t_qasm(n, 600, 123))
+    plan = Q.Plan(n, 2**n, O.gate_stream(qc), Q.PlanOptions(**opts))
+    first = None
+    for _ in range(6):
+        u = Q.Unitary(n)
+        plan.run(u)
+        got = u.download()
+        u.close()
+        if first is None:
+            first = got
+            assert frob_rel(got, O.to_matrix_rowform(qc)) < TOL
+        else:
+            assert np.array_equal(got.view(np.float64), first.view(np.float64))
