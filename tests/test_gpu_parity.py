@@ -292,7 +292,8 @@ def test_n10_against_oracle_default_schedule():
     assert frob_rel(got, want) < TOL
 
 
-@pytest.mark.parametrize("opts", [{}, {"fuse": 0}, {"tile_qubits": 7, "log2_tile_cols": 4}])
+@pytest.mark.parametrize("opts", [{}, {"fuse": 0}, {"tile_qubits": 7, "log2_tile_cols": 4}, {"dense_block": 5},
+                                  {"reg_qubits": 3, "tile_qubits": 9, "no_perm_folding": 2}])
 def test_repeated_runs_are_bitwise_identical(opts):
     """A folded permutation makes threads of a CTA read rows that other threads write: the result
     must not depend on warp timing (regression: a one-stage sweep lacked the barrier between its
