@@ -110,7 +110,9 @@ typedef struct qsx_plan_options {
                               n >= 13, none below; < 0: never, the tile grows first come, first served)         */
     int32_t no_diag_conjugation; /* 1: apply pending diagonal tables before an in-register X / CX / SWAP instead of
                                     carrying them through it (default 0)                                        */
-    int32_t reserved[4];
+    int32_t no_1q_fusion;  /* 1: never multiply runs of uncontrolled single-qubit gates on one qubit together
+                              (default 0: fused on the host when one micro-op is cheaper than the separate ones) */
+    int32_t reserved[3];
 } qsx_plan_options;
 
 typedef struct qsx_plan_stats {

@@ -441,7 +441,8 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), 1)
             int const n_t = st->n_t;
 #pragma unroll
             for (int k = 0; k < kMaxTileBits; ++k) {
-                uint32_t const b = k < n_t ? ((trow >> k) & 1u) : 0u;
+                if (k >= n_t) break;  // uniform; n_t = m - R (4 at the default tile)
+                uint32_t const b = (trow >> k) & 1u;
                 lbase |= b << st->tl[k];
                 grow |= b << st->tg[k];
             }

@@ -420,7 +420,24 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
                 if (((uint32_t)i & creg) == creg) g0.tab[i] = cmul(g0.tab[i], d0);
         }
     };
+    // Single-qubit fusion: the last uncontrolled non-diagonal op on register bit j that nothing
+    // emitted since involves (no target, control or table dependence on j).  A later uncontrolled
+    // op on j commutes back to it, so the two are multiplied on the host when one micro-op for the
+    // product is cheaper than the separate ones (costs: the measured model of DESIGN.md 3.1).
+    struct Fusable {
+        int idx = -1;  // position in st.uops
+        Cx m[4];
+        double cost = 0;
+    };
+    Fusable fus[kMaxRegBits];
+    auto depends_on = [&](Group const& g, int j) {
+        for (int i = 0; i < E; ++i)
+            if (g.tab[i].re != g.tab[i ^ (1 << j)].re || g.tab[i].im != g.tab[i ^ (1 << j)].im) return true;
+        return false;
+    };
     auto emit_group = [&](Group const& g) {
+        for (int j = 0; j < R; ++j)
+            if (depends_on(g, j)) fus[j].idx = -1;
         uint32_t active = 0;
         for (int i = 0; i < E; ++i)
             if (g.tab[i].re != 1.0 || g.tab[i].im != 0.0) active |= 1u << i;
@@ -473,6 +490,119 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
         groups.swap(keep);
     };
 
+    auto conjugate_tables = [&](bool is_swap, uint32_t creg, int j0, int j1) {
+        for (Group& g : groups) {
+            std::vector<Cx> t((size_t)E);
+            for (int i = 0; i < E; ++i) {
+                int pi = i;
+                if (((uint32_t)i & creg) == creg) {
+                    if (!is_swap)
+                        pi = i ^ (1 << j0);
+                    else if (((i >> j0) & 1) != ((i >> j1) & 1))
+                        pi = i ^ (1 << j0) ^ (1 << j1);
+                }
+                t[(size_t)pi] = g.tab[i];
+            }
+            g.tab.swap(t);
+        }
+    };
+    auto matrix_of = [&](LoweredOp const& op, Cx (&m)[4]) {
+        if (op.kind == OP_H) {
+            m[0] = {op.c[0], 0}, m[1] = {op.c[0], 0}, m[2] = {op.c[0], 0}, m[3] = {-op.c[0], 0};
+        } else if (op.kind == OP_X) {
+            m[0] = {0, 0}, m[1] = {1, 0}, m[2] = {1, 0}, m[3] = {0, 0};
+        } else {
+            for (int i = 0; i < 4; ++i) m[i] = {op.c[2 * i], op.c[2 * i + 1]};
+        }
+    };
+    auto cost_of = [](int kind) { return kind == K_H ? 4.1 : kind == K_X ? 3.7 : 8.1; };
+    // a one-bit diagonal between two ops usually rides along with a table that is emitted anyway,
+    // so absorbing it is not counted as a saving; fusion must win by a clear margin
+    double const kDiagCost = 0.0, kMargin = 0.5;
+    // B = op (an uncontrolled U1 / H / X on register bit u.j0).  Returns true when B was
+    // multiplied into the previous op on that bit (or cancelled against it) and needs no micro-op.
+    auto try_fuse = [&](LoweredOp const& op, MicroOp const& u) -> bool {
+        int const j = u.j0;
+        Fusable& f  = fus[j];
+        // live tables that depend on bit j sit between the previous op and B
+        int absorb = -1;
+        for (size_t gi = 0; gi < groups.size(); ++gi) {
+            Group const& g = groups[gi];
+            if (!depends_on(g, j)) continue;
+            if (op.kind == OP_X) continue;  // a permutation: carried through, not applied
+            bool only_j = g.cother == 0 && g.czero == 0 && absorb < 0;
+            for (int i = 0; i < E && only_j; ++i) {
+                Cx const& want = g.tab[((i >> j) & 1) ? (1 << j) : 0];
+                only_j         = g.tab[i].re == want.re && g.tab[i].im == want.im;
+            }
+            if (!only_j) return false;  // a table on several bits must be applied first: no fusion
+            absorb = (int)gi;
+        }
+        Cx d0{1, 0}, d1{1, 0};
+        if (absorb >= 0) d0 = groups[(size_t)absorb].tab[0], d1 = groups[(size_t)absorb].tab[(size_t)1 << j];
+        Cx mb[4];
+        matrix_of(op, mb);
+        Cx bd[4] = {cmul(mb[0], d0), cmul(mb[1], d1), cmul(mb[2], d0), cmul(mb[3], d1)};  // B * D
+        auto cadd = [](Cx a, Cx b) { return Cx{a.re + b.re, a.im + b.im}; };
+        double const tol = plan.cfg.snap_tol;
+        auto snap = [&](Cx z) { return Cx{snap1(z.re, tol), snap1(z.im, tol)}; };
+        int const bkind = op.kind == OP_H ? K_H : op.kind == OP_X ? K_X : K_U1;
+        if (f.idx >= 0) {
+            Cx m[4] = {snap(cadd(cmul(bd[0], f.m[0]), cmul(bd[1], f.m[2]))), snap(cadd(cmul(bd[0], f.m[1]), cmul(bd[1], f.m[3]))),
+                       snap(cadd(cmul(bd[2], f.m[0]), cmul(bd[3], f.m[2]))), snap(cadd(cmul(bd[2], f.m[1]), cmul(bd[3], f.m[3])))};
+            auto zero = [](Cx z) { return z.re == 0.0 && z.im == 0.0; };
+            auto one  = [](Cx z) { return z.re == 1.0 && z.im == 0.0; };
+            bool const diag = zero(m[1]) && zero(m[2]);
+            bool const isx  = zero(m[0]) && zero(m[3]) && one(m[1]) && one(m[2]);
+            bool const ish  = m[0].im == 0.0 && m[1].im == 0.0 && m[2].im == 0.0 && m[3].im == 0.0 && m[0].re == m[1].re &&
+                             m[0].re == m[2].re && m[0].re == -m[3].re;
+            double const fused_cost = diag ? (one(m[0]) && one(m[3]) ? 0.0 : 0.5) : isx ? 3.7 : ish ? 4.1 : 8.1;
+            double const separate   = f.cost + (absorb >= 0 ? kDiagCost : 0.0) + cost_of(bkind);
+            if (fused_cost + kMargin < separate) {
+                if (op.kind == OP_X && plan.cfg.conjugate_diagonals) conjugate_tables(false, 0u, j, -1);
+                else if (op.kind == OP_X) return false;
+                if (absorb >= 0) groups.erase(groups.begin() + absorb);
+                MicroOp& a = st.uops[(size_t)f.idx];
+                a.n_src += 1;
+                if (diag) {
+                    a.kind = -1;  // dropped below; the product joins the live tables
+                    f.idx  = -1;
+                    if (!(one(m[0]) && one(m[3]))) {
+                        Group& g = group_for(0, 0);
+                        for (int i = 0; i < E; ++i) g.tab[i] = cmul(g.tab[i], ((i >> j) & 1) ? m[3] : m[0]);
+                    }
+                    return true;
+                }
+                std::memset(a.c, 0, sizeof(a.c));
+                if (isx) {
+                    a.kind = K_X, a.c[7] = -0.0;
+                } else if (ish) {
+                    a.kind = K_H, a.c[0] = m[0].re;
+                } else {
+                    a.kind = K_U1;
+                    for (int i = 0; i < 4; ++i) a.c[2 * i] = m[i].re, a.c[2 * i + 1] = m[i].im;
+                }
+                for (int i = 0; i < 4; ++i) f.m[i] = m[i];
+                f.cost = fused_cost;
+                return true;
+            }
+        }
+        if (absorb >= 0 && op.kind == OP_U1) {  // a general 2x2 takes the one-bit diagonal for free
+            groups.erase(groups.begin() + absorb);
+            MicroOp v = u;
+            v.kind    = K_U1;
+            v.n_src   = 1;
+            for (int i = 0; i < 4; ++i) v.c[2 * i] = bd[i].re, v.c[2 * i + 1] = bd[i].im;
+            flush(1u << j);
+            f.idx = (int)st.uops.size();
+            for (int i = 0; i < 4; ++i) f.m[i] = bd[i];
+            f.cost = 8.1;
+            st.uops.push_back(std::move(v));
+            return true;
+        }
+        return false;
+    };
+
     for (int pos = 0; pos < (int)st.ops.size(); ++pos) {
         LoweredOp const& op = plan.ops[st.ops[pos]];
         if (op.tmask() == 0) {
@@ -487,24 +617,16 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
         u.j1     = op.t1 >= 0 ? regidx_of[op.t1] : -1;
         std::memcpy(u.c, op.c, sizeof(u.c));
         uint32_t const jmask = (1u << u.j0) | (u.j1 >= 0 ? 1u << u.j1 : 0u);
+        bool const plain_1q = (op.kind == OP_U1 || op.kind == OP_H || op.kind == OP_X) && u.creg == 0 && u.cother == 0;
+        if (plan.cfg.fuse_1q && plain_1q && try_fuse(op, u)) continue;
         if (plan.cfg.conjugate_diagonals && (op.kind == OP_X || op.kind == OP_SWAP) && u.cother == 0) {
-            for (Group& g : groups) {
-                std::vector<Cx> t((size_t)E);
-                for (int i = 0; i < E; ++i) {
-                    int pi = i;
-                    if (((uint32_t)i & u.creg) == u.creg) {
-                        if (op.kind == OP_X)
-                            pi = i ^ (1 << u.j0);
-                        else if (((i >> u.j0) & 1) != ((i >> u.j1) & 1))
-                            pi = i ^ (1 << u.j0) ^ (1 << u.j1);
-                    }
-                    t[(size_t)pi] = g.tab[i];
-                }
-                g.tab.swap(t);
-            }
+            conjugate_tables(op.kind == OP_SWAP, u.creg, u.j0, u.j1);
         } else {
             flush(jmask);
         }
+        // whatever this op touches in the registers can no longer be fused across
+        for (int j = 0; j < R; ++j)
+            if (((jmask | u.creg) >> j) & 1u) fus[j].idx = -1;
         switch (op.kind) {
             case OP_U1: u.kind = K_U1; break;
             case OP_H: u.kind = K_H; break;
@@ -526,9 +648,16 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
         }
         // the exchange handlers move half of the data through the FP64 pipe as x + (-0.0)
         if (u.kind == K_X || u.kind == K_XC || u.kind == K_SWAP) u.c[7] = -0.0;
+        if (plain_1q) {
+            Fusable& f = fus[u.j0];
+            f.idx      = (int)st.uops.size();
+            matrix_of(op, f.m);
+            f.cost = cost_of(u.kind);
+        }
         st.uops.push_back(std::move(u));
     }
     for (Group const& g : groups) emit_group(g);
+    st.uops.erase(std::remove_if(st.uops.begin(), st.uops.end(), [](MicroOp const& v) { return v.kind < 0; }), st.uops.end());
     if (!scalars.empty()) {
         MicroOp u;
         u.kind = K_SCALN;
@@ -1071,6 +1200,7 @@ int build_plan(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gat
     // the search costs a few ms of host time: worth it once a sweep takes milliseconds (n >= 13)
     cfg.search      = o.search > 0 ? (int)o.search : (o.search < 0 || n_qubits < 13 ? 0 : 3);
     cfg.conjugate_diagonals = o.no_diag_conjugation == 0;
+    cfg.fuse_1q             = o.no_1q_fusion == 0;
 
     plan.stats          = qsx_plan_stats{};
     plan.stats.n_gates  = n_gates;
@@ -1158,7 +1288,7 @@ std::string dump_plan_json(const Plan& plan) {
                 MicroOp const& u = st.uops[i];
                 os << (i ? "," : "") << "{\"kind\":\"" << kMicro[u.kind] << "\",\"j0\":" << u.j0 << ",\"j1\":" << u.j1
                    << ",\"creg\":" << u.creg << ",\"cother\":" << u.cother << ",\"czero\":" << u.czero
-                   << ",\"sel\":" << u.sel << ",\"src\":" << u.src << ",\"c\":[";
+                   << ",\"sel\":" << u.sel << ",\"src\":" << u.src << ",\"n_src\":" << u.n_src << ",\"c\":[";
                 for (int k = 0; k < 8; ++k) os << (k ? "," : "") << u.c[k];
                 os << "],\"table\":[";
                 if (u.kind != K_SCALN)

@@ -35,7 +35,8 @@ struct MicroOp {
     int      sel    = -1;           // K_DSCAL: global row bit choosing d1
     double   c[8]   = {0, 0, 0, 0, 0, 0, 0, 0};
     std::vector<double> table;      // K_DTAB*: complex entries ; K_U2: 4x4 matrix
-    int      src    = -1;           // non-diagonal kinds: position in PlannedStage::ops
+    int      src    = -1;           // non-diagonal kinds: position in PlannedStage::ops (of the first fused op)
+    int      n_src  = 1;            // semantic ops multiplied into this micro-op (single-qubit fusion)
 };
 
 struct PlannedStage {
@@ -71,6 +72,7 @@ struct PlanConfig {
     bool fuse = true;
     bool fold_perms = true;  // fold X / CX / SWAP into the addressing of stage boundaries
     bool defer_perms = false;
+    bool fuse_1q = true;              // multiply runs of uncontrolled single-qubit ops on one register bit
     bool conjugate_diagonals = true;  // carry pending diagonal tables through in-register permutations
     int  dense_k = 0;  // >= 3: fold the gate stream into dense k-qubit blocks (FP64 tensor pipe)  // never swap registers: an X-type op that cannot be hoisted ends the stage
     double snap_tol = 1e-15;

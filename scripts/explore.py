@@ -35,6 +35,7 @@ def main():
     workload = sys.argv[4] if len(sys.argv) > 4 else "clifford_t"
     min_tail = int(sys.argv[5]) if len(sys.argv) > 5 else 0
     search = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+    extra = json.loads(sys.argv[7]) if len(sys.argv) > 7 else {}
     text = W.random_rotation_qasm(n, g, 20261019) if workload == "rot" else W.random_clifford_t_qasm(n, g, 20261019)
     qc = host.Circuit(qasm_text=text)
     gs = qc.gate_array()
@@ -44,7 +45,7 @@ def main():
         pol = cfg[5] if len(cfg) > 5 else 0
         dense = cfg[6] if len(cfg) > 6 else 0
         opt = Q.PlanOptions(fuse=fuse, reg_qubits=R, tile_qubits=tile, log2_tile_cols=w, max_ops_per_sweep=cap, no_perm_folding=pol,
-                            dense_block=dense, min_tail_ops=min_tail, search=search)
+                            dense_block=dense, min_tail_ops=min_tail, search=search, **extra)
         try:
             r = time_plan(n, gs, opt)
         except Exception as e:  # noqa

@@ -158,21 +158,25 @@ def run_plan_uops(dump, u):
                     sel = tsel & (((regidx >> j) & 1) == 1)
                     u[sel] *= tab[kidx[sel]][:, None]
                 else:
-                    op = st["ops"][uop["src"]]
-                    nondiag_seen.append(uop["src"])
-                    # the micro-op must encode the same condition as the semantic op
-                    req = uop["cother"]
+                    # executed from the micro-op's own encoding (what the kernel sees)
                     creg = uop["creg"] | ((1 << uop["j1"]) if k == "XC" else 0)
+                    req = uop["cother"]
                     for j, b in enumerate(rb):
                         if (creg >> j) & 1:
                             req |= 1 << b
-                    assert req == op["req"] and uop["czero"] == 0, (uop, op)
-                    assert rb[uop["j0"]] == op["t0"]
-                    if op["t1"] >= 0 and k != "XC":
-                        assert rb[uop["j1"]] == op["t1"]
-                    apply_op(u, n, op)
+                    assert uop["czero"] == 0
+                    mop = {"kind": "X" if k == "XC" else k, "req": req, "t0": rb[uop["j0"]],
+                           "t1": rb[uop["j1"]] if (uop["j1"] >= 0 and k != "XC") else -1, "c": c, "dbit": -1,
+                           "mat": uop["table"] if k == "U2" else []}
+                    if uop.get("n_src", 1) == 1 and not uop.get("absorbed", False):
+                        # not a product of several gates: must encode the semantic op's condition and targets
+                        op = st["ops"][uop["src"]]
+                        assert req == op["req"] and mop["t0"] == op["t0"], (uop, op)
+                        if op["t1"] >= 0 and k != "XC":
+                            assert mop["t1"] == op["t1"]
+                    nondiag_seen.append(uop["src"])
+                    apply_op(u, n, mop)
             assert nondiag_seen == sorted(nondiag_seen)
-            assert nondiag_seen == [i for i, op in enumerate(st["ops"]) if op["t0"] >= 0]
             if used_scalar:
                 assert st["uops"][-1]["kind"] == "SAPPLY"
             assert np.all(scal == 1)
