@@ -370,16 +370,31 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
     //   * in-register permutations (X / CX / SWAP whose controls are all register bits):
     //     D then P  ==  P then D',  D'[P(i)] = D[i]  -- the table is permuted instead of applied;
     // it is applied right before an op that mixes a bit it depends on, or at the end of the stage.
+    // A group is kept factored: value(i) = tab[i] * prod_j f[j][bit j of i].  Single-bit diagonals
+    // (z, s, t, rz, p ...) go to the factors, so that before an op on bit j only the factor of j has
+    // to be applied (one phase, K_PHJ) or absorbed (general 2x2), while the rest stays live.
     struct Group {
         uint32_t cother, czero;
         std::vector<Cx> tab;
+        Cx f[kMaxRegBits][2];
     };
     std::vector<Group> groups;
     auto group_for = [&](uint32_t cother, uint32_t czero) -> Group& {
         for (Group& g : groups)
             if (g.cother == cother && g.czero == czero) return g;
-        groups.push_back(Group{cother, czero, std::vector<Cx>((size_t)E)});
+        Group g;
+        g.cother = cother, g.czero = czero;
+        g.tab.assign((size_t)E, Cx{});
+        groups.push_back(std::move(g));
         return groups.back();
+    };
+    auto is_unit = [](Cx z) { return z.re == 1.0 && z.im == 0.0; };
+    auto same    = [](Cx a, Cx b) { return a.re == b.re && a.im == b.im; };
+    // folds the factor of bit j into the table (needed before the table is permuted by a controlled op on j)
+    auto merge_factor = [&](Group& g, int j) {
+        if (is_unit(g.f[j][0]) && is_unit(g.f[j][1])) return;
+        for (int i = 0; i < E; ++i) g.tab[i] = cmul(g.tab[i], g.f[j][(i >> j) & 1]);
+        g.f[j][0] = Cx{}, g.f[j][1] = Cx{};
     };
     auto add_diagonal = [&](LoweredOp const& op) {
         uint32_t const creg   = creg_of(op.req);
@@ -403,13 +418,22 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
         if (!is_diag2) {
             Group& g   = group_for(cother, 0);
             Cx const w = phase_of(op);
-            for (int i = 0; i < E; ++i)
-                if (((uint32_t)i & creg) == creg) g.tab[i] = cmul(g.tab[i], w);
+            if (popc(creg) == 1) {
+                int const j = __builtin_ctz(creg);
+                g.f[j][1]   = cmul(g.f[j][1], w);
+            } else {
+                for (int i = 0; i < E; ++i)
+                    if (((uint32_t)i & creg) == creg) g.tab[i] = cmul(g.tab[i], w);
+            }
         } else if (dj >= 0) {
             Group& g = group_for(cother, 0);
             Cx const d0{op.c[0], op.c[1]}, d1{op.c[2], op.c[3]};
-            for (int i = 0; i < E; ++i)
-                if (((uint32_t)i & creg) == creg) g.tab[i] = cmul(g.tab[i], ((i >> dj) & 1) ? d1 : d0);
+            if (creg == 0) {
+                g.f[dj][0] = cmul(g.f[dj][0], d0), g.f[dj][1] = cmul(g.f[dj][1], d1);
+            } else {
+                for (int i = 0; i < E; ++i)
+                    if (((uint32_t)i & creg) == creg) g.tab[i] = cmul(g.tab[i], ((i >> dj) & 1) ? d1 : d0);
+            }
         } else {  // selecting bit outside the registers, a control inside
             Cx const d0{op.c[0], op.c[1]}, d1{op.c[2], op.c[3]};
             Group& g1 = group_for(cother | (1u << op.dbit), 0);
@@ -430,14 +454,17 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
         double cost = 0;
     };
     Fusable fus[kMaxRegBits];
-    auto depends_on = [&](Group const& g, int j) {
+    auto table_depends_on = [&](Group const& g, int j) {
         for (int i = 0; i < E; ++i)
-            if (g.tab[i].re != g.tab[i ^ (1 << j)].re || g.tab[i].im != g.tab[i ^ (1 << j)].im) return true;
+            if (!same(g.tab[i], g.tab[i ^ (1 << j)])) return true;
         return false;
     };
-    auto emit_group = [&](Group const& g) {
-        for (int j = 0; j < R; ++j)
+    auto depends_on = [&](Group const& g, int j) { return !same(g.f[j][0], g.f[j][1]) || table_depends_on(g, j); };
+    auto emit_group = [&](Group g) {  // by value: factors are folded into the copy
+        for (int j = 0; j < R; ++j) {
             if (depends_on(g, j)) fus[j].idx = -1;
+            merge_factor(g, j);
+        }
         uint32_t active = 0;
         for (int i = 0; i < E; ++i)
             if (g.tab[i].re != 1.0 || g.tab[i].im != 0.0) active |= 1u << i;
@@ -472,26 +499,45 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
         }
         st.uops.push_back(std::move(u));
     };
-    // applies (and forgets) every live table that depends on one of the register bits in jmask
+    // applies whatever depends on one of the register bits in jmask: the whole group when its
+    // table does, else only the factors of those bits (a phase on one register bit each)
     auto flush = [&](uint32_t jmask) {
         std::vector<Group> keep;
         for (Group& g : groups) {
-            bool dep = false;
-            for (int j = 0; j < R && !dep; ++j) {
-                if (!((jmask >> j) & 1u)) continue;
-                for (int i = 0; i < E && !dep; ++i)
-                    dep = g.tab[i].re != g.tab[i ^ (1 << j)].re || g.tab[i].im != g.tab[i ^ (1 << j)].im;
-            }
-            if (dep)
+            bool whole = false;
+            for (int j = 0; j < R && !whole; ++j)
+                if ((jmask >> j) & 1u) whole = table_depends_on(g, j) || (!same(g.f[j][0], g.f[j][1]) && !is_unit(g.f[j][0]));
+            if (whole) {
                 emit_group(g);
-            else
-                keep.push_back(std::move(g));
+                continue;
+            }
+            for (int j = 0; j < R; ++j) {
+                if (!((jmask >> j) & 1u) || same(g.f[j][0], g.f[j][1])) continue;
+                MicroOp u;  // f[j][0] == 1: a phase on the bit-j-set half
+                u.kind   = K_PHJ;
+                u.cother = g.cother;
+                u.czero  = g.czero;
+                u.j0     = j;
+                u.c[0] = g.f[j][1].re, u.c[1] = g.f[j][1].im;
+                st.uops.push_back(std::move(u));
+                g.f[j][1]  = Cx{};
+                fus[j].idx = -1;
+            }
+            keep.push_back(std::move(g));
         }
         groups.swap(keep);
     };
-
     auto conjugate_tables = [&](bool is_swap, uint32_t creg, int j0, int j1) {
         for (Group& g : groups) {
+            if (creg != 0) {  // the factor of a conditionally moved bit stops being a one-bit function
+                merge_factor(g, j0);
+                if (is_swap) merge_factor(g, j1);
+            } else if (is_swap) {
+                std::swap(g.f[j0][0], g.f[j1][0]);
+                std::swap(g.f[j0][1], g.f[j1][1]);
+            } else {
+                std::swap(g.f[j0][0], g.f[j0][1]);
+            }
             std::vector<Cx> t((size_t)E);
             for (int i = 0; i < E; ++i) {
                 int pi = i;
@@ -524,22 +570,21 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
     auto try_fuse = [&](LoweredOp const& op, MicroOp const& u) -> bool {
         int const j = u.j0;
         Fusable& f  = fus[j];
-        // live tables that depend on bit j sit between the previous op and B
+        // live diagonals that depend on bit j sit between the previous op and B: an unconditional
+        // one-bit factor can be multiplied into B, anything else has to be applied first
         int absorb = -1;
-        for (size_t gi = 0; gi < groups.size(); ++gi) {
+        for (size_t gi = 0; gi < groups.size() && op.kind != OP_X; ++gi) {  // (a permutation carries them through)
             Group const& g = groups[gi];
-            if (!depends_on(g, j)) continue;
-            if (op.kind == OP_X) continue;  // a permutation: carried through, not applied
-            bool only_j = g.cother == 0 && g.czero == 0 && absorb < 0;
-            for (int i = 0; i < E && only_j; ++i) {
-                Cx const& want = g.tab[((i >> j) & 1) ? (1 << j) : 0];
-                only_j         = g.tab[i].re == want.re && g.tab[i].im == want.im;
-            }
-            if (!only_j) return false;  // a table on several bits must be applied first: no fusion
+            if (table_depends_on(g, j)) return false;
+            if (same(g.f[j][0], g.f[j][1])) continue;
+            if (g.cother != 0 || g.czero != 0 || absorb >= 0) return false;
             absorb = (int)gi;
         }
         Cx d0{1, 0}, d1{1, 0};
-        if (absorb >= 0) d0 = groups[(size_t)absorb].tab[0], d1 = groups[(size_t)absorb].tab[(size_t)1 << j];
+        if (absorb >= 0) d0 = groups[(size_t)absorb].f[j][0], d1 = groups[(size_t)absorb].f[j][1];
+        auto absorbed = [&]() {
+            if (absorb >= 0) groups[(size_t)absorb].f[j][0] = Cx{}, groups[(size_t)absorb].f[j][1] = Cx{};
+        };
         Cx mb[4];
         matrix_of(op, mb);
         Cx bd[4] = {cmul(mb[0], d0), cmul(mb[1], d1), cmul(mb[2], d0), cmul(mb[3], d1)};  // B * D
@@ -561,7 +606,7 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
             if (fused_cost + kMargin < separate) {
                 if (op.kind == OP_X && plan.cfg.conjugate_diagonals) conjugate_tables(false, 0u, j, -1);
                 else if (op.kind == OP_X) return false;
-                if (absorb >= 0) groups.erase(groups.begin() + absorb);
+                absorbed();
                 MicroOp& a = st.uops[(size_t)f.idx];
                 a.n_src += 1;
                 if (diag) {
@@ -569,7 +614,7 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
                     f.idx  = -1;
                     if (!(one(m[0]) && one(m[3]))) {
                         Group& g = group_for(0, 0);
-                        for (int i = 0; i < E; ++i) g.tab[i] = cmul(g.tab[i], ((i >> j) & 1) ? m[3] : m[0]);
+                        g.f[j][0] = cmul(g.f[j][0], m[0]), g.f[j][1] = cmul(g.f[j][1], m[3]);
                     }
                     return true;
                 }
@@ -588,7 +633,7 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
             }
         }
         if (absorb >= 0 && op.kind == OP_U1) {  // a general 2x2 takes the one-bit diagonal for free
-            groups.erase(groups.begin() + absorb);
+            absorbed();
             MicroOp v = u;
             v.kind    = K_U1;
             v.n_src   = 1;
