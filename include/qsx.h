@@ -112,7 +112,10 @@ typedef struct qsx_plan_options {
                                     carrying them through it (default 0)                                        */
     int32_t no_1q_fusion;  /* 1: never multiply runs of uncontrolled single-qubit gates on one qubit together
                               (default 0: fused on the host when one micro-op is cheaper than the separate ones) */
-    int32_t reserved[3];
+    int32_t stage_search;  /* 1: choose each stage's register bits by trying every R-subset of the tile bits;
+                              < 0: first come, first served; 0 (default): on when n >= 13 (costs ~2 ms of host
+                              time per 2000 gates, pays once a sweep takes milliseconds)                        */
+    int32_t reserved[2];
 } qsx_plan_options;
 
 typedef struct qsx_plan_stats {

@@ -55,7 +55,8 @@ class PlanOptions(C.Structure):
                 ("tile_qubits", C.c_int32), ("log2_tile_cols", C.c_int32), ("max_ops_per_sweep", C.c_int32),
                 ("lookahead", C.c_int32), ("dense_block", C.c_int32), ("no_perm_folding", C.c_int32), ("min_tail_ops", C.c_int32),
                 ("search", C.c_int32), ("no_diag_conjugation", C.c_int32),
-                ("no_1q_fusion", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("no_1q_fusion", C.c_int32), ("stage_search", C.c_int32),
+                ("reserved", C.c_int32 * 2)]
 
     def __init__(self, fuse: int = 1, **kw):
         super().__init__()

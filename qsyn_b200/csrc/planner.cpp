@@ -212,6 +212,47 @@ void build_stages(Plan& plan, std::vector<int> chosen, PlannedSweep& sw) {
         int u2_t0 = -1, u2_t1 = -1;
         Picker pk;
         std::vector<int> rest;
+        // Register bits of the stage: first come, first served -- or (stage_search) the R-subset of
+        // the tile bits under which the stage takes the most register ops.  The trial pass ignores
+        // the affinity test of folded permutations; it only ranks subsets.
+        uint32_t allowed = 0;
+        if (plan.cfg.stage_search && (int)sw.tile_bits.size() > R) {
+            uint32_t tile_mask = 0;
+            for (int b : sw.tile_bits) tile_mask |= 1u << b;
+            auto trial = [&](uint32_t cand) {
+                Picker tp;
+                uint32_t cT = 0, cA = 0;
+                int score = 0;
+                for (int idx : chosen) {
+                    LoweredOp const& op = plan.ops[idx];
+                    if (!tp.passes(op)) {
+                        tp.block(op);
+                        continue;
+                    }
+                    uint32_t const T = op.tmask(), A = T | op.dmask();
+                    if (plan.cfg.fold_perms && is_perm_op(op) && (T & cA) == 0 && (A & cT) == 0 && popc(op.req) <= 1) continue;
+                    if ((T & ~cand) == 0 && op.kind != OP_U2) {
+                        cT |= T, cA |= A;
+                        // a permutation gains nothing from sitting in registers (it may fold at the next boundary)
+                        score += T == 0 ? 1 : is_perm_op(op) ? 0 : 4;
+                    } else {
+                        tp.block(op);
+                    }
+                }
+                return score;
+            };
+            int best = -1;
+            for (uint32_t cand = tile_mask;; cand = (cand - 1) & tile_mask) {  // all submasks of the tile
+                if (popc(cand) == R) {
+                    int const sc = trial(cand);
+                    if (sc > best) best = sc, allowed = cand;
+                }
+                if (cand == 0) break;
+            }
+            // two-target dense ops need the first-come rule (their pair is pinned to register bits 1, 0)
+            for (int idx : chosen)
+                if (plan.ops[idx].kind == OP_U2) allowed = 0;
+        }
         for (int idx : chosen) {
             LoweredOp const& op = plan.ops[idx];
             if (!pk.passes(op)) {
@@ -237,7 +278,7 @@ void build_stages(Plan& plan, std::vector<int> chosen, PlannedSweep& sw) {
                     continue;
                 }
             }
-            bool ok = popc(rm | T) <= R;
+            bool ok = allowed != 0 ? (T & ~allowed) == 0 : popc(rm | T) <= R;
             if (ok && op.kind == OP_U2 && u2_t0 >= 0 && (u2_t0 != op.t0 || u2_t1 != op.t1)) ok = false;
             if (ok) {
                 if (op.kind == OP_U2) u2_t0 = op.t0, u2_t1 = op.t1;
@@ -1246,6 +1287,7 @@ int build_plan(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gat
     cfg.search      = o.search > 0 ? (int)o.search : (o.search < 0 || n_qubits < 13 ? 0 : 3);
     cfg.conjugate_diagonals = o.no_diag_conjugation == 0;
     cfg.fuse_1q             = o.no_1q_fusion == 0;
+    cfg.stage_search        = o.stage_search > 0 || (o.stage_search == 0 && n_qubits >= 13);
 
     plan.stats          = qsx_plan_stats{};
     plan.stats.n_gates  = n_gates;

@@ -72,6 +72,7 @@ struct PlanConfig {
     bool fuse = true;
     bool fold_perms = true;  // fold X / CX / SWAP into the addressing of stage boundaries
     bool defer_perms = false;
+    bool stage_search = false;        // pick each stage's register bits by trying every R-subset of the tile
     bool fuse_1q = true;              // multiply runs of uncontrolled single-qubit ops on one register bit
     bool conjugate_diagonals = true;  // carry pending diagonal tables through in-register permutations
     int  dense_k = 0;  // >= 3: fold the gate stream into dense k-qubit blocks (FP64 tensor pipe)  // never swap registers: an X-type op that cannot be hoisted ends the stage
