@@ -154,9 +154,15 @@ typedef struct qsx_run_stats {
  * returns non-zero the call drains the stream and returns QSX_ERR_INTERRUPTED. */
 int qsx_plan_run(const qsx_plan* plan, qsx_unitary* u, qsx_stop_fn should_stop, void* stop_arg,
                  uint32_t flags, qsx_run_stats* stats);
-/* convenience: plan_create + plan_run + plan_destroy */
+/* One-shot: schedule the stream, stage its programs (pinned staging, no stream synchronisation) and
+ * run it.  This is what to_tensor(QCir) calls (qcir_to_tensor.cpp:143-214). */
 int qsx_apply_gates(qsx_unitary* u, const qsx_gate* gates, size_t n_gates, const qsx_plan_options* opt,
                     qsx_stop_fn should_stop, void* stop_arg, qsx_run_stats* stats);
+/* Same, but returns as soon as the sweeps are enqueued on the device's stream: the host can schedule
+ * the next operand while this one is being built.  Errors of the sweeps surface at the next
+ * synchronising call on the device (download, equiv_partial, qsx_device_synchronize). */
+int qsx_apply_gates_async(qsx_unitary* u, const qsx_gate* gates, size_t n_gates, const qsx_plan_options* opt,
+                          qsx_run_stats* stats);
 
 /* ---- verification: replaces inner_product / cosine_similarity (tensor.hpp:393-403) and
  *      global_scalar_factor / global_norm / global_phase / is_equivalent (qtensor.hpp:383-417) ---- */

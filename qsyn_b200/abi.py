@@ -113,6 +113,7 @@ def _declare(L: C.CDLL) -> None:
         "qsx_plan_run": [vp, vp, STOP_FN, vp, C.c_uint32, C.POINTER(RunStats)],
         "qsx_apply_gates": [vp, C.POINTER(GateStruct), C.c_size_t, C.POINTER(PlanOptions), STOP_FN, vp,
                             C.POINTER(RunStats)],
+        "qsx_apply_gates_async": [vp, C.POINTER(GateStruct), C.c_size_t, C.POINTER(PlanOptions), C.POINTER(RunStats)],
         "qsx_equiv_partial": [vp, vp, dp],
         "qsx_equiv_finish": [dp, C.c_double, i32, C.POINTER(EquivResult)],
         "qsx_unitary_adjoint_inplace": [vp],
@@ -244,6 +245,16 @@ class Unitary:
         _check(lib().qsx_apply_gates(self._h, arr, n, C.byref(options) if options is not None else None, cb, None,
                                      C.byref(st)))
         return st
+
+    def apply_async(self, gates, options: PlanOptions | None = None) -> RunStats:
+        """qsx_apply_gates_async: returns once the sweeps are enqueued (gates: tuples or (qsx_gate*, count))."""
+        if isinstance(gates, tuple) and len(gates) == 2 and isinstance(gates[1], int):
+            arr, n, keep = gates[0], gates[1], None
+        else:
+            arr, keep, n = pack_gates(gates)
+        st = RunStats()
+        _check(lib().qsx_apply_gates_async(self._h, arr, n, C.byref(options) if options is not None else None, C.byref(st)))
+        return st  # (the gate matrices are only read while scheduling, i.e. before the call returns)
 
     def equiv_partial(self, other: "Unitary") -> np.ndarray:
         out = np.zeros(8, dtype=np.float64)

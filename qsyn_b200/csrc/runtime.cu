@@ -61,9 +61,18 @@ struct DeviceCtx {
     double*      scratch  = nullptr;  // equiv partials + 8 outputs
     double*      host8    = nullptr;  // pinned
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+    // one-shot programs of qsx_apply_gates*: a grow-only device buffer (reuse is ordered by the
+    // stream) fed from two pinned staging buffers (reuse is ordered by an event each)
+    unsigned char* prog_dev = nullptr;
+    size_t         prog_dev_cap = 0;
+    unsigned char* prog_pin[2] = {nullptr, nullptr};
+    size_t         prog_pin_cap[2] = {0, 0};
+    cudaEvent_t    prog_ev[2] = {nullptr, nullptr};
+    int            prog_slot = 0;
 };
 
 std::mutex g_mu;
+std::mutex g_prog_mu;  // guards the program staging state of every DeviceCtx (held for microseconds)
 std::map<int, DeviceCtx> g_ctx;
 
 int device_count_nothrow() {
@@ -154,8 +163,9 @@ int qsx_unitary_set_identity(qsx_unitary* u) {
     if (u == nullptr) return fail(QSX_ERR_BAD_ARG, "null unitary");
     DeviceCtx* c = nullptr;
     if (int rc = get_ctx(u->device, &c)) return rc;
+    // stream-ordered like every other operation on the unitary; host-visible results
+    // (download, equiv sums) synchronise on their own
     QSX_CUDA(qsx::launch_set_identity(u->data, u->n, u->col0, u->ncols, c->stream));
-    QSX_CUDA(cudaStreamSynchronize(c->stream));
     return QSX_OK;
 }
 
@@ -265,30 +275,10 @@ int qsx_plan_dump(const qsx_plan* plan, char* buf, size_t buf_size, size_t* need
     return QSX_OK;
 }
 
-int qsx_plan_run(const qsx_plan* cplan, qsx_unitary* u, qsx_stop_fn should_stop, void* stop_arg, uint32_t flags,
-                 qsx_run_stats* stats) {
-    if (cplan == nullptr || u == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
-    auto* plan           = const_cast<qsx_plan*>(cplan);
-    qsx::Plan const& pl  = plan->plan;
-    if (pl.cfg.n != u->n || pl.cfg.ncols != u->ncols)
-        return fail(QSX_ERR_SHAPE, "plan was built for a different shard geometry");
-    if (stats != nullptr) *stats = qsx_run_stats{};
-    DeviceCtx* c = nullptr;
-    if (int rc = get_ctx(u->device, &c)) return rc;
-    if (pl.sweeps.empty()) return QSX_OK;
-    unsigned char* dblob = nullptr;
-    {
-        std::lock_guard<std::mutex> lk(plan->mu);
-        auto it = plan->device_blob.find(u->device);
-        if (it == plan->device_blob.end()) {
-            QSX_CUDA(cudaMalloc(&dblob, pl.blob.size()));
-            QSX_CUDA(cudaMemcpyAsync(dblob, pl.blob.data(), pl.blob.size(), cudaMemcpyHostToDevice, c->stream));
-            QSX_CUDA(cudaStreamSynchronize(c->stream));  // pl.blob is pageable
-            plan->device_blob.emplace(u->device, dblob);
-        } else {
-            dblob = it->second;
-        }
-    }
+namespace {
+// enqueues the sweeps of a plan whose programs are at dblob (device); synchronises unless QSX_RUN_ASYNC
+int run_sweeps(qsx::Plan const& pl, qsx_unitary* u, DeviceCtx* c, unsigned char* dblob, qsx_stop_fn should_stop,
+               void* stop_arg, uint32_t flags, qsx_run_stats* stats) {
     bool const async = (flags & QSX_RUN_ASYNC) != 0;
     if (!async) QSX_CUDA(cudaEventRecord(c->ev0, c->stream));
     uint64_t launches = 0;
@@ -323,17 +313,97 @@ int qsx_plan_run(const qsx_plan* cplan, qsx_unitary* u, qsx_stop_fn should_stop,
     }
     return QSX_OK;
 }
+}  // namespace
+
+int qsx_plan_run(const qsx_plan* cplan, qsx_unitary* u, qsx_stop_fn should_stop, void* stop_arg, uint32_t flags,
+                 qsx_run_stats* stats) {
+    if (cplan == nullptr || u == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    auto* plan           = const_cast<qsx_plan*>(cplan);
+    qsx::Plan const& pl  = plan->plan;
+    if (pl.cfg.n != u->n || pl.cfg.ncols != u->ncols)
+        return fail(QSX_ERR_SHAPE, "plan was built for a different shard geometry");
+    if (stats != nullptr) *stats = qsx_run_stats{};
+    DeviceCtx* c = nullptr;
+    if (int rc = get_ctx(u->device, &c)) return rc;
+    if (pl.sweeps.empty()) return QSX_OK;
+    unsigned char* dblob = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(plan->mu);
+        auto it = plan->device_blob.find(u->device);
+        if (it == plan->device_blob.end()) {
+            QSX_CUDA(cudaMalloc(&dblob, pl.blob.size()));
+            QSX_CUDA(cudaMemcpyAsync(dblob, pl.blob.data(), pl.blob.size(), cudaMemcpyHostToDevice, c->stream));
+            QSX_CUDA(cudaStreamSynchronize(c->stream));  // pl.blob is pageable
+            plan->device_blob.emplace(u->device, dblob);
+        } else {
+            dblob = it->second;
+        }
+    }
+    return run_sweeps(pl, u, c, dblob, should_stop, stop_arg, flags, stats);
+}
+
+namespace {
+// stages a one-shot plan's programs on the device without synchronising the stream
+int stage_programs(DeviceCtx* c, qsx::Plan const& pl, unsigned char** dblob) {
+    std::lock_guard<std::mutex> lk(g_prog_mu);
+    size_t const bytes = pl.blob.size();
+    if (bytes > c->prog_dev_cap) {
+        if (c->prog_dev != nullptr) QSX_CUDA(cudaFree(c->prog_dev));  // (waits for the sweeps that read it)
+        c->prog_dev     = nullptr;
+        c->prog_dev_cap = 0;
+        size_t const cap = std::max(bytes * 2, size_t{1} << 20);
+        QSX_CUDA(cudaMalloc(&c->prog_dev, cap));
+        c->prog_dev_cap = cap;
+    }
+    int const slot = c->prog_slot ^= 1;
+    if (c->prog_ev[slot] == nullptr) QSX_CUDA(cudaEventCreateWithFlags(&c->prog_ev[slot], cudaEventDisableTiming));
+    QSX_CUDA(cudaEventSynchronize(c->prog_ev[slot]));  // the copy that last read this staging buffer is done
+    if (bytes > c->prog_pin_cap[slot]) {
+        if (c->prog_pin[slot] != nullptr) QSX_CUDA(cudaFreeHost(c->prog_pin[slot]));
+        c->prog_pin[slot]     = nullptr;
+        c->prog_pin_cap[slot] = 0;
+        size_t const cap = std::max(bytes * 2, size_t{1} << 20);
+        QSX_CUDA(cudaMallocHost(&c->prog_pin[slot], cap));
+        c->prog_pin_cap[slot] = cap;
+    }
+    std::memcpy(c->prog_pin[slot], pl.blob.data(), bytes);
+    QSX_CUDA(cudaMemcpyAsync(c->prog_dev, c->prog_pin[slot], bytes, cudaMemcpyHostToDevice, c->stream));
+    QSX_CUDA(cudaEventRecord(c->prog_ev[slot], c->stream));
+    *dblob = c->prog_dev;
+    return QSX_OK;
+}
+
+int apply_impl(qsx_unitary* u, const qsx_gate* gates, size_t n_gates, const qsx_plan_options* opt, qsx_stop_fn should_stop,
+               void* stop_arg, uint32_t flags, qsx_run_stats* stats) {
+    if (u == nullptr) return fail(QSX_ERR_BAD_ARG, "null unitary");
+    if (stats != nullptr) *stats = qsx_run_stats{};
+    qsx::Plan pl;
+    std::string msg;
+    int rc;
+    try {
+        rc = qsx::build_plan(u->n, u->ncols, gates, n_gates, opt, pl, msg);
+    } catch (std::bad_alloc const&) {
+        rc  = QSX_ERR_OOM;
+        msg = "host allocation failed while planning";
+    }
+    if (rc != QSX_OK) return fail(rc, msg);
+    DeviceCtx* c = nullptr;
+    if (int e = get_ctx(u->device, &c)) return e;
+    if (pl.sweeps.empty()) return QSX_OK;
+    unsigned char* dblob = nullptr;
+    if (int e = stage_programs(c, pl, &dblob)) return e;
+    return run_sweeps(pl, u, c, dblob, should_stop, stop_arg, flags, stats);
+}
+}  // namespace
 
 int qsx_apply_gates(qsx_unitary* u, const qsx_gate* gates, size_t n_gates, const qsx_plan_options* opt,
                     qsx_stop_fn should_stop, void* stop_arg, qsx_run_stats* stats) {
-    if (u == nullptr) return fail(QSX_ERR_BAD_ARG, "null unitary");
-    qsx_plan* plan = nullptr;
-    if (int rc = qsx_plan_create(u->n, u->ncols, gates, n_gates, opt, &plan)) return rc;
-    int const rc = qsx_plan_run(plan, u, should_stop, stop_arg, 0, stats);
-    std::string const keep = g_err;
-    qsx_plan_destroy(plan);
-    g_err = keep;
-    return rc;
+    return apply_impl(u, gates, n_gates, opt, should_stop, stop_arg, 0u, stats);
+}
+
+int qsx_apply_gates_async(qsx_unitary* u, const qsx_gate* gates, size_t n_gates, const qsx_plan_options* opt,
+                          qsx_run_stats* stats) {
+    return apply_impl(u, gates, n_gates, opt, nullptr, nullptr, QSX_RUN_ASYNC, stats);
 }
 
 // ---- verification -----------------------------------------------------------------------

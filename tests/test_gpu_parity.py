@@ -312,3 +312,18 @@ def test_repeated_runs_are_bitwise_identical(opts):
             assert frob_rel(got, O.to_matrix_rowform(qc)) < TOL
         else:
             assert np.array_equal(got.view(np.float64), first.view(np.float64))
+
+
+def test_async_apply_matches_sync_and_reuses_staging():
+    """qsx_apply_gates_async: several one-shot programs in flight through the two pinned staging
+    buffers and the single device program buffer (reuse ordered by events / the stream)."""
+    n = 9
+    circuits = [_rand_circuit(n, 150 + 40 * k, 30 + k) for k in range(5)]
+    want = [run_device(qc) for qc in circuits]
+    us = [Q.Unitary(n) for _ in circuits]
+    for u, qc in zip(us, circuits):  # no synchronisation between the five submissions
+        st = u.apply_async(O.gate_stream(qc))
+        assert st.launches > 0 and st.device_ms == 0
+    for u, w in zip(us, want):
+        assert np.array_equal(u.download().view(np.float64), w.view(np.float64))
+        u.close()
