@@ -95,7 +95,7 @@ typedef struct qsx_plan_options {
     int32_t fuse;          /* 0: one sweep per gate (no scheduling); 1 (default): blocked multi-gate sweeps     */
     double  snap_tol;      /* matrix entries within snap_tol of 0 / +-1 / +-i are snapped (default 1e-15);
                               < 0 disables snapping: the host-built matrices are applied as given               */
-    int32_t reg_qubits;    /* qubits held in registers per thread (1..4, default 4)                             */
+    int32_t reg_qubits;    /* qubits held in registers per thread (1..5, default 4; 5 was measured slower)      */
     int32_t tile_qubits;   /* max row bits staged per shared-memory tile (default 8)                            */
     int32_t log2_tile_cols;/* log2 of tile width in columns (default 3 -> 128 B contiguous per row)             */
     int32_t max_ops_per_sweep; /* cap on ops per sweep (default 96)                                             */

@@ -252,26 +252,26 @@ template <int R, int H>
 __device__ __forceinline__ void run_handler(double2 (&e)[1 << R], double2& scal, const DevOp* __restrict__ op, uint32_t creg,
                                             int pool_off, int sel, uint32_t grow, const double* __restrict__ pool) {
     const double* const c = op->c;
-    if constexpr ((H >= H_H && H < H_H + 4) || (H >= H_HG && H < H_HG + 4)) {
-        constexpr bool all = H < H_H + 4;
+    if constexpr ((H >= H_H && H < H_H + kJ) || (H >= H_HG && H < H_HG + kJ)) {
+        constexpr bool all = H < H_H + kJ;
         constexpr int J    = all ? H - H_H : H - H_HG;
         if constexpr (J < R) op_h<R, J, all>(e, c[0], creg);
-    } else if constexpr ((H >= H_X && H < H_X + 4) || (H >= H_XG && H < H_XG + 4)) {
-        constexpr bool all = H < H_X + 4;
+    } else if constexpr ((H >= H_X && H < H_X + kJ) || (H >= H_XG && H < H_XG + kJ)) {
+        constexpr bool all = H < H_X + kJ;
         constexpr int J    = all ? H - H_X : H - H_XG;
         if constexpr (J < R) op_x<R, J, all>(e, creg, c[7]);
-    } else if constexpr (H >= H_XC && H < H_XC + 16) {
-        constexpr int J = (H - H_XC) >> 2, JC = (H - H_XC) & 3;
+    } else if constexpr (H >= H_XC && H < H_XC + kJ * kJ) {
+        constexpr int J = (H - H_XC) / kJ, JC = (H - H_XC) % kJ;
         if constexpr (J < R && JC < R && J != JC) op_xc<R, J, JC>(e, c[7]);
-    } else if constexpr ((H >= H_U1 && H < H_U1 + 4) || (H >= H_U1G && H < H_U1G + 4)) {
-        constexpr bool all = H < H_U1 + 4;
+    } else if constexpr ((H >= H_U1 && H < H_U1 + kJ) || (H >= H_U1G && H < H_U1G + kJ)) {
+        constexpr bool all = H < H_U1 + kJ;
         constexpr int J    = all ? H - H_U1 : H - H_U1G;
         if constexpr (J < R) op_u1<R, J, all>(e, c, creg);
-    } else if constexpr (H >= H_AD && H < H_ADG + 4) {
-        constexpr int J = (H - H_AD) & 3;
+    } else if constexpr (H >= H_AD && H < H_ADG + kJ) {
+        constexpr int J = (H - H_AD) % kJ;
         if constexpr (J < R) op_ad<R, J, (H < H_ADG)>(e, c, creg);
-    } else if constexpr (H >= H_SWAP && H < H_SWAPG + 16) {
-        constexpr int JA = ((H - H_SWAP) & 15) >> 2, JB = (H - H_SWAP) & 3;
+    } else if constexpr (H >= H_SWAP && H < H_SWAPG + kJ * kJ) {
+        constexpr int JA = ((H - H_SWAP) % (kJ * kJ)) / kJ, JB = (H - H_SWAP) % kJ;
         if constexpr (JA < R && JB < JA) op_swap<R, JA, JB, (H < H_SWAPG)>(e, creg, c[7]);
     } else if constexpr (H == H_U2) {
         op_u2<R>(e, pool + pool_off, creg);
@@ -279,10 +279,10 @@ __device__ __forceinline__ void run_handler(double2 (&e)[1 << R], double2& scal,
         bool const hi   = sel >= 0 && ((grow >> sel) & 1u);
         double2 const d = hi ? make_double2(c[2], c[3]) : make_double2(c[0], c[1]);
         scal            = cmul(scal, d);
-    } else if constexpr (H >= H_DTABH && H < H_DTABH + 4) {
+    } else if constexpr (H >= H_DTABH && H < H_DTABH + kJ) {
         constexpr int J = H - H_DTABH;
         if constexpr (J < R) op_dtab_half<R, J>(e, reinterpret_cast<const double2*>(pool + pool_off));
-    } else if constexpr (H >= H_PHJ && H < H_PHJ + 4) {
+    } else if constexpr (H >= H_PHJ && H < H_PHJ + kJ) {
         constexpr int J = H - H_PHJ;
         if constexpr (J < R) {
             double2 const w = make_double2(c[0], c[1]);
@@ -321,6 +321,7 @@ __device__ __forceinline__ void run_handler(double2 (&e)[1 << R], double2& scal,
 #define QSX_CASE(h) \
     case h: run_handler<R, h>(e, scal, op, creg, pool_off, sel, grow, pool); break;
 #define QSX_CASE8(b) QSX_CASE(b) QSX_CASE(b + 1) QSX_CASE(b + 2) QSX_CASE(b + 3) QSX_CASE(b + 4) QSX_CASE(b + 5) QSX_CASE(b + 6) QSX_CASE(b + 7)
+#define QSX_CASE16(b) QSX_CASE8(b) QSX_CASE8(b + 8)
 
 // hdr = {handler, j0, j1, creg}, hdr2 = {cother, czero, pool, sel}: already loaded (prefetched) by the caller
 template <int R, bool LEAN>
@@ -331,41 +332,33 @@ __device__ __forceinline__ void apply_op(double2 (&e)[1 << R], double2& scal, co
     if ((grow & cother) != cother || (grow & czero) != 0u) return;
     int const pool_off = hdr2.z, sel = hdr2.w;
     if constexpr (LEAN) {
-        switch (hdr.x) {  // dense 0..H_COMMON-1: one jump table
-            QSX_CASE8(0)
-            QSX_CASE8(8)
-            QSX_CASE8(16)
-            QSX_CASE8(24)
-            QSX_CASE(32)
-            QSX_CASE(33)
-            QSX_CASE(34)
-            QSX_CASE(35)
-            QSX_CASE(36)
-            QSX_CASE(37)
+        switch (hdr.x) {  // dense 0..H_COMMON-1
+            QSX_CASE16(0)
+            QSX_CASE16(16)
+            QSX_CASE16(32)
+            QSX_CASE(48)
+            QSX_CASE(49)
+            QSX_CASE(50)
+            QSX_CASE(51)
             default: break;
         }
     } else {
         switch (hdr.x) {
-            QSX_CASE8(0)
-            QSX_CASE8(8)
-            QSX_CASE8(16)
-            QSX_CASE8(24)
-            QSX_CASE8(32)
-            QSX_CASE8(40)
-            QSX_CASE8(48)
-            QSX_CASE8(56)
-            QSX_CASE8(64)
-            QSX_CASE8(72)
-            QSX_CASE8(80)
-            QSX_CASE(88)
-            QSX_CASE(89)
-            QSX_CASE(90)
-            QSX_CASE(91)
-            QSX_CASE(92)
+            QSX_CASE16(0)
+            QSX_CASE16(16)
+            QSX_CASE16(32)
+            QSX_CASE16(48)
+            QSX_CASE16(64)
+            QSX_CASE16(80)
+            QSX_CASE16(96)
+            QSX_CASE16(112)
+            QSX_CASE(128)
+            QSX_CASE(129)
             default: break;
         }
     }
 }
+#undef QSX_CASE16
 #undef QSX_CASE8
 #undef QSX_CASE
 
@@ -391,7 +384,7 @@ __device__ __forceinline__ void permute_rows(uint32_t (&rows)[R + 1], const DevP
 }
 
 template <int R, bool LEAN>
-__global__ void __launch_bounds__(1 << max_threads_log2(R), 1)
+__global__ void __launch_bounds__(1 << max_threads_log2(R), min_ctas_per_sm(R))
     sweep_kernel(double2* __restrict__ u, const unsigned char* __restrict__ gprog, uint32_t prog_bytes, int log2_ncols,
                  int log2_ncb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -937,6 +930,8 @@ cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, int R, const DevSwee
         case 7: return launch_sweep_r<3, true>(u, n, ncols, hs, prog, prog_bytes, s);
         case 8: return launch_sweep_r<4, false>(u, n, ncols, hs, prog, prog_bytes, s);
         case 9: return launch_sweep_r<4, true>(u, n, ncols, hs, prog, prog_bytes, s);
+        case 10: return launch_sweep_r<5, false>(u, n, ncols, hs, prog, prog_bytes, s);
+        case 11: return launch_sweep_r<5, true>(u, n, ncols, hs, prog, prog_bytes, s);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -202,6 +202,7 @@ bool boundary_accept(LoweredOp const& op, uint32_t& taint) {
 
 void build_stages(Plan& plan, std::vector<int> chosen, PlannedSweep& sw) {
     int const R = plan.cfg.R;
+    bool first_come_once = false;  // set when a searched register set made no progress
     while (!chosen.empty()) {
         PlannedStage st;
         bool const first = sw.stages.empty();
@@ -216,7 +217,7 @@ void build_stages(Plan& plan, std::vector<int> chosen, PlannedSweep& sw) {
         // the tile bits under which the stage takes the most register ops.  The trial pass ignores
         // the affinity test of folded permutations; it only ranks subsets.
         uint32_t allowed = 0;
-        if (plan.cfg.stage_search && (int)sw.tile_bits.size() > R) {
+        if (plan.cfg.stage_search && !first_come_once && (int)sw.tile_bits.size() > R) {
             uint32_t tile_mask = 0;
             for (int b : sw.tile_bits) tile_mask |= 1u << b;
             auto trial = [&](uint32_t cand) {
@@ -234,7 +235,7 @@ void build_stages(Plan& plan, std::vector<int> chosen, PlannedSweep& sw) {
                     if ((T & ~cand) == 0 && op.kind != OP_U2) {
                         cT |= T, cA |= A;
                         // a permutation gains nothing from sitting in registers (it may fold at the next boundary)
-                        score += T == 0 ? 1 : is_perm_op(op) ? 0 : 4;
+                        score += is_perm_op(op) || T == 0 ? 1 : 4;
                     } else {
                         tp.block(op);
                     }
@@ -291,6 +292,11 @@ void build_stages(Plan& plan, std::vector<int> chosen, PlannedSweep& sw) {
                 rest.push_back(idx);
             }
         }
+        if (allowed != 0 && rest.size() == chosen.size()) {  // nothing placed or folded: the ranking misled us
+            first_come_once = true;
+            continue;
+        }
+        first_come_once = false;
         chosen.swap(rest);
         if (st.ops.empty() && st.pre.empty()) continue;  // everything went to the previous boundary
         // register-bit assignment: a U2 pair must sit on register bits (1,0)
@@ -1052,12 +1058,12 @@ int handler_of(MicroOp const& u) {
     switch (u.kind) {
         case K_H: return (g ? H_HG : H_H) + u.j0;
         case K_X: return (g ? H_XG : H_X) + u.j0;
-        case K_XC: return H_XC + u.j0 * 4 + u.j1;
+        case K_XC: return H_XC + u.j0 * kJ + u.j1;
         case K_U1: return (g ? H_U1G : H_U1) + u.j0;
         case K_AD: return (g ? H_ADG : H_AD) + u.j0;
         case K_SWAP: {
             int const ja = std::max(u.j0, u.j1), jb = std::min(u.j0, u.j1);
-            return (g ? H_SWAPG : H_SWAP) + ja * 4 + jb;
+            return (g ? H_SWAPG : H_SWAP) + ja * kJ + jb;
         }
         case K_U2: return H_U2;
         case K_DSCAL: return H_DSCAL;

@@ -23,13 +23,15 @@
 
 namespace qsx {
 
-constexpr int kMaxRegBits  = 4;
+constexpr int kMaxRegBits  = 5;
 constexpr int kMaxTileBits = 11;
 constexpr int kMaxRowBits  = 26;
 
 // CTA size limit of sweep_kernel<R>: 2^R complex128 live in registers per thread, so the
-// R >= 3 instantiations are compiled for <= 512 threads (128 registers), the others for 1024.
-QSX_HD constexpr int max_threads_log2(int R) { return R >= 3 ? 9 : 10; }
+// R = 3, 4 instantiations are compiled for <= 512 threads (128 registers), R = 5 (32 elements =
+// 128 data registers) for 128 threads x 3 CTAs per SM (170 registers), the others for 1024.
+QSX_HD constexpr int max_threads_log2(int R) { return R >= 5 ? 7 : R >= 3 ? 9 : 10; }
+QSX_HD constexpr int min_ctas_per_sm(int R) { return R >= 5 ? 2 : 1; }
 
 // semantic kinds of lowered gates (host side, planner + dumps)
 enum OpKind : int32_t {
@@ -64,33 +66,35 @@ enum MicroKind : int32_t {
                     //   s *= pass ? (sel >= 0 && row bit sel ? d1 : d0) : 1 ; then e[i] *= s
 };
 
-// Flat handler ids: the kernel dispatches every micro-op with ONE jump-table branch.  A handler
-// is a (kind, register bit(s), "has in-register controls") combination, numbered for the
-// maximum R = 4; combinations that do not exist for a smaller R are never emitted.
+// Flat handler ids: the kernel dispatches every micro-op with ONE switch.  A handler is a (kind,
+// register bit(s), "has in-register controls") combination, numbered for the maximum R = kJ;
+// combinations that do not exist for a smaller R are never emitted.
+constexpr int kJ = kMaxRegBits;
 enum Handler : int32_t {
-    // -- common handlers, numbered densely from 0 so that the lean kernel's switch is ONE jump table --
-    H_H      = 0,   // +J          uncontrolled inside the registers (no per-element tests)
-    H_X      = 4,   // +J
-    H_XC     = 8,   // +J*4+JC
-    H_U1     = 24,  // +J
-    H_DTABH  = 28,  // +J
-    H_DTABF  = 32,
-    H_SCALN  = 33,
-    H_PHJ    = 34,  // +J
-    H_COMMON = 38,  // number of common handlers
+    // -- common handlers, numbered densely from 0 (the lean kernel contains only these) --
+    H_H      = 0,                    // +J          uncontrolled inside the registers (no per-element tests)
+    H_X      = H_H + kJ,             // +J
+    H_XC     = H_X + kJ,             // +J*kJ+JC
+    H_U1     = H_XC + kJ * kJ,       // +J
+    H_DTABH  = H_U1 + kJ,            // +J
+    H_DTABF  = H_DTABH + kJ,
+    H_SCALN  = H_DTABF + 1,
+    H_PHJ    = H_SCALN + 1,          // +J
+    H_COMMON = H_PHJ + kJ,           // number of common handlers
     // -- rare handlers (full kernel only) --
-    H_HG     = 38,  // +J          generic: runtime creg
-    H_XG     = 42,  // +J
-    H_U1G    = 46,  // +J
-    H_AD     = 50,  // +J
-    H_ADG    = 54,  // +J
-    H_SWAP   = 58,  // +JA*4+JB  (JA > JB)
-    H_SWAPG  = 74,  // +JA*4+JB
-    H_U2     = 90,
-    H_DSCAL  = 91,
-    H_SAPPLY = 92,
-    H_COUNT  = 93,
+    H_HG     = H_COMMON,             // +J          generic: runtime creg
+    H_XG     = H_HG + kJ,            // +J
+    H_U1G    = H_XG + kJ,            // +J
+    H_AD     = H_U1G + kJ,           // +J
+    H_ADG    = H_AD + kJ,            // +J
+    H_SWAP   = H_ADG + kJ,           // +JA*kJ+JB  (JA > JB)
+    H_SWAPG  = H_SWAP + kJ * kJ,     // +JA*kJ+JB
+    H_U2     = H_SWAPG + kJ * kJ,
+    H_DSCAL  = H_U2 + 1,
+    H_SAPPLY = H_DSCAL + 1,
+    H_COUNT  = H_SAPPLY + 1,
 };
+static_assert(H_COMMON == 52 && H_COUNT == 130, "the kernel's switch enumerates these ranges");
 
 // Thread-level predicate of every micro-op: (row & cother) == cother && (row & czero) == 0, where
 // `row` is the thread's global row index with the register bits cleared.
@@ -123,7 +127,7 @@ struct alignas(16) DevStage {
     int32_t n_t;                  // number of thread-row bits = m - r
     int32_t rl[kMaxRegBits];      // tile-local bit position of register bit j
     int32_t tl[kMaxTileBits];     // tile-local bit positions of the thread-row bits, ascending
-    int32_t pad;
+    int32_t pad[3];
     int32_t pre_begin, pre_end;   // permutation steps applied at this stage's LOAD (stage 0 only: global load)
     int32_t post_begin, post_end; // permutation steps applied at this stage's STORE
     int32_t rg[kMaxRegBits];      // GLOBAL row-bit position of register bit j   (= sp[rl[j]], precomputed)

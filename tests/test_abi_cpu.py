@@ -74,7 +74,12 @@ def test_schedule_preserves_the_unitary(n, g, seed, fuse):
                 Q.PlanOptions(fuse=fuse, snap_tol=-1.0, reg_qubits=2), Q.PlanOptions(fuse=fuse, reg_qubits=1, tile_qubits=2),
                 Q.PlanOptions(fuse=fuse, no_perm_folding=1), Q.PlanOptions(fuse=fuse, no_perm_folding=2, reg_qubits=3),
                 Q.PlanOptions(fuse=fuse, reg_qubits=4, tile_qubits=8, max_ops_per_sweep=200),
-                Q.PlanOptions(fuse=fuse, no_perm_folding=2, tile_qubits=7)):
+                Q.PlanOptions(fuse=fuse, no_perm_folding=2, tile_qubits=7),
+                # every search / fusion knob, and the R = 5 instantiation (a planner that stops making
+                # progress shows up here, on CPU, as a timeout instead of a hung GPU test)
+                Q.PlanOptions(fuse=fuse, reg_qubits=5, tile_qubits=9, stage_search=1),
+                Q.PlanOptions(fuse=fuse, stage_search=1, search=3, tile_qubits=5, reg_qubits=3),
+                Q.PlanOptions(fuse=fuse, stage_search=-1, search=-1, min_tail_ops=-1, no_1q_fusion=1, no_diag_conjugation=1)):
         plan = Q.Plan(n, 2**n, O.gate_stream(qc), opt)
         d = plan.dump()
         st = plan.stats()

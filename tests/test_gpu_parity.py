@@ -72,11 +72,11 @@ def _all_single_gate_circuits(n):
     yield "ccswap", [3, 0, 1, 2], O.str_to_operation("ccswap")
 
 
-@pytest.mark.parametrize("reg_qubits", [1, 2, 3, 4])
+@pytest.mark.parametrize("reg_qubits", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("snap", [1e-15, -1.0])
 def test_every_gate_kind_every_position(reg_qubits, snap):
     """One gate on a NON-trivial input (a random unitary prefix) so that misplaced rows show up."""
-    n = 4
+    n = max(4, reg_qubits)
     prefix = _rand_circuit(n, 30, 77, extra=True)
     base = O.to_matrix_rowform(prefix)
     opt = Q.PlanOptions(reg_qubits=reg_qubits, snap_tol=snap)
@@ -105,6 +105,7 @@ def test_random_circuits_match_oracle(n, g, seed, fuse):
                 Q.PlanOptions(fuse=fuse, reg_qubits=2, tile_qubits=4, log2_tile_cols=1, snap_tol=-1.0),
                 Q.PlanOptions(fuse=fuse, reg_qubits=4, tile_qubits=8, log2_tile_cols=4, max_ops_per_sweep=200),
                 Q.PlanOptions(fuse=fuse, reg_qubits=1, tile_qubits=3, log2_tile_cols=-1),
+                Q.PlanOptions(fuse=fuse, reg_qubits=5, tile_qubits=9, stage_search=1),
                 Q.PlanOptions(fuse=fuse, no_perm_folding=1), Q.PlanOptions(fuse=fuse, no_perm_folding=2, tile_qubits=7),
                 Q.PlanOptions(fuse=fuse, no_perm_folding=2, reg_qubits=3, max_ops_per_sweep=200)):
         got = run_device(qc, opt)
