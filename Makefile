@@ -32,8 +32,10 @@ $(OBJDIR)/host_%.o: $(HOST)/capi/%.cpp $(HOSTHDRS) include/qsx_host.h
 	$(CXX) $(HOSTFLAGS) -c $< -o $@
 
 # C ABI of the host layer (include/qsx_host.h) for non-C++ callers (tests, bench.py)
-$(LIBHOST): $(OBJDIR)/host_qcir_io.o $(OBJDIR)/host_qcir_to_tensor.o $(OBJDIR)/host_qsx_host.o $(LIBQSX)
-	$(CXX) -shared -o $@ $(OBJDIR)/host_qcir_io.o $(OBJDIR)/host_qcir_to_tensor.o $(OBJDIR)/host_qsx_host.o \
+HOSTOBJS  := $(OBJDIR)/host_qcir_io.o $(OBJDIR)/host_qcir_to_tensor.o $(OBJDIR)/host_zx_io.o $(OBJDIR)/host_zxgraph_to_tensor.o
+
+$(LIBHOST): $(HOSTOBJS) $(OBJDIR)/host_qsx_host.o $(LIBQSX)
+	$(CXX) -shared -o $@ $(HOSTOBJS) $(OBJDIR)/host_qsx_host.o \
 	    -L$(LIBDIR) -lqsx -Wl,-rpath,'$$ORIGIN'
 
 $(BCAST): $(CSRC)/tools/bcast_probe.cu
@@ -51,13 +53,17 @@ $(OBJDIR)/host_%.o: $(HOST)/qcir/%.cpp $(HOSTHDRS)
 $(OBJDIR)/host_%.o: $(HOST)/convert/%.cpp $(HOSTHDRS)
 	@mkdir -p $(OBJDIR)
 	$(CXX) $(HOSTFLAGS) -c $< -o $@
+$(OBJDIR)/host_%.o: $(HOST)/zx/%.cpp $(HOSTHDRS)
+	@mkdir -p $(OBJDIR)
+	$(CXX) $(HOSTFLAGS) -c $< -o $@
+
 $(OBJDIR)/host_%.o: $(HOST)/cli/%.cpp $(HOSTHDRS)
 	@mkdir -p $(OBJDIR)
 	$(CXX) $(HOSTFLAGS) -c $< -o $@
 
-$(SHIM): $(OBJDIR)/host_qcir_io.o $(OBJDIR)/host_qcir_to_tensor.o $(OBJDIR)/host_shim_main.o $(LIBQSX)
+$(SHIM): $(HOSTOBJS) $(OBJDIR)/host_shim_main.o $(LIBQSX)
 	@mkdir -p bin
-	$(CXX) -o $@ $(OBJDIR)/host_qcir_io.o $(OBJDIR)/host_qcir_to_tensor.o $(OBJDIR)/host_shim_main.o \
+	$(CXX) -o $@ $(HOSTOBJS) $(OBJDIR)/host_shim_main.o \
 	    -L$(LIBDIR) -lqsx -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.hpp) include/qsx.h $(wildcard qsyn_b200/host/util/*.hpp)

@@ -3,6 +3,8 @@
 // enough of qsyn's command surface to replay the reference's own dofiles for
 // this path verbatim and diff the output against its golden logs:
 //     qcir {new|read|delete|list|print|qubit add|gate add}, convert qcir tensor (alias qc2ts),
+//     zx {new|read|delete|checkout|list|vertex add|edge add|edge remove|tensor-product|adjoint},
+//     convert zx tensor (alias zx2ts)                                     [SURVEY.md 8 f2],
 //     tensor {list|print|equiv|adjoint|delete|checkout|write|read}, logger, quit -f.
 // Echo / spacing rules and message texts follow cli_exec.cpp:40-105, conversion_cmd.cpp:84-98,
 // tensor_cmd.cpp:100-177, data_structure_manager.hpp and the golden logs.  The CLI framework
@@ -19,6 +21,7 @@
 #include <vector>
 
 #include "../convert/qcir_to_tensor.hpp"
+#include "../convert/zxgraph_to_tensor.hpp"
 #include "../qcir/qcir.hpp"
 #include "../tensor/qtensor.hpp"
 #include "../util/logger.hpp"
@@ -29,6 +32,7 @@ namespace {
 
 using qsyn::qcir::QCir;
 using qsyn::tensor::QTensor;
+using qsyn::zx::ZXGraph;
 
 // minimal DataStructureManager with the reference's messages (data_structure_manager.hpp:35-198)
 template <typename T>
@@ -117,7 +121,14 @@ bool is_prefix(std::string const& p, std::string const& full) { return !p.empty(
 struct Shell {
     Manager<QCir> qcir_mgr{"QCir"};
     Manager<QTensor<double>> tensor_mgr{"Tensor"};
+    Manager<ZXGraph> zx_mgr{"ZXGraph"};
     bool quit = false;
+
+    bool need_zx() {
+        if (!zx_mgr.empty()) return true;
+        spdlog::error("ZXGraph list is empty. Please create a ZXGraph first!!");
+        return false;
+    }
 
     bool need_qcir() {
         if (!qcir_mgr.empty()) return true;
@@ -235,6 +246,142 @@ struct Shell {
         }
     }
 
+    // zx_cmd.cpp:219-262 (read), 364-470 (vertex add), 512-560 (edge add/remove), zxgraph_mgr
+    void cmd_zx(std::vector<std::string> a) {
+        if (a.empty()) return;
+        std::string const sub = a[0];
+        a.erase(a.begin());
+        using qsyn::zx::EdgeType;
+        using qsyn::zx::VertexType;
+        if (is_prefix(sub, "new")) {
+            zx_mgr.add(a.empty() ? zx_mgr.get_next_id() : std::stoul(a[0]));
+        } else if (is_prefix(sub, "read")) {
+            bool keep_id = false, replace = false;
+            std::string path;
+            for (auto const& t : a) {
+                if (t == "--keep-id")
+                    keep_id = true;
+                else if (t == "-r" || is_prefix(t, "--replace"))
+                    replace = true;
+                else
+                    path = t;
+            }
+            auto graph = qsyn::zx::from_zx(std::filesystem::path(path), keep_id);
+            if (!graph.has_value()) return;
+            auto up = std::make_unique<ZXGraph>(std::move(*graph));
+            if (zx_mgr.empty() || !replace) {
+                zx_mgr.add(zx_mgr.get_next_id(), std::move(up));
+            } else {
+                zx_mgr.set(std::move(up));
+            }
+            zx_mgr.get()->set_filename(std::filesystem::path(path).stem().string());
+        } else if (is_prefix(sub, "delete")) {
+            if (!a.empty() && (a[0] == "--all" || a[0] == "-a"))
+                zx_mgr.clear();
+            else if (!a.empty())
+                zx_mgr.remove(std::stoul(a[0]));
+        } else if (is_prefix(sub, "checkout")) {
+            if (!a.empty()) zx_mgr.checkout(std::stoul(a[0]));
+        } else if (is_prefix(sub, "list")) {
+            zx_mgr.print_list([](ZXGraph const& g) { return pad_right(g.get_filename().substr(0, 19), 19) + " " + join(g.get_procedures(), " ➔ "); });
+        } else if (is_prefix(sub, "vertex")) {
+            if (a.size() < 2 || !is_prefix(a[0], "add") || !need_zx()) return;
+            ZXGraph* g           = zx_mgr.get();
+            std::string const vt = a[1];
+            if (is_prefix(vt, "input") || is_prefix(vt, "output")) {
+                bool const in = is_prefix(vt, "input");
+                int const qid = a.size() > 2 ? std::stoi(a[2]) : (in ? g->max_input_qubit() : g->max_output_qubit()) + 1;
+                if (in ? g->is_input_qubit(qid) : g->is_output_qubit(qid)) {
+                    if (in)
+                        spdlog::error("Input vertex for qubit {} already exists!!", qid);
+                    else
+                        spdlog::error("Error: output vertex for qubit {} already exists!!", qid);
+                    return;
+                }
+                in ? g->add_input(qid) : g->add_output(qid);
+                spdlog::info("Adding {} vertex for qubit {}...", in ? "input" : "output", qid);
+                return;
+            }
+            VertexType type;
+            if (is_prefix(vt, "zspider"))
+                type = VertexType::z;
+            else if (is_prefix(vt, "xspider"))
+                type = VertexType::x;
+            else if (is_prefix(vt, "hbox"))
+                type = VertexType::h_box;
+            else {
+                std::fprintf(stderr, "Error: invalid vertex type \"%s\"!!\n", vt.c_str());
+                return;
+            }
+            dvlab::Phase phase = type == VertexType::h_box ? dvlab::Phase(1) : dvlab::Phase(0);
+            if (a.size() > 2) {
+                auto const ph = dvlab::Phase::from_string(a[2]);
+                if (!ph.has_value()) {
+                    std::fprintf(stderr, "Error: invalid phase \"%s\"!!\n", a[2].c_str());
+                    return;
+                }
+                phase = *ph;
+            }
+            auto* v = g->add_vertex(type, phase);
+            spdlog::info("Adding vertex {}...", v->get_id());
+        } else if (is_prefix(sub, "edge")) {
+            if (a.size() < 3 || !need_zx()) return;
+            ZXGraph* g = zx_mgr.get();
+            size_t const id0 = std::stoul(a[1]), id1 = std::stoul(a[2]);
+            for (size_t id : {id0, id1})
+                if (!g->is_v_id(id)) {
+                    spdlog::error("Cannot find vertex with ID {} in the ZXGraph!!", id);
+                    return;
+                }
+            auto parse_etype = [&](std::string t) -> std::optional<EdgeType> {
+                for (auto& ch : t) ch = static_cast<char>(std::tolower(static_cast<unsigned char>(ch)));
+                if (is_prefix(t, "simple")) return EdgeType::simple;
+                if (is_prefix(t, "hadamard")) return EdgeType::hadamard;
+                return std::nullopt;
+            };
+            if (is_prefix(a[0], "add")) {
+                auto const et = a.size() > 3 ? parse_etype(a[3]) : std::nullopt;
+                if (!et.has_value()) {
+                    std::fprintf(stderr, "Error: missing or invalid edge type!!\n");
+                    return;
+                }
+                try {
+                    g->add_edge(g->vertex(id0), g->vertex(id1), *et);
+                } catch (std::logic_error const& e) {
+                    spdlog::error("{}", e.what());
+                }
+            } else if (is_prefix(a[0], "remove")) {
+                auto const et = a.size() > 3 ? parse_etype(a[3]) : std::nullopt;
+                if (et.has_value())
+                    g->remove_edge(g->vertex(id0), g->vertex(id1), *et);
+                else
+                    g->remove_edge(g->vertex(id0), g->vertex(id1));
+            }
+        } else if (sub == "tensor-product") {
+            if (a.empty() || !need_zx()) return;
+            auto* other = zx_mgr.find_by_id(std::stoul(a[0]));
+            if (other != nullptr) zx_mgr.get()->tensor_product(*other);
+        } else if (is_prefix(sub, "adjoint")) {
+            if (!need_zx()) return;
+            zx_mgr.get()->adjoint();
+        } else {
+            std::fprintf(stderr, "Error: zx subcommand \"%s\" is outside the tensor-verification path of this build!!\n", sub.c_str());
+        }
+    }
+
+    // conversion_cmd.cpp:221-240
+    void cmd_zx2ts() {
+        if (!need_zx()) return;
+        spdlog::info("Converting ZXGraph {} to Tensor {}...", zx_mgr.focused_id(), tensor_mgr.get_next_id());
+        auto tensor = qsyn::to_tensor(*zx_mgr.get());
+        if (tensor.has_value()) {
+            tensor_mgr.add(tensor_mgr.get_next_id(), std::make_unique<QTensor<double>>(std::move(tensor.value())));
+            tensor_mgr.get()->set_filename(zx_mgr.get()->get_filename());
+            tensor_mgr.get()->add_procedures(zx_mgr.get()->get_procedures());
+            tensor_mgr.get()->add_procedure("ZX2TS");
+        }
+    }
+
     // conversion_cmd.cpp:84-98
     void cmd_qc2ts() {
         if (!need_qcir()) return;
@@ -347,11 +494,17 @@ struct Shell {
         tok.erase(tok.begin());
         if (cmd == "qc2ts") {
             cmd_qc2ts();
+        } else if (cmd == "zx2ts") {
+            cmd_zx2ts();
         } else if (is_prefix(cmd, "convert") && cmd.size() >= 3) {
             if (tok.size() >= 2 && is_prefix(tok[0], "qcir") && is_prefix(tok[1], "tensor"))
                 cmd_qc2ts();
+            else if (tok.size() >= 2 && tok[0] == "zx" && is_prefix(tok[1], "tensor"))
+                cmd_zx2ts();
             else
-                std::fprintf(stderr, "Error: this build only converts qcir -> tensor!!\n");
+                std::fprintf(stderr, "Error: this build only converts qcir / zx -> tensor!!\n");
+        } else if (cmd == "zx") {
+            cmd_zx(tok);
         } else if (cmd == "qcir") {
             cmd_qcir(tok);
         } else if (is_prefix(cmd, "tensor") && cmd.size() >= 3) {

@@ -248,36 +248,53 @@ QTensor<T> QTensor<T>::to_matrix() {
 //------------------------------
 
 // The 8 sums {Re,Im sum conj(t1) t2, sum|t1|^2, sum|t2|^2, Re,Im sum t1, Re,Im sum t2}.
-// Both device-resident: one fused GPU pass.  A host operand facing a device operand is
-// uploaded first (e.g. QTensor::identity(n) in qcir_equiv.cpp:65).  Returns false on a shape
-// mismatch.
+// One fused GPU pass over two device-resident unitaries; a host operand that is an n-qubit
+// operator is uploaded first (QTensor::identity(n) in qcir_equiv.cpp:65, zx2ts results, tensors
+// read from files).  Returns false on a shape mismatch.
 template <typename U>
 bool equivalence_sums(QTensor<U> const& t1, QTensor<U> const& t2, double (&sums)[8]) {
     if (t1.shape() != t2.shape()) return false;
     if constexpr (std::is_same_v<U, double>) {
         DeviceUnitary const* d1 = t1.device_unitary();
         DeviceUnitary const* d2 = t2.device_unitary();
-        if (d1 != nullptr || d2 != nullptr) {
-            DeviceUnitary tmp;
-            auto lift = [&](QTensor<U> const& h, DeviceUnitary const& like) {
+        // a 2^n x 2^n operand (matrix, or the rank-2n tensor of an n-qubit operator) belongs on the
+        // device even when both sides were built on the host (zx2ts, tensor read)
+        auto qubits_of = [](QTensor<U> const& t) -> int {
+            auto const sh = t.shape();
+            size_t rows = 0;
+            if (sh.size() == 2 && sh[0] == sh[1]) {
+                rows = sh[0];
+            } else if (sh.size() >= 2 && sh.size() % 2 == 0 && std::all_of(sh.begin(), sh.end(), [](size_t e) { return e == 2; })) {
+                rows = size_t{1} << (sh.size() / 2);
+            }
+            int n = 0;
+            while ((size_t{1} << n) < rows) ++n;
+            return rows >= 2 && (size_t{1} << n) == rows ? n : 0;
+        };
+        int const nq = (d1 != nullptr) ? d1->n_qubits() : (d2 != nullptr) ? d2->n_qubits() : qubits_of(t1);
+        if (nq > 0) {
+            DeviceUnitary tmp1, tmp2;
+            auto lift = [&](QTensor<U> const& h) {
                 // host tensor -> device, in the physical [out | in] matrix layout
                 QTensor<U> m = h;
                 if (m.dimension() != 2) m = m.to_matrix();
                 auto const v = m.host_elements();
-                return DeviceUnitary::from_host(like.n_qubits(), v.data());
+                return DeviceUnitary::from_host(nq, v.data());
             };
             if (d1 == nullptr) {
-                tmp = lift(t1, *d2);
-                d1  = &tmp;
-            } else if (d2 == nullptr) {
-                tmp = lift(t2, *d1);
-                d2  = &tmp;
+                tmp1 = lift(t1);
+                d1   = &tmp1;
+            }
+            if (d2 == nullptr) {
+                tmp2 = lift(t2);
+                d2   = &tmp2;
             }
             auto const s = d1->equiv_sums(*d2);
             for (int i = 0; i < 8; ++i) sums[i] = s[i];
             return true;
         }
     }
+    // neither operand is an n-qubit operator (e.g. a 4 x 2 isometry): a handful of elements
     auto const a = t1.host_elements(), b = t2.host_elements();
     std::complex<double> ab(0, 0), sa(0, 0), sb(0, 0);
     double aa = 0, bb = 0;

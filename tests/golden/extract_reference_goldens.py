@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Builds tests/golden/reference_goldens.json from the reference's OWN test
-fixtures for the tensor-verification path (the ZX-free cases).
+fixtures for the tensor-verification path and its ZX operand (8 f2).
 
 Run in the build container only (needs /root/reference, which does not exist
 on the GPU box):  python tests/golden/extract_reference_goldens.py
@@ -25,6 +25,12 @@ CASES = {
     "error": ("tests/tensor/not_equiv/dof/error.dof", "tests/tensor/not_equiv/ref/error.log"),
     "size": ("tests/tensor/not_equiv/dof/size.dof", "tests/tensor/not_equiv/ref/size.log"),
     "empty_mgr": ("tests/conversion/dof/empty_mgr.dof", "tests/conversion/ref/empty_mgr.log"),
+    # the ZX operand
+    "zx2ts_h_edge": ("tests/conversion/zx2ts/dof/h_edge.dof", "tests/conversion/zx2ts/ref/h_edge.log"),
+    "zx2ts_disconnected": ("tests/conversion/zx2ts/dof/disconnected.dof", "tests/conversion/zx2ts/ref/disconnected.log"),
+    "zx2ts_invalid_graph": ("tests/conversion/zx2ts/dof/invalid_graph.dof", "tests/conversion/zx2ts/ref/invalid_graph.log"),
+    "tiny_circuits": ("tests/tensor/equiv/dof/tiny_circuits.dof", "tests/tensor/equiv/ref/tiny_circuits.log"),
+    "tensor_adjoint": ("tests/tensor/manip/dof/adjoint.dof", "tests/tensor/manip/ref/adjoint.log"),
 }
 
 # in-repo circuit families that are equivalent by construction (SURVEY 8c last bullet)
@@ -33,6 +39,9 @@ EXTRA_INPUTS = [f"benchmark/qft/qft_{n}{v}.qasm" for n in (2, 3, 4, 5, 8) for v 
     "benchmark/qasm/qc2ts/swap.qasm",
     "benchmark/qasm/qc2ts/toffoli.qasm",
     "benchmark/qasm/qc2ts/test.qasm",
+    # examples/tensor-equiv.dof (BASELINE.json configs[0]) reads these two
+    "benchmark/zx/tof3_op.zx",
+    "benchmark/zx/tof3_zh.zx",
 ]
 
 
@@ -42,7 +51,7 @@ def main():
         dof_text = open(os.path.join(REF, dof)).read()
         log_text = open(os.path.join(REF, log)).read()
         out["cases"][name] = {"dof_path": dof, "dof": dof_text, "log": log_text}
-        for m in re.finditer(r"qcir read (\S+)", dof_text):
+        for m in re.finditer(r"(?:qcir|zx) read (\S+)", dof_text):
             p = m.group(1)
             out["inputs"][p] = open(os.path.join(REF, p)).read()
     for p in EXTRA_INPUTS:
