@@ -188,6 +188,10 @@ int qsx_equiv_finish(const double sums[8], double eps, int strict, qsx_equiv_res
 /* ---- whole-tensor ops on one shard ----------------------------------------------- */
 /* conjugate transpose in place; only valid for a full (unsharded) unitary: replaces Tensor::adjoint_inplace (tensor.hpp:303-306) */
 int qsx_unitary_adjoint_inplace(qsx_unitary* u);
+/* conjugate transpose of a column-sharded unitary, in place: shards[k] must hold columns [k c, (k+1) c) and may live
+ * on different devices of this process (peer access required).  Diagonal blocks transpose locally; each off-diagonal
+ * block pair is exchanged by one kernel that reads and writes the partner block in peer memory. */
+int qsx_unitary_adjoint_sharded(qsx_unitary* const* shards, int n_shards);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@ from .abi import (  # noqa: F401
     Plan,
     PlanOptions,
     Unitary,
+    adjoint_sharded,
     device_count,
     equiv_finish,
     lib,

@@ -117,6 +117,7 @@ def _declare(L: C.CDLL) -> None:
         "qsx_equiv_partial": [vp, vp, dp],
         "qsx_equiv_finish": [dp, C.c_double, i32, C.POINTER(EquivResult)],
         "qsx_unitary_adjoint_inplace": [vp],
+        "qsx_unitary_adjoint_sharded": [C.POINTER(vp), C.c_int],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -274,6 +275,12 @@ class Unitary:
             self.close()
         except Exception:
             pass
+
+
+def adjoint_sharded(shards: Sequence["Unitary"]) -> None:
+    """qsx_unitary_adjoint_sharded: shards[k] holds columns [k c, (k+1) c), possibly on different devices."""
+    arr = (C.c_void_p * len(shards))(*[u._h for u in shards])
+    _check(lib().qsx_unitary_adjoint_sharded(arr, len(shards)))
 
 
 def equiv_finish(sums: Sequence[float], eps: float = 1e-6, strict: bool = False) -> EquivResult:

@@ -892,6 +892,31 @@ __global__ void __launch_bounds__(kTr * 8) adjoint_inplace_kernel(double2* __res
     }
 }
 
+// Off-diagonal block pair of a column-sharded matrix: A is a c x c row-major block of one shard,
+// B the mirrored block of another shard (possibly in a PEER device's memory, read and written
+// over NVLink): A <- conj(B^T), B <- conj(A^T), in place, every element moved exactly once.
+__global__ void __launch_bounds__(kTr * 8) adjoint_block_pair_kernel(double2* __restrict__ a, double2* __restrict__ b, uint64_t c) {
+    __shared__ double2 ta[kTr][kTr + 1];
+    __shared__ double2 tb[kTr][kTr + 1];
+    uint64_t const r0 = (uint64_t)blockIdx.y * kTr, c0 = (uint64_t)blockIdx.x * kTr;  // tile (r0, c0) of A, (c0, r0) of B
+    int const tx = threadIdx.x & (kTr - 1), ty = threadIdx.x / kTr;
+    for (int r = ty; r < kTr; r += 8) {
+        if (r0 + r < c && c0 + tx < c) ta[r][tx] = a[(r0 + r) * c + c0 + tx];
+        if (c0 + r < c && r0 + tx < c) tb[r][tx] = b[(c0 + r) * c + r0 + tx];
+    }
+    __syncthreads();
+    for (int r = ty; r < kTr; r += 8) {
+        if (r0 + r < c && c0 + tx < c) {
+            double2 const v            = tb[tx][r];
+            a[(r0 + r) * c + c0 + tx] = make_double2(v.x, -v.y);
+        }
+        if (c0 + r < c && r0 + tx < c) {
+            double2 const v            = ta[tx][r];
+            b[(c0 + r) * c + r0 + tx] = make_double2(v.x, -v.y);
+        }
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_set_identity(double2* u, int n, uint64_t col0, uint64_t ncols, cudaStream_t s) {
@@ -950,11 +975,17 @@ cudaError_t launch_equiv(const double2* a, const double2* b, uint64_t n_elems, d
     return cudaGetLastError();
 }
 
-cudaError_t launch_adjoint_inplace(double2* u, int n, cudaStream_t s) {
-    uint64_t const dim = 1ull << n;
-    unsigned const nb  = (unsigned)((dim + kTr - 1) / kTr);
+cudaError_t launch_adjoint_inplace(double2* u, uint64_t dim, cudaStream_t s) {
+    unsigned const nb = (unsigned)((dim + kTr - 1) / kTr);
     dim3 grid(nb, nb);
     adjoint_inplace_kernel<<<grid, kTr * 8, 0, s>>>(u, dim);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_adjoint_block_pair(double2* a, double2* b, uint64_t c, cudaStream_t s) {
+    unsigned const nb = (unsigned)((c + kTr - 1) / kTr);
+    dim3 grid(nb, nb);
+    adjoint_block_pair_kernel<<<grid, kTr * 8, 0, s>>>(a, b, c);
     return cudaGetLastError();
 }
 

@@ -22,6 +22,9 @@ cudaError_t launch_equiv(const double2* a, const double2* b, uint64_t n_elems, d
                          cudaStream_t s);
 
 // in-place conjugate transpose of a full 2^n x 2^n matrix (K5)
-cudaError_t launch_adjoint_inplace(double2* u, int n, cudaStream_t s);
+// in-place conjugate transpose of a dim x dim row-major matrix
+cudaError_t launch_adjoint_inplace(double2* u, uint64_t dim, cudaStream_t s);
+// a <- conj(b^T), b <- conj(a^T) for two c x c row-major blocks (b may live on a peer device)
+cudaError_t launch_adjoint_block_pair(double2* a, double2* b, uint64_t c, cudaStream_t s);
 
 }  // namespace qsx

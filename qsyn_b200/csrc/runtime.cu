@@ -459,11 +459,60 @@ int qsx_equiv_finish(const double sums[8], double eps, int strict, qsx_equiv_res
 int qsx_unitary_adjoint_inplace(qsx_unitary* u) {
     if (u == nullptr) return fail(QSX_ERR_BAD_ARG, "null unitary");
     if (u->col0 != 0 || u->ncols != (1ull << u->n))
-        return fail(QSX_ERR_UNSUPPORTED, "adjoint of a column-sharded unitary needs an all-to-all (not built yet)");
-    DeviceCtx* c = nullptr;
-    if (int rc = get_ctx(u->device, &c)) return rc;
-    QSX_CUDA(qsx::launch_adjoint_inplace(u->data, u->n, c->stream));
-    QSX_CUDA(cudaStreamSynchronize(c->stream));
+        return fail(QSX_ERR_UNSUPPORTED, "one column shard cannot be transposed alone: use qsx_unitary_adjoint_sharded");
+    qsx_unitary* one[1] = {u};
+    return qsx_unitary_adjoint_sharded(one, 1);
+}
+
+// Shard k holds columns [k c, (k+1) c) of the 2^n x 2^n matrix, so its rows [j c, (j+1) c) are
+// the contiguous c x c block (j, k).  The adjoint swaps block (j, k) with block (k, j): the
+// diagonal blocks transpose locally, every off-diagonal pair is exchanged by ONE kernel that reads
+// and writes the partner block directly in the peer GPU's memory (NVLink P2P) -- the transfer and
+// the transpose are the same pass, nothing is staged, no second copy of the tensor exists.
+int qsx_unitary_adjoint_sharded(qsx_unitary* const* shards, int n_shards) {
+    if (shards == nullptr || n_shards < 1) return fail(QSX_ERR_BAD_ARG, "no shards");
+    for (int k = 0; k < n_shards; ++k)
+        if (shards[k] == nullptr) return fail(QSX_ERR_BAD_ARG, "null shard");
+    int const n        = shards[0]->n;
+    uint64_t const dim = 1ull << n, c = shards[0]->ncols;
+    if (c * (uint64_t)n_shards != dim) return fail(QSX_ERR_SHAPE, "the shards do not cover all columns");
+    for (int k = 0; k < n_shards; ++k)
+        if (shards[k]->n != n || shards[k]->ncols != c || shards[k]->col0 != (uint64_t)k * c)
+            return fail(QSX_ERR_SHAPE, "shard k must hold columns [k c, (k+1) c)");
+    std::vector<DeviceCtx*> ctx((size_t)n_shards, nullptr);
+    for (int k = 0; k < n_shards; ++k)
+        if (int rc = get_ctx(shards[k]->device, &ctx[(size_t)k])) return rc;
+    // everything queued on any shard must be done before a peer touches it
+    for (int k = 0; k < n_shards; ++k) {
+        QSX_CUDA(cudaSetDevice(shards[k]->device));
+        QSX_CUDA(cudaStreamSynchronize(ctx[(size_t)k]->stream));
+    }
+    for (int i = 0; i < n_shards; ++i) {
+        int const di = shards[i]->device;
+        QSX_CUDA(cudaSetDevice(di));
+        for (int j = i; j < n_shards; ++j) {
+            double2* const a = shards[i]->data + (uint64_t)j * c * c;  // block (j, i)
+            if (j == i) {
+                QSX_CUDA(qsx::launch_adjoint_inplace(a, c, ctx[(size_t)i]->stream));
+                continue;
+            }
+            int const dj = shards[j]->device;
+            if (dj != di) {
+                int can = 0;
+                QSX_CUDA(cudaDeviceCanAccessPeer(&can, di, dj));
+                if (!can) return fail(QSX_ERR_UNSUPPORTED, "devices " + std::to_string(di) + " and " + std::to_string(dj) + " have no peer access");
+                cudaError_t const e = cudaDeviceEnablePeerAccess(dj, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(QSX_ERR_CUDA, cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            double2* const b = shards[j]->data + (uint64_t)i * c * c;  // block (i, j), possibly peer memory
+            QSX_CUDA(qsx::launch_adjoint_block_pair(a, b, c, ctx[(size_t)i]->stream));
+        }
+    }
+    for (int k = 0; k < n_shards; ++k) {
+        QSX_CUDA(cudaSetDevice(shards[k]->device));
+        QSX_CUDA(cudaStreamSynchronize(ctx[(size_t)k]->stream));
+    }
     return QSX_OK;
 }
 

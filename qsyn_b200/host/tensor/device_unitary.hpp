@@ -139,8 +139,7 @@ public:
     }
 
     void adjoint_inplace() {
-        if (_shards.size() != 1) throw std::runtime_error("adjoint of a sharded unitary is not supported yet");
-        check(qsx_unitary_adjoint_inplace(_shards[0]));
+        check(qsx_unitary_adjoint_sharded(_shards.data(), static_cast<int>(_shards.size())));
     }
 
     // whole matrix, row-major (print / write / element access; small n only)

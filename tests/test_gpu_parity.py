@@ -226,6 +226,34 @@ def test_adjoint_inplace():
     assert ei.value.status == "QSX_ERR_UNSUPPORTED"
 
 
+@pytest.mark.parametrize("n,shards", [(2, 2), (5, 4), (7, 2), (8, 8), (9, 4), (6, 64)])
+def test_adjoint_of_a_column_sharded_unitary(n, shards):
+    """block (j, k) <-> block (k, j), in place.  Shards are spread round-robin over the
+    visible devices (all on device 0 on a one-GPU box; over NVLink peers with --gpus 2+)."""
+    rng = np.random.default_rng(n * 100 + shards)
+    dim = 2**n
+    m = rng.standard_normal((dim, dim)) + 1j * rng.standard_normal((dim, dim))
+    c = dim // shards
+    ndev = Q.device_count()
+    us = []
+    for k in range(shards):
+        u = Q.Unitary(n, k % ndev, k * c, c, identity=False)
+        u.upload(np.ascontiguousarray(m[:, k * c:(k + 1) * c]))
+        us.append(u)
+    Q.adjoint_sharded(us)
+    want = m.conj().T
+    for k, u in enumerate(us):
+        assert np.array_equal(u.download(), want[:, k * c:(k + 1) * c]), k
+    Q.adjoint_sharded(us)  # an involution
+    for k, u in enumerate(us):
+        assert np.array_equal(u.download(), m[:, k * c:(k + 1) * c]), k
+        u.close()
+    with pytest.raises(Q.QsxError) as ei:  # shards must be in column order and complete
+        a, b = Q.Unitary(3, 0, 4, 4), Q.Unitary(3, 0, 0, 4)
+        Q.adjoint_sharded([a, b])
+    assert ei.value.status == "QSX_ERR_SHAPE"
+
+
 def test_interrupt_and_oom():
     qc = _rand_circuit(6, 200, 50)
     u = Q.Unitary(6)
