@@ -895,10 +895,12 @@ __global__ void __launch_bounds__(kTr * 8) adjoint_inplace_kernel(double2* __res
 // Off-diagonal block pair of a column-sharded matrix: A is a c x c row-major block of one shard,
 // B the mirrored block of another shard (possibly in a PEER device's memory, read and written
 // over NVLink): A <- conj(B^T), B <- conj(A^T), in place, every element moved exactly once.
-__global__ void __launch_bounds__(kTr * 8) adjoint_block_pair_kernel(double2* __restrict__ a, double2* __restrict__ b, uint64_t c) {
+__global__ void __launch_bounds__(kTr * 8)
+    adjoint_block_pair_kernel(double2* __restrict__ a, double2* __restrict__ b, uint64_t c, uint32_t bx0, uint32_t by0) {
     __shared__ double2 ta[kTr][kTr + 1];
     __shared__ double2 tb[kTr][kTr + 1];
-    uint64_t const r0 = (uint64_t)blockIdx.y * kTr, c0 = (uint64_t)blockIdx.x * kTr;  // tile (r0, c0) of A, (c0, r0) of B
+    // tile (r0, c0) of A, (c0, r0) of B; (bx0, by0) lets two devices split one block pair
+    uint64_t const r0 = (uint64_t)(blockIdx.y + by0) * kTr, c0 = (uint64_t)(blockIdx.x + bx0) * kTr;
     int const tx = threadIdx.x & (kTr - 1), ty = threadIdx.x / kTr;
     for (int r = ty; r < kTr; r += 8) {
         if (r0 + r < c && c0 + tx < c) ta[r][tx] = a[(r0 + r) * c + c0 + tx];
@@ -982,10 +984,18 @@ cudaError_t launch_adjoint_inplace(double2* u, uint64_t dim, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_adjoint_block_pair(double2* a, double2* b, uint64_t c, cudaStream_t s) {
-    unsigned const nb = (unsigned)((c + kTr - 1) / kTr);
-    dim3 grid(nb, nb);
-    adjoint_block_pair_kernel<<<grid, kTr * 8, 0, s>>>(a, b, c);
+cudaError_t launch_adjoint_block_pair(double2* a, double2* b, uint64_t c, int part, cudaStream_t s) {
+    unsigned const nb = (unsigned)((c + kTr - 1) / kTr), half = nb / 2;
+    // part 0: everything; part 1: tile rows [0, nb/2) of a; part 2 (called with the blocks swapped by
+    // the other device): the tile COLUMNS [nb/2, nb) of its a = the rest of the pair
+    if (part == 0 || half == 0) {
+        if (part == 2) return cudaSuccess;
+        adjoint_block_pair_kernel<<<dim3(nb, nb), kTr * 8, 0, s>>>(a, b, c, 0u, 0u);
+    } else if (part == 1) {
+        adjoint_block_pair_kernel<<<dim3(nb, half), kTr * 8, 0, s>>>(a, b, c, 0u, 0u);
+    } else {
+        adjoint_block_pair_kernel<<<dim3(nb - half, nb), kTr * 8, 0, s>>>(a, b, c, half, 0u);
+    }
     return cudaGetLastError();
 }
 

@@ -24,7 +24,9 @@ cudaError_t launch_equiv(const double2* a, const double2* b, uint64_t n_elems, d
 // in-place conjugate transpose of a full 2^n x 2^n matrix (K5)
 // in-place conjugate transpose of a dim x dim row-major matrix
 cudaError_t launch_adjoint_inplace(double2* u, uint64_t dim, cudaStream_t s);
-// a <- conj(b^T), b <- conj(a^T) for two c x c row-major blocks (b may live on a peer device)
-cudaError_t launch_adjoint_block_pair(double2* a, double2* b, uint64_t c, cudaStream_t s);
+// a <- conj(b^T), b <- conj(a^T) for two c x c row-major blocks (b may live on a peer device).
+// part 0: the whole pair; parts 1 and 2 split it between the two owning devices: part 1 is
+// launched by a's device, part 2 by b's device with the arguments swapped.
+cudaError_t launch_adjoint_block_pair(double2* a, double2* b, uint64_t c, int part, cudaStream_t s);
 
 }  // namespace qsx

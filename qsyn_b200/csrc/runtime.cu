@@ -496,17 +496,27 @@ int qsx_unitary_adjoint_sharded(qsx_unitary* const* shards, int n_shards) {
                 QSX_CUDA(qsx::launch_adjoint_inplace(a, c, ctx[(size_t)i]->stream));
                 continue;
             }
-            int const dj = shards[j]->device;
-            if (dj != di) {
+            int const dj     = shards[j]->device;
+            double2* const b = shards[j]->data + (uint64_t)i * c * c;  // block (i, j), possibly peer memory
+            if (dj == di) {
+                QSX_CUDA(qsx::launch_adjoint_block_pair(a, b, c, 0, ctx[(size_t)i]->stream));
+                continue;
+            }
+            for (auto [from, to] : {std::pair<int, int>{di, dj}, std::pair<int, int>{dj, di}}) {
                 int can = 0;
-                QSX_CUDA(cudaDeviceCanAccessPeer(&can, di, dj));
-                if (!can) return fail(QSX_ERR_UNSUPPORTED, "devices " + std::to_string(di) + " and " + std::to_string(dj) + " have no peer access");
-                cudaError_t const e = cudaDeviceEnablePeerAccess(dj, 0);
+                QSX_CUDA(cudaDeviceCanAccessPeer(&can, from, to));
+                if (!can) return fail(QSX_ERR_UNSUPPORTED, "devices " + std::to_string(from) + " and " + std::to_string(to) + " have no peer access");
+                QSX_CUDA(cudaSetDevice(from));
+                cudaError_t const e = cudaDeviceEnablePeerAccess(to, 0);
                 if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(QSX_ERR_CUDA, cudaGetErrorString(e));
                 cudaGetLastError();
             }
-            double2* const b = shards[j]->data + (uint64_t)i * c * c;  // block (i, j), possibly peer memory
-            QSX_CUDA(qsx::launch_adjoint_block_pair(a, b, c, ctx[(size_t)i]->stream));
+            // both owners work on the pair: each takes half of the tiles, with ITS block as the local one
+            QSX_CUDA(cudaSetDevice(di));
+            QSX_CUDA(qsx::launch_adjoint_block_pair(a, b, c, 1, ctx[(size_t)i]->stream));
+            QSX_CUDA(cudaSetDevice(dj));
+            QSX_CUDA(qsx::launch_adjoint_block_pair(b, a, c, 2, ctx[(size_t)j]->stream));
+            QSX_CUDA(cudaSetDevice(di));
         }
     }
     for (int k = 0; k < n_shards; ++k) {
