@@ -284,6 +284,45 @@ struct Shell {
             if (!a.empty()) zx_mgr.checkout(std::stoul(a[0]));
         } else if (is_prefix(sub, "list")) {
             zx_mgr.print_list([](ZXGraph const& g) { return pad_right(g.get_filename().substr(0, 19), 19) + " " + join(g.get_procedures(), " ➔ "); });
+        } else if (is_prefix(sub, "print")) {
+            if (!need_zx()) return;
+            ZXGraph const* g = zx_mgr.get();
+            std::cout << std::flush;
+            if (a.empty()) {
+                g->print_graph();
+            } else if (a[0] == "-v" || (a[0].size() > 2 && is_prefix(a[0], "--vertices"))) {
+                std::vector<size_t> ids;
+                for (size_t i = 1; i < a.size(); ++i) ids.push_back(std::stoul(a[i]));
+                ids.empty() ? g->print_vertices() : g->print_vertices(ids);
+            } else if (a[0] == "-i" || (a[0].size() > 2 && is_prefix(a[0], "--inputs"))) {
+                g->print_boundary(true);
+            } else if (a[0] == "-o" || (a[0].size() > 2 && is_prefix(a[0], "--outputs"))) {
+                g->print_boundary(false);
+            } else if (a[0] == "-e" || (a[0].size() > 2 && is_prefix(a[0], "--edges"))) {
+                g->print_edges();
+            } else {
+                std::fprintf(stderr, "Error: `zx print %s` is outside the tensor-verification path of this build!!\n", a[0].c_str());
+            }
+            std::fflush(stdout);
+        } else if (is_prefix(sub, "vertex") && a.size() >= 2 && is_prefix(a[0], "remove")) {
+            if (!need_zx()) return;
+            ZXGraph* g = zx_mgr.get();
+            if (a[1] == "-i" || is_prefix(a[1], "--isolated")) {
+                spdlog::info("Removing isolated vertices...");
+                g->remove_isolated_vertices();
+                return;
+            }
+            for (size_t i = 1; i < a.size(); ++i) {
+                size_t const id = std::stoul(a[i]);
+                if (!g->is_v_id(id)) {
+                    spdlog::error("Cannot find vertex with ID {} in the ZXGraph!!", id);
+                    return;
+                }
+            }
+            for (size_t i = 1; i < a.size(); ++i) {
+                spdlog::info("Removing vertex {}...", a[i]);
+                g->remove_vertex(std::stoul(a[i]));
+            }
         } else if (is_prefix(sub, "vertex")) {
             if (a.size() < 2 || !is_prefix(a[0], "add") || !need_zx()) return;
             ZXGraph* g           = zx_mgr.get();

@@ -10,6 +10,9 @@
 
 #include <algorithm>
 #include <cstddef>
+#include <cstdio>
+#include <format>
+#include <limits>
 #include <filesystem>
 #include <fstream>
 #include <functional>
@@ -291,6 +294,92 @@ public:
         return count / 2;
     }
     size_t remove_edge(ZXVertex* vs, ZXVertex* vt) { return remove_edge(vs, vt, EdgeType::simple) + remove_edge(vs, vt, EdgeType::hadamard); }
+
+    // zxgraph.cpp:535-600
+    size_t remove_vertex(ZXVertex* v) {
+        if (!_vertices.contains(v)) return 0;
+        for (auto const& nb : v->_neighbors.keys()) {
+            v->_neighbors.erase(nb);
+            nb.first->_neighbors.erase({v, nb.second});
+        }
+        _vertices.erase(v);
+        _id_to_vertices.erase(v->get_id());
+        if (_inputs.contains(v)) {
+            _input_list.erase(v->get_qubit());
+            _inputs.erase(v);
+        }
+        if (_outputs.contains(v)) {
+            _output_list.erase(v->get_qubit());
+            _outputs.erase(v);
+        }
+        delete v;
+        return 1;
+    }
+    size_t remove_vertex(size_t id) {
+        if (!is_v_id(id)) {
+            spdlog::warn("Vertex with id {} does not exist", id);
+            return 0;
+        }
+        return remove_vertex(vertex(id));
+    }
+    size_t remove_isolated_vertices() {
+        size_t n = 0;
+        for (ZXVertex* v : _vertices.keys())
+            if (num_neighbors(v) == 0) n += remove_vertex(v);
+        return n;
+    }
+    size_t num_edges() const {
+        size_t n = 0;
+        _vertices.for_each([&](ZXVertex* v, char) { n += v->_neighbors.size(); });
+        return n / 2;
+    }
+
+    // zxgraph_print.cpp:27-143, zxvertex.cpp:62-78 (printed without a level prefix)
+    static std::string vertex_line(ZXVertex const* v) {
+        auto nbrs = v->_neighbors.keys();
+        std::sort(nbrs.begin(), nbrs.end(), [](NeighborPair const& a, NeighborPair const& b) {
+            return a.first->get_id() != b.first->get_id() ? a.first->get_id() < b.first->get_id() : a.second < b.second;
+        });
+        std::string list;
+        for (size_t i = 0; i < nbrs.size(); ++i) list += std::format("{}({}, {})", i ? " " : "", nbrs[i].first->get_id(), to_symbol(nbrs[i].second));
+        std::string const head = std::format("({}, {})", to_symbol(v->type()), v->phase().get_print_string());
+        // the reference pads to 12 display columns; std::format would count the bytes of the bullet
+        size_t cols = 0;
+        for (unsigned char ch : head) cols += (ch & 0xC0) != 0x80;
+        std::string const where = v->is_boundary() ? std::format("({}, {})", v->get_qubit(), v->get_col()) : std::format("({}, {})", v->get_row(), v->get_col());
+        return std::format("ID: {:>4} {}{} (Qubit, Col): {:<14} #Neighbors: {:>3}    {}", v->get_id(), head, std::string(cols < 12 ? 12 - cols : 0, ' '), where,
+                           nbrs.size(), list);
+    }
+    void print_vertices() const {
+        std::puts("");
+        _vertices.for_each([](ZXVertex* v, char) { std::puts(vertex_line(v).c_str()); });
+        std::puts(std::format("Total #Vertices: {}", num_vertices()).c_str());
+        std::puts("");
+    }
+    void print_vertices(std::vector<size_t> const& ids) const {
+        std::puts("");
+        for (size_t id : ids)
+            if (is_v_id(id)) std::puts(vertex_line(vertex(id)).c_str());
+        std::puts("");
+    }
+    void print_boundary(bool inputs) const {
+        std::string ids;
+        (inputs ? _inputs : _outputs).for_each([&](ZXVertex* v, char) { ids += (ids.empty() ? "" : ", ") + std::to_string(v->get_id()); });
+        std::puts(std::format("{} ({})", inputs ? "Input: " : "Output:", ids).c_str());
+        std::puts(std::format("Total #{}: {}", inputs ? "Inputs" : "Outputs", inputs ? num_inputs() : num_outputs()).c_str());
+    }
+    void print_edges() const {
+        _vertices.for_each([&](ZXVertex* v, char) {
+            v->_neighbors.for_each([&](NeighborPair const& nb, char) {
+                if (nb.first->get_id() > v->get_id())
+                    std::puts(std::format("{:<12} Type: {}", std::format("({}, {})", v->get_id(), nb.first->get_id()), to_symbol(nb.second)).c_str());
+            });
+        });
+        std::puts(std::format("Total #Edges: {}", num_edges()).c_str());
+    }
+    void print_graph() const {
+        std::puts(std::format("Graph ({} inputs, {} outputs, {} vertices, {} edges)", num_inputs(), num_outputs(), num_vertices(), num_edges()).c_str());
+    }
 
     // zxgraph.cpp:672-681
     void adjoint() {

@@ -31,6 +31,8 @@ CASES = {
     "zx2ts_invalid_graph": ("tests/conversion/zx2ts/dof/invalid_graph.dof", "tests/conversion/zx2ts/ref/invalid_graph.log"),
     "tiny_circuits": ("tests/tensor/equiv/dof/tiny_circuits.dof", "tests/tensor/equiv/ref/tiny_circuits.log"),
     "tensor_adjoint": ("tests/tensor/manip/dof/adjoint.dof", "tests/tensor/manip/ref/adjoint.log"),
+    "zx_add_remove": ("tests/zx/graph/dof/add_remove.dof", "tests/zx/graph/ref/add_remove.log"),
+    "zx_tensor_product": ("tests/zx/graph/dof/tensor_product.dof", "tests/zx/graph/ref/tensor_product.log"),
 }
 
 # in-repo circuit families that are equivalent by construction (SURVEY 8c last bullet)

@@ -137,10 +137,11 @@ def run_dof(tmp_path, goldens, dof_text):
     return r.returncode, r.stdout
 
 
-@pytest.mark.parametrize("case", ["zx2ts_disconnected", "zx2ts_invalid_graph"])
-def test_host_layer_replays_zx2ts_dofiles_without_a_device(tmp_path, goldens, case):
-    """ZX -> tensor is host work (a handful of axes): these two dofiles never reach `tensor equiv`,
-    so the C++ host layer must reproduce the golden logs byte for byte on any machine."""
+@pytest.mark.parametrize("case", ["zx2ts_disconnected", "zx2ts_invalid_graph", "zx_add_remove", "zx_tensor_product"])
+def test_host_layer_replays_zx_dofiles_without_a_device(tmp_path, goldens, case):
+    """ZX -> tensor is host work (a handful of axes): these dofiles never reach `tensor equiv`,
+    so the C++ host layer must reproduce the golden logs byte for byte on any machine
+    (zx_add_remove / zx_tensor_product: vertex and edge removal, id renumbering, `zx print -v/-i/-o`)."""
     c = goldens["cases"][case]
     rc, out = run_dof(tmp_path, goldens, c["dof"])
     assert rc == 0 and out == c["log"]
