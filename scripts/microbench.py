@@ -30,7 +30,8 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 12
     k = 32
     tile = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-    opt = lambda **kw: Q.PlanOptions(max_ops_per_sweep=1000, tile_qubits=tile, min_tail_ops=-1, **kw)
+    opt = lambda **kw: Q.PlanOptions(max_ops_per_sweep=1000, tile_qubits=tile, min_tail_ops=-1, no_1q_fusion=1, search=-1,
+                                     stage_search=-1, **kw)  # the cost model wants every gate as its own micro-op
     q = lambda b: n - 1 - b  # row bit -> qubit id
     cases = {}
     # register bits will be the first 4 distinct target bits: use row bits 0..3 as register bits
