@@ -284,6 +284,14 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": st_a.alg_bytes_per_run / max(st_a.n_sweeps, 1),
                          "launches": st_a.n_sweeps, "avg_launch_us": round(sweep_ms * 1e3 / max(st_a.n_sweeps, 1), 2)},
         }
+        if not args.dense:
+            # the fused sweeps are co-limited by the FP64 FMA pipe: the same launches against that roof
+            fp64_peak_tflops = 36.66  # measured DFMA peak of this pool's B200 (bin/fp64_peak, profiles/r1_fp64_peak.json)
+            instr = _fp64_instructions_per_run(plan_a, float(dim) * ncols)
+            ach = 2.0 * instr / (sweep_ms * 1e-3) / 1e12  # an FP64 pipe slot is worth 2 flop at the DFMA peak
+            out["roofline_fp64"] = {"bound": "fp64_pipe", "kernel": "sweep_kernel<%d>" % args.reg, "achieved": round(ach, 2),
+                                    "peak": fp64_peak_tflops, "unit": "TFLOP/s (FP64 pipe slots x 2)", "frac": round(ach / fp64_peak_tflops, 4),
+                                    "fp64_instructions_per_element_per_launch": round(instr / (float(dim) * ncols) / max(st_a.n_sweeps, 1), 2)}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args.workload, budget_s=args.cpu_budget)
     if world > 1:
@@ -291,6 +299,26 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out), flush=True)
+
+
+# FP64-pipe instructions per element of every micro-op kind (kernels.cu handlers): h = DMUL + 2 DFMA
+# per component pair; general 2x2 = 16 per pair; complex multiply = 4; exchange = 3 DADD per
+# element moved.  A thread-level control halves the share of threads that do the work.
+_FP64_PER_ELEMENT = {"H": 3.0, "U1": 8.0, "X": 3.0, "XC": 1.5, "SWAP": 1.5, "AD": 4.0, "U2": 32.0, "PHJ": 2.0, "DTABH": 2.0,
+                     "DTABF": 4.0, "SCALN": 4.0, "SAPPLY": 4.0, "DSCAL": 0.0}
+
+
+def _fp64_instructions_per_run(plan, elements_per_shard: float) -> float:
+    total = 0.0
+    for sw in plan.dump()["sweeps"]:
+        frac_sweep = 0.5 ** bin(sw.get("fixed_one", 0)).count("1")
+        for st in sw["stages"]:
+            for u in st["uops"]:
+                share = 0.5 ** bin(u["cother"] | u["czero"]).count("1")
+                if u["kind"] in ("X", "H", "U1", "AD", "SWAP") and u["creg"]:
+                    share *= 0.5 ** bin(u["creg"]).count("1")
+                total += _FP64_PER_ELEMENT.get(u["kind"], 0.0) * share * frac_sweep * elements_per_shard
+    return total
 
 
 def _plan_blob_bytes(plan):
