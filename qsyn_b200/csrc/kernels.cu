@@ -386,7 +386,7 @@ __device__ __forceinline__ void permute_rows(uint32_t (&rows)[R + 1], const DevP
 template <int R, bool LEAN>
 __global__ void __launch_bounds__(1 << max_threads_log2(R), min_ctas_per_sm(R))
     sweep_kernel(double2* __restrict__ u, const unsigned char* __restrict__ gprog, uint32_t prog_bytes, int log2_ncols,
-                 int log2_ncb) {
+                 int log2_ncb, uint32_t reverse) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // the sweep program (a few KB, read by every thread for every op) is staged in shared
     // memory once per CTA; the tile follows it
@@ -410,7 +410,8 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), min_ctas_per_sm(R))
     uint32_t const tid   = threadIdx.x;
     uint32_t const cw    = tid & ((1u << log2w) - 1u);
     uint32_t const trow  = tid >> log2w;
-    uint64_t const tid64 = blockIdx.x;
+    // odd sweeps walk the tiles backwards: what the previous sweep wrote last is still in L2
+    uint64_t const tid64 = reverse ? (uint64_t)(gridDim.x - 1u - blockIdx.x) : (uint64_t)blockIdx.x;
     uint64_t const cb    = tid64 & ((1ull << log2_ncb) - 1ull);
     uint32_t const rc    = (uint32_t)(tid64 >> log2_ncb);
 
@@ -557,7 +558,7 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), min_ctas_per_sm(R))
 
 template <int R, bool LEAN>
 cudaError_t launch_sweep_r(double2* u, int n, uint64_t ncols, const DevSweep& hs, const unsigned char* prog,
-                           size_t prog_bytes, cudaStream_t s) {
+                           size_t prog_bytes, bool reverse, cudaStream_t s) {
     (void)n;
     int const m        = hs.m;
     int const threads  = 1 << (m - R + hs.log2w);
@@ -578,7 +579,7 @@ cudaError_t launch_sweep_r(double2* u, int n, uint64_t ncols, const DevSweep& hs
         if (rc != cudaSuccess) return rc;
         attr_set[dev] = true;
     }
-    sweep_kernel<R, LEAN><<<(unsigned)nblocks, threads, smem, s>>>(u, prog, (uint32_t)prog_bytes, log2_ncols, log2_ncb);
+    sweep_kernel<R, LEAN><<<(unsigned)nblocks, threads, smem, s>>>(u, prog, (uint32_t)prog_bytes, log2_ncols, log2_ncb, reverse ? 1u : 0u);
     return cudaGetLastError();
 }
 
@@ -932,7 +933,7 @@ cudaError_t launch_set_identity(double2* u, int n, uint64_t col0, uint64_t ncols
 }
 
 cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, int R, const DevSweep& hs, const unsigned char* prog,
-                         size_t prog_bytes, cudaStream_t s) {
+                         size_t prog_bytes, bool reverse, cudaStream_t s) {
     if (hs.dense_k != 0) {
         switch (hs.dense_k) {
             case 3: return launch_dense_k<3>(u, ncols, hs, prog, s);
@@ -949,16 +950,16 @@ cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, int R, const DevSwee
         for (int i = 0; i < hs.n_ops && lean; ++i) lean = is_common_handler(ops[i].handler);
     }
     switch (R * 2 + (lean ? 1 : 0)) {
-        case 2: return launch_sweep_r<1, false>(u, n, ncols, hs, prog, prog_bytes, s);
-        case 3: return launch_sweep_r<1, true>(u, n, ncols, hs, prog, prog_bytes, s);
-        case 4: return launch_sweep_r<2, false>(u, n, ncols, hs, prog, prog_bytes, s);
-        case 5: return launch_sweep_r<2, true>(u, n, ncols, hs, prog, prog_bytes, s);
-        case 6: return launch_sweep_r<3, false>(u, n, ncols, hs, prog, prog_bytes, s);
-        case 7: return launch_sweep_r<3, true>(u, n, ncols, hs, prog, prog_bytes, s);
-        case 8: return launch_sweep_r<4, false>(u, n, ncols, hs, prog, prog_bytes, s);
-        case 9: return launch_sweep_r<4, true>(u, n, ncols, hs, prog, prog_bytes, s);
-        case 10: return launch_sweep_r<5, false>(u, n, ncols, hs, prog, prog_bytes, s);
-        case 11: return launch_sweep_r<5, true>(u, n, ncols, hs, prog, prog_bytes, s);
+        case 2: return launch_sweep_r<1, false>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
+        case 3: return launch_sweep_r<1, true>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
+        case 4: return launch_sweep_r<2, false>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
+        case 5: return launch_sweep_r<2, true>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
+        case 6: return launch_sweep_r<3, false>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
+        case 7: return launch_sweep_r<3, true>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
+        case 8: return launch_sweep_r<4, false>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
+        case 9: return launch_sweep_r<4, true>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
+        case 10: return launch_sweep_r<5, false>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
+        case 11: return launch_sweep_r<5, true>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -13,7 +13,7 @@ cudaError_t launch_set_identity(double2* u, int n, uint64_t col0, uint64_t ncols
 
 // one sweep (K1 a-e): `prog` is the device copy of a serialized DevSweep blob, `hs` its host copy
 cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, int R, const DevSweep& hs, const unsigned char* prog,
-                         size_t prog_bytes, cudaStream_t s);
+                         size_t prog_bytes, bool reverse, cudaStream_t s);
 
 // fused equivalence reduction (K4): 8 compensated sums of a shard pair.
 // `partials` must hold equiv_partials_doubles() doubles of device scratch; out8 is device memory.
