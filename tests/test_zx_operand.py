@@ -174,3 +174,25 @@ def test_baseline_config0_tensor_equiv_example(tmp_path, goldens):
     assert rc == 0
     assert "★ 1    tof3_op             #Dim: 2   ZX2TS\n" in out and "  0    tof3_zh             #Dim: 2   ZX2TS\n" in out
     assert "qsyn> tensor equiv 0 1\nEquivalent\n- Global Norm : 1\n- Global Phase: 0\n" in out
+
+
+def _parse_printed_matrix(text):
+    """xtensor's print of a complex matrix: {{a+bi, ...},\n {...}} with 6 decimals."""
+    import re
+    rows = []
+    for line in text.strip().splitlines():
+        vals = re.findall(r"(-?\d*\.\d*(?:e[-+]?\d+)?) *([-+]) *(\d*\.\d*(?:e[-+]?\d+)?)i", line)
+        rows.append([complex(float(a), float(b) * (-1 if s == "-" else 1)) for a, s, b in vals])
+    return np.array(rows)
+
+
+@pytest.mark.parametrize("name", ["swap", "cnot", "tof3", "tof3_zh", "tof3_op"])
+def test_host_layer_zx_tensor_values_match_oracle(tmp_path, goldens, name):
+    """`zx read; zx2ts; tensor print` through the C++ host layer vs the oracle's matrix (6 printed decimals)."""
+    rc, out = run_dof(tmp_path, goldens, f"zx read benchmark/zx/{name}.zx\nzx2ts\ntensor print\nquit -f\n")
+    assert rc == 0
+    body = out[out.index("qsyn> tensor print\n") + len("qsyn> tensor print\n"):out.index("\n\nqsyn> quit -f")]
+    got = _parse_printed_matrix(body)
+    want = Z.zx2ts(Z.zxgraph_from_zx_text(goldens["inputs"][f"benchmark/zx/{name}.zx"]))
+    assert got.shape == want.shape
+    assert np.allclose(got, want, rtol=0, atol=1.5e-6)
