@@ -14,7 +14,8 @@ LIBDIR    := qsyn_b200/lib
 OBJDIR    := build/obj
 
 LIBQSX    := $(LIBDIR)/libqsx.so
-OBJS      := $(OBJDIR)/kernels.o $(OBJDIR)/runtime.o $(OBJDIR)/planner.o
+OBJS      := $(OBJDIR)/kernels.o $(OBJDIR)/runtime.o $(OBJDIR)/planner.o $(OBJDIR)/planner_lower.o \
+             $(OBJDIR)/planner_schedule.o $(OBJDIR)/planner_emit.o
 
 HOST      := qsyn_b200/host
 SHIM      := bin/qsyn-b200
