@@ -323,14 +323,15 @@ __device__ __forceinline__ void run_handler(double2 (&e)[1 << R], double2& scal,
 #define QSX_CASE8(b) QSX_CASE(b) QSX_CASE(b + 1) QSX_CASE(b + 2) QSX_CASE(b + 3) QSX_CASE(b + 4) QSX_CASE(b + 5) QSX_CASE(b + 6) QSX_CASE(b + 7)
 #define QSX_CASE16(b) QSX_CASE8(b) QSX_CASE8(b + 8)
 
-// hdr = {handler, j0, j1, creg}, hdr2 = {cother, czero, pool, sel}: already loaded (prefetched) by the caller
+// hdr = {handler, cother, czero, pool}: the first 16 bytes of the op, loaded by the caller
 template <int R, bool LEAN>
-__device__ __forceinline__ void apply_op(double2 (&e)[1 << R], double2& scal, const DevOp* __restrict__ op, int4 hdr, int4 hdr2,
-                                         uint32_t grow, const double* __restrict__ pool) {
-    uint32_t const creg   = (uint32_t)hdr.w;
-    uint32_t const cother = (uint32_t)hdr2.x, czero = (uint32_t)hdr2.y;
+__device__ __forceinline__ void apply_op(double2 (&e)[1 << R], double2& scal, const DevOp* __restrict__ op, int4 hdr, uint32_t grow,
+                                         const double* __restrict__ pool) {
+    uint32_t const cother = (uint32_t)hdr.y, czero = (uint32_t)hdr.z;
     if ((grow & cother) != cother || (grow & czero) != 0u) return;
-    int const pool_off = hdr2.z, sel = hdr2.w;
+    int const pool_off  = hdr.w;
+    uint32_t const creg = op->creg;  // (these two are loaded only inside the handlers that read them)
+    int const sel       = op->sel;
     if constexpr (LEAN) {
         switch (hdr.x) {  // dense 0..H_COMMON-1
             QSX_CASE16(0)
@@ -400,10 +401,11 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), min_ctas_per_sm(R))
     double2* const tile             = reinterpret_cast<double2*>(smem_raw + prog_bytes);
 
     const DevSweep* const sw     = reinterpret_cast<const DevSweep*>(prog);
-    const DevStage* const stages = reinterpret_cast<const DevStage*>(prog + sizeof(DevSweep));
+    // the ops come first: op o sits at a compile-time constant plus o * 96, no base register needed
+    const DevOp* const ops       = reinterpret_cast<const DevOp*>(prog + sizeof(DevSweep));
+    const DevStage* const stages = reinterpret_cast<const DevStage*>(ops + sw->n_ops);
     int const n_stages           = sw->n_stages;
-    const DevOp* const ops       = reinterpret_cast<const DevOp*>(stages + n_stages);
-    const DevPerm* const perms   = reinterpret_cast<const DevPerm*>(ops + sw->n_ops);
+    const DevPerm* const perms   = reinterpret_cast<const DevPerm*>(stages + n_stages);
     const double* const pool     = reinterpret_cast<const double*>(perms + sw->n_perms);
 
     int const log2w      = sw->log2w;
@@ -502,9 +504,8 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), min_ctas_per_sm(R))
                 if ((grow & (uint32_t)hdr2.x) != (uint32_t)hdr2.x || (grow & (uint32_t)hdr2.y) != 0u) continue;
                 run_handler<R, H_H>(e, scal, ops + o, 0u, 0, 0, grow, pool);  // timing experiment: control test, no switch
 #else
-                int4 const hdr  = *reinterpret_cast<const int4*>(ops + o);
-                int4 const hdr2 = *(reinterpret_cast<const int4*>(ops + o) + 1);
-                apply_op<R, LEAN>(e, scal, ops + o, hdr, hdr2, grow, pool);
+                int4 const hdr = *reinterpret_cast<const int4*>(ops + o);
+                apply_op<R, LEAN>(e, scal, ops + o, hdr, grow, pool);
 #endif
             }
         }
@@ -946,7 +947,7 @@ cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, int R, const DevSwee
     bool lean = true;
     {
         const unsigned char* const host = reinterpret_cast<const unsigned char*>(&hs);
-        const DevOp* const ops = reinterpret_cast<const DevOp*>(host + sizeof(DevSweep) + (size_t)hs.n_stages * sizeof(DevStage));
+        const DevOp* const ops = reinterpret_cast<const DevOp*>(host + sizeof(DevSweep));
         for (int i = 0; i < hs.n_ops && lean; ++i) lean = is_common_handler(ops[i].handler);
     }
     switch (R * 2 + (lean ? 1 : 0)) {

@@ -196,10 +196,10 @@ void serialize(Plan& plan) {
         unsigned char* p = plan.blob.data() + off;
         std::memcpy(p, &hs, sizeof(hs));
         p += sizeof(hs);
-        if (!stages.empty()) std::memcpy(p, stages.data(), stages.size() * sizeof(DevStage));
-        p += stages.size() * sizeof(DevStage);
         if (!ops.empty()) std::memcpy(p, ops.data(), ops.size() * sizeof(DevOp));
         p += ops.size() * sizeof(DevOp);
+        if (!stages.empty()) std::memcpy(p, stages.data(), stages.size() * sizeof(DevStage));
+        p += stages.size() * sizeof(DevStage);
         if (!perms.empty()) std::memcpy(p, perms.data(), perms.size() * sizeof(DevPerm));
         p += perms.size() * sizeof(DevPerm);
         if (!pool.empty()) std::memcpy(p, pool.data(), pool.size() * sizeof(double));

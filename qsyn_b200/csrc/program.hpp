@@ -99,12 +99,14 @@ static_assert(H_COMMON == 52 && H_COUNT == 130, "the kernel's switch enumerates 
 // Thread-level predicate of every micro-op: (row & cother) == cother && (row & czero) == 0, where
 // `row` is the thread's global row index with the register bits cleared.
 struct alignas(16) DevOp {
+    // first 16 bytes: everything the dispatch of a micro-op needs, one LDS.128
     int32_t  handler;  // Handler id (kind + register bits folded in)
-    int32_t  j0, j1;   // register-bit indices (or -1); informative, the handler already encodes them
-    uint32_t creg;     // required-one mask over the register index (bits 0..r-1), non-diagonal kinds only
     uint32_t cother;   // required-one mask over GLOBAL row bits that are not register bits this stage
     uint32_t czero;    // required-zero mask over GLOBAL row bits that are not register bits this stage
     int32_t  pool;     // offset in doubles into the constant pool (K_U2 matrix, K_DTAB* table)
+    // second 16 bytes: read by the few handlers that need them
+    int32_t  j0, j1;   // register-bit indices (or -1); K_SCALN: j0 = number of entries
+    uint32_t creg;     // required-one mask over the register index (bits 0..r-1), generic non-diagonal kinds only
     int32_t  sel;      // K_DSCAL: global row bit selecting d1 (or -1)
     double   c[8];
 };
@@ -148,8 +150,8 @@ struct alignas(16) DevSweep {
     int32_t  outer[kMaxRowBits];  // global positions of the enumerated outer bits, ascending
     int32_t  dense_k;             // 0: interpreted sweep.  k >= 3: ONE dense 2^k x 2^k block (dense_kernel<k>)
     int32_t  pad2[2];
-    // interpreted sweep: followed by DevStage stages[n_stages]; DevOp ops[n_ops]; DevPerm perms[n_perms];
-    //                    double pool[pool_doubles]
+    // interpreted sweep: followed by DevOp ops[n_ops]; DevStage stages[n_stages]; DevPerm perms[n_perms];
+    //                    double pool[pool_doubles]   (ops first: their shared-memory address is o * 96 + a constant)
     // dense sweep:       followed by int32 block_local[8] (tile-local position of block bit i = bit i of the
     //                    component index); then the REAL form of the block matrix,
     //                    A[(2c'+p')][(2c+p)] with p = 0 re / 1 im, 2^(k+1) rows of dense_lda(k) doubles
