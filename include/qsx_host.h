@@ -38,6 +38,16 @@ int qsxh_circuit_destroy(qsxh_circuit* c);
 /* convert qcir tensor: nullopt cases of the reference return QSX_ERR_BAD_ARG (empty circuit),
  * QSX_ERR_UNSUPPORTED, QSX_ERR_INTERRUPTED, QSX_ERR_OOM with the reference's log line as the error text */
 int qsxh_qc2ts(const qsxh_circuit* c, qsxh_tensor** out);
+
+/* the ZX operand: qsyn::zx::ZXGraph from `.zx` text (src/zx/zx_io.cpp:83-436) and
+ * `convert zx tensor` (src/convert/zxgraph_to_tensor.cpp:95-135).  The tensor is built on the host;
+ * qsxh_tensor_equiv lifts it to the device when it is an n-qubit operator. */
+typedef struct qsxh_zxgraph qsxh_zxgraph;
+int qsxh_zxgraph_from_zx_text(const char* text, int keep_id, qsxh_zxgraph** out);
+int qsxh_zxgraph_from_zx_file(const char* path, int keep_id, qsxh_zxgraph** out);
+int qsxh_zxgraph_info(const qsxh_zxgraph* g, size_t* n_inputs, size_t* n_outputs, size_t* n_vertices, size_t* n_edges);
+int qsxh_zx2ts(const qsxh_zxgraph* g, qsxh_tensor** out);
+int qsxh_zxgraph_destroy(qsxh_zxgraph* g);
 int qsxh_tensor_shape(const qsxh_tensor* t, size_t* dims, size_t max_dims, size_t* n_dims);
 /* host copy of the matrix, row-major complex128; n_doubles = 2 * rows * cols */
 int qsxh_tensor_download(const qsxh_tensor* t, double* out, size_t n_doubles);

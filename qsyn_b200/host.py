@@ -32,6 +32,11 @@ def lib() -> C.CDLL:
             "qsxh_circuit_gate_stream": [vp, C.POINTER(C.POINTER(abi.GateStruct)), C.POINTER(sz)],
             "qsxh_circuit_destroy": [vp],
             "qsxh_qc2ts": [vp, C.POINTER(vp)],
+            "qsxh_zxgraph_from_zx_text": [C.c_char_p, C.c_int, C.POINTER(vp)],
+            "qsxh_zxgraph_from_zx_file": [C.c_char_p, C.c_int, C.POINTER(vp)],
+            "qsxh_zxgraph_info": [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)],
+            "qsxh_zx2ts": [vp, C.POINTER(vp)],
+            "qsxh_zxgraph_destroy": [vp],
             "qsxh_tensor_shape": [vp, C.POINTER(sz), sz, C.POINTER(sz)],
             "qsxh_tensor_download": [vp, C.POINTER(C.c_double), sz],
             "qsxh_tensor_adjoint_inplace": [vp],
@@ -117,6 +122,39 @@ class Circuit:
     def close(self):
         if getattr(self, "_h", None):
             lib().qsxh_circuit_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ZXGraph:
+    """qsyn::zx::ZXGraph behind the host C ABI (`.zx` reader + zx2ts)."""
+
+    def __init__(self, zx_text: str | None = None, zx_file: str | None = None, keep_id: bool = False):
+        self._h = C.c_void_p()
+        if zx_text is not None:
+            _check(lib().qsxh_zxgraph_from_zx_text(zx_text.encode(), int(keep_id), C.byref(self._h)))
+        else:
+            _check(lib().qsxh_zxgraph_from_zx_file(str(zx_file).encode(), int(keep_id), C.byref(self._h)))
+
+    @property
+    def info(self):
+        v = [C.c_size_t() for _ in range(4)]
+        _check(lib().qsxh_zxgraph_info(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("inputs", "outputs", "vertices", "edges"), (x.value for x in v)))
+
+    def zx2ts(self) -> "Tensor":
+        h = C.c_void_p()
+        _check(lib().qsxh_zx2ts(self._h, C.byref(h)))
+        return Tensor(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().qsxh_zxgraph_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

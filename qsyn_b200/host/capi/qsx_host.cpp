@@ -3,10 +3,12 @@
 
 #include <cstring>
 #include <format>
+#include <filesystem>
 #include <sstream>
 #include <string>
 
 #include "../convert/qcir_to_tensor.hpp"
+#include "../convert/zxgraph_to_tensor.hpp"
 #include "../qcir/qcir.hpp"
 #include "../tensor/qtensor.hpp"
 
@@ -20,6 +22,9 @@ struct qsxh_circuit {
 };
 struct qsxh_tensor {
     qsyn::tensor::QTensor<double> tensor;
+};
+struct qsxh_zxgraph {
+    qsyn::zx::ZXGraph graph;
 };
 
 namespace {
@@ -131,6 +136,55 @@ int qsxh_circuit_gate_stream(qsxh_circuit* c, const qsx_gate** gates, size_t* n_
 
 int qsxh_circuit_destroy(qsxh_circuit* c) {
     delete c;
+    return QSX_OK;
+}
+
+int qsxh_zxgraph_from_zx_text(const char* text, int keep_id, qsxh_zxgraph** out) {
+    if (text == nullptr || out == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    return guarded([&] {
+        std::istringstream in{std::string(text)};
+        auto g = qsyn::zx::from_zx(in, keep_id != 0);
+        if (!g.has_value()) return fail(QSX_ERR_BAD_ARG, "the format of the ZX text has something wrong (see the log)");
+        *out = new qsxh_zxgraph{std::move(*g)};
+        return (int)QSX_OK;
+    });
+}
+
+int qsxh_zxgraph_from_zx_file(const char* path, int keep_id, qsxh_zxgraph** out) {
+    if (path == nullptr || out == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    return guarded([&] {
+        auto g = qsyn::zx::from_zx(std::filesystem::path(path), keep_id != 0);
+        if (!g.has_value()) return fail(QSX_ERR_BAD_ARG, std::string("cannot read a ZXGraph from \"") + path + "\"");
+        g->set_filename(std::filesystem::path(path).stem().string());
+        *out = new qsxh_zxgraph{std::move(*g)};
+        return (int)QSX_OK;
+    });
+}
+
+int qsxh_zxgraph_info(const qsxh_zxgraph* g, size_t* n_inputs, size_t* n_outputs, size_t* n_vertices, size_t* n_edges) {
+    if (g == nullptr) return fail(QSX_ERR_BAD_ARG, "null graph");
+    if (n_inputs != nullptr) *n_inputs = g->graph.num_inputs();
+    if (n_outputs != nullptr) *n_outputs = g->graph.num_outputs();
+    if (n_vertices != nullptr) *n_vertices = g->graph.num_vertices();
+    if (n_edges != nullptr) *n_edges = g->graph.num_edges();
+    return QSX_OK;
+}
+
+int qsxh_zx2ts(const qsxh_zxgraph* g, qsxh_tensor** out) {
+    if (g == nullptr || out == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    return guarded([&] {
+        auto t = qsyn::to_tensor(g->graph);  // conversion_cmd.cpp:226
+        if (!t.has_value()) return fail(QSX_ERR_UNSUPPORTED, "conversion failed (see the log)");
+        t->set_filename(g->graph.get_filename());
+        t->add_procedures(g->graph.get_procedures());
+        t->add_procedure("ZX2TS");
+        *out = new qsxh_tensor{std::move(*t)};
+        return (int)QSX_OK;
+    });
+}
+
+int qsxh_zxgraph_destroy(qsxh_zxgraph* g) {
+    delete g;
     return QSX_OK;
 }
 

@@ -196,3 +196,30 @@ def test_host_layer_zx_tensor_values_match_oracle(tmp_path, goldens, name):
     want = Z.zx2ts(Z.zxgraph_from_zx_text(goldens["inputs"][f"benchmark/zx/{name}.zx"]))
     assert got.shape == want.shape
     assert np.allclose(got, want, rtol=0, atol=1.5e-6)
+
+
+@pytest.mark.parametrize("name", ["swap", "cnot", "tof3", "tof3_zh", "tof3_op"])
+def test_host_c_abi_zx2ts_matches_oracle_to_rounding(goldens, name):
+    """qsxh_zxgraph_from_zx_text + qsxh_zx2ts (include/qsx_host.h): full double precision this time."""
+    from qsyn_b200 import host
+    text = goldens["inputs"][f"benchmark/zx/{name}.zx"]
+    g = host.ZXGraph(zx_text=text)
+    og = Z.zxgraph_from_zx_text(text)
+    assert g.info == {"inputs": len(og.inputs), "outputs": len(og.outputs), "vertices": len(og.vertices),
+                      "edges": sum(len(v.nbrs) for v in og.vertices) // 2}
+    got = g.zx2ts().to_numpy()
+    want = Z.zx2ts(og)
+    assert got.shape == want.shape and np.allclose(got, want, rtol=0, atol=1e-14)
+    with pytest.raises(Exception):
+        host.ZXGraph(zx_text="Q0 S1\n")
+
+
+@pytest.mark.gpu
+def test_host_c_abi_zx_vs_qcir_equivalence_runs_on_the_device(goldens):
+    from qsyn_b200 import host
+    zx = host.ZXGraph(zx_text=goldens["inputs"]["benchmark/zx/swap.zx"]).zx2ts()
+    qc = host.Circuit(n_qubits=2)
+    for a, b in [(0, 1), (1, 0), (0, 1)]:
+        qc.append("cx", [a, b])
+    r, text = qc.qc2ts().equiv(zx, 1e-6, True)
+    assert r.equivalent == 1 and text == "Equivalent\n- Global Norm : 1\n- Global Phase: 0\n"
