@@ -241,11 +241,25 @@ __device__ __forceinline__ void op_dtab_half(double2 (&e)[1 << R], const double2
     }
 }
 
-// The handlers almost every sweep uses.  sweep_kernel<R, LEAN = true> contains only these: the
+// The handlers almost every sweep uses.  sweep_kernel<R, kLean> contains only these: the
 // kernel is an interpreter whose hot loop jumps between handler bodies, and the full set is
 // ~160 KB of SASS -- far beyond the instruction caches ("no_instruction" was the third largest
-// stall reason).  A sweep that needs any other handler runs in the LEAN = false instantiation.
+// stall reason).  A sweep that needs any other handler runs in the kFull instantiation.
 __host__ __device__ constexpr bool is_common_handler(int h) { return h >= 0 && h < H_COMMON; }
+
+// Three instantiations of the interpreter (template parameter MODE):
+//   kFull  every handler;
+//   kLean  the common handlers, 128 registers (R = 4: 4 CTAs of 128 threads per SM);
+//   kLight the common handlers WITHOUT the general 2x2 (the only common handler that needs more
+//          than ~96 registers: 16 live elements + 8 matrix entries + products), compiled for 96
+//          registers = 5 CTAs (20 warps) per SM.  The interpreter is latency-bound (dispatch
+//          chain, CTA ramp), so the extra warps are worth -5 % on Clifford+T sweeps, while the
+//          general 2x2 spills at 96 registers (+33 % on rotation circuits): sweeps that contain
+//          one stay in kLean.  Only CTAs of <= 128 threads (the default tile) can run kLight.
+constexpr int kFull = 0, kLean = 1, kLight = 2;
+__host__ __device__ constexpr bool is_light_handler(int h) { return is_common_handler(h) && !(h >= H_U1 && h < H_U1 + kJ); }
+__host__ __device__ constexpr int mode_threads_log2(int R, int mode) { return mode == kLight ? 7 : max_threads_log2(R); }
+__host__ __device__ constexpr int mode_min_ctas(int R, int mode) { return mode == kLight ? 5 : min_ctas_per_sm(R); }
 
 // One handler = one straight-line body; everything about it is known at compile time.
 template <int R, int H>
@@ -318,13 +332,15 @@ __device__ __forceinline__ void run_handler(double2 (&e)[1 << R], double2& scal,
     }
 }
 
-#define QSX_CASE(h) \
-    case h: run_handler<R, h>(e, scal, op, creg, pool_off, sel, grow, pool); break;
+#define QSX_CASE(h)                                                                                   \
+    case h:                                                                                           \
+        if constexpr (MODE != kLight || is_light_handler(h)) run_handler<R, h>(e, scal, op, creg, pool_off, sel, grow, pool); \
+        break;
 #define QSX_CASE8(b) QSX_CASE(b) QSX_CASE(b + 1) QSX_CASE(b + 2) QSX_CASE(b + 3) QSX_CASE(b + 4) QSX_CASE(b + 5) QSX_CASE(b + 6) QSX_CASE(b + 7)
 #define QSX_CASE16(b) QSX_CASE8(b) QSX_CASE8(b + 8)
 
 // hdr = {handler, cother, czero, pool}: the first 16 bytes of the op, loaded by the caller
-template <int R, bool LEAN>
+template <int R, int MODE>
 __device__ __forceinline__ void apply_op(double2 (&e)[1 << R], double2& scal, const DevOp* __restrict__ op, int4 hdr, uint32_t grow,
                                          const double* __restrict__ pool) {
     uint32_t const cother = (uint32_t)hdr.y, czero = (uint32_t)hdr.z;
@@ -332,7 +348,7 @@ __device__ __forceinline__ void apply_op(double2 (&e)[1 << R], double2& scal, co
     int const pool_off  = hdr.w;
     uint32_t const creg = op->creg;  // (these two are loaded only inside the handlers that read them)
     int const sel       = op->sel;
-    if constexpr (LEAN) {
+    if constexpr (MODE != kFull) {
         switch (hdr.x) {  // dense 0..H_COMMON-1
             QSX_CASE16(0)
             QSX_CASE16(16)
@@ -384,8 +400,8 @@ __device__ __forceinline__ void permute_rows(uint32_t (&rows)[R + 1], const DevP
     }
 }
 
-template <int R, bool LEAN>
-__global__ void __launch_bounds__(1 << max_threads_log2(R), min_ctas_per_sm(R))
+template <int R, int MODE>
+__global__ void __launch_bounds__(1 << mode_threads_log2(R, MODE), mode_min_ctas(R, MODE))
     sweep_kernel(double2* __restrict__ u, const unsigned char* __restrict__ gprog, uint32_t prog_bytes, int log2_ncols,
                  int log2_ncb, uint32_t reverse) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -505,7 +521,7 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), min_ctas_per_sm(R))
                 run_handler<R, H_H>(e, scal, ops + o, 0u, 0, 0, grow, pool);  // timing experiment: control test, no switch
 #else
                 int4 const hdr = *reinterpret_cast<const int4*>(ops + o);
-                apply_op<R, LEAN>(e, scal, ops + o, hdr, grow, pool);
+                apply_op<R, MODE>(e, scal, ops + o, hdr, grow, pool);
 #endif
             }
         }
@@ -557,7 +573,7 @@ __global__ void __launch_bounds__(1 << max_threads_log2(R), min_ctas_per_sm(R))
     }
 }
 
-template <int R, bool LEAN>
+template <int R, int MODE>
 cudaError_t launch_sweep_r(double2* u, int n, uint64_t ncols, const DevSweep& hs, const unsigned char* prog,
                            size_t prog_bytes, bool reverse, cudaStream_t s) {
     (void)n;
@@ -569,18 +585,18 @@ cudaError_t launch_sweep_r(double2* u, int n, uint64_t ncols, const DevSweep& hs
     while ((1ull << log2_ncols) < ncols) ++log2_ncols;
     int const log2_ncb = log2_ncols - hs.log2w;
     uint64_t const nblocks = 1ull << (log2_ncb + hs.n_outer);
-    if (threads < 1 || threads > (1 << max_threads_log2(R)) || nblocks > 0x7fffffffull)
+    if (threads < 1 || threads > (1 << mode_threads_log2(R, MODE)) || nblocks > 0x7fffffffull)
         return cudaErrorInvalidConfiguration;
     static bool attr_set[64] = {};  // per template instantiation, per device
     int dev                  = 0;
     if (cudaError_t const rc = cudaGetDevice(&dev); rc != cudaSuccess) return rc;
     if (dev < 64 && !attr_set[dev]) {
         cudaError_t const rc =
-            cudaFuncSetAttribute(sweep_kernel<R, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(sweep_kernel<R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (rc != cudaSuccess) return rc;
         attr_set[dev] = true;
     }
-    sweep_kernel<R, LEAN><<<(unsigned)nblocks, threads, smem, s>>>(u, prog, (uint32_t)prog_bytes, log2_ncols, log2_ncb, reverse ? 1u : 0u);
+    sweep_kernel<R, MODE><<<(unsigned)nblocks, threads, smem, s>>>(u, prog, (uint32_t)prog_bytes, log2_ncols, log2_ncb, reverse ? 1u : 0u);
     return cudaGetLastError();
 }
 
@@ -943,24 +959,28 @@ cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, int R, const DevSwee
             default: return cudaErrorInvalidValue;
         }
     }
-    // does every micro-op of this sweep have a handler in the lean instantiation?
-    bool lean = true;
+    // the smallest instantiation that has a handler for every micro-op of this sweep
+    bool lean = true, light = R == 4 && (hs.m - R + hs.log2w) <= mode_threads_log2(R, kLight);
     {
         const unsigned char* const host = reinterpret_cast<const unsigned char*>(&hs);
         const DevOp* const ops = reinterpret_cast<const DevOp*>(host + sizeof(DevSweep));
-        for (int i = 0; i < hs.n_ops && lean; ++i) lean = is_common_handler(ops[i].handler);
+        for (int i = 0; i < hs.n_ops && lean; ++i) {
+            lean  = is_common_handler(ops[i].handler);
+            light = light && is_light_handler(ops[i].handler);
+        }
     }
+    if (lean && light) return launch_sweep_r<4, kLight>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
     switch (R * 2 + (lean ? 1 : 0)) {
-        case 2: return launch_sweep_r<1, false>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
-        case 3: return launch_sweep_r<1, true>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
-        case 4: return launch_sweep_r<2, false>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
-        case 5: return launch_sweep_r<2, true>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
-        case 6: return launch_sweep_r<3, false>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
-        case 7: return launch_sweep_r<3, true>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
-        case 8: return launch_sweep_r<4, false>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
-        case 9: return launch_sweep_r<4, true>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
-        case 10: return launch_sweep_r<5, false>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
-        case 11: return launch_sweep_r<5, true>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
+        case 2: return launch_sweep_r<1, kFull>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
+        case 3: return launch_sweep_r<1, kLean>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
+        case 4: return launch_sweep_r<2, kFull>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
+        case 5: return launch_sweep_r<2, kLean>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
+        case 6: return launch_sweep_r<3, kFull>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
+        case 7: return launch_sweep_r<3, kLean>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
+        case 8: return launch_sweep_r<4, kFull>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
+        case 9: return launch_sweep_r<4, kLean>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
+        case 10: return launch_sweep_r<5, kFull>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
+        case 11: return launch_sweep_r<5, kLean>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
         default: return cudaErrorInvalidValue;
     }
 }
