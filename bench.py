@@ -279,7 +279,7 @@ def run_ours(args):
             "e2e": {"value": round(e2e_value, 2), "unit": "GB/s", "ms_per_step": round(e2e_s * 1e3, 4),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64,
                     "note": "host gate arrays -> qsx_apply_gates_async (schedule + program upload + sweeps) x2 -> qsx_equiv_partial -> verdict"},
-            "roofline": {"bound": "hbm", "kernel": ("dense_kernel<%d>" % args.dense) if args.dense else ("sweep_kernel<%d>" % args.reg), "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": ("dense_kernel<%d>" % args.dense) if args.dense else ("sweep_kernel<%d, *>" % args.reg), "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": st_a.alg_bytes_per_run / max(st_a.n_sweeps, 1),
                          "launches": st_a.n_sweeps, "avg_launch_us": round(sweep_ms * 1e3 / max(st_a.n_sweeps, 1), 2)},
@@ -289,7 +289,7 @@ def run_ours(args):
             fp64_peak_tflops = 36.66  # measured DFMA peak of this pool's B200 (bin/fp64_peak, profiles/r1_fp64_peak.json)
             instr = _fp64_instructions_per_run(plan_a, float(dim) * ncols)
             ach = 2.0 * instr / (sweep_ms * 1e-3) / 1e12  # an FP64 pipe slot is worth 2 flop at the DFMA peak
-            out["roofline_fp64"] = {"bound": "fp64_pipe", "kernel": "sweep_kernel<%d>" % args.reg, "achieved": round(ach, 2),
+            out["roofline_fp64"] = {"bound": "fp64_pipe", "kernel": "sweep_kernel<%d, *>" % args.reg, "achieved": round(ach, 2),
                                     "peak": fp64_peak_tflops, "unit": "TFLOP/s (FP64 pipe slots x 2)", "frac": round(ach / fp64_peak_tflops, 4),
                                     "fp64_instructions_per_element_per_launch": round(instr / (float(dim) * ncols) / max(st_a.n_sweeps, 1), 2)}
         if world == 1 and not args.no_cpu_baseline:
