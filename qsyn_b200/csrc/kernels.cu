@@ -112,16 +112,6 @@ __device__ __forceinline__ void u1_inplace(double2& a, double2& b, const double*
         : "d"(m[0]), "d"(m[1]), "d"(m[2]), "d"(m[3]), "d"(m[4]), "d"(m[5]), "d"(m[6]), "d"(m[7]));
 }
 
-template <int N, int I = 0, class Fn>
-__device__ __forceinline__ void static_switch(int v, Fn&& fn) {
-    if constexpr (I < N) {
-        if (v == I)
-            fn(std::integral_constant<int, I>{});
-        else
-            static_switch<N, I + 1>(v, fn);
-    }
-}
-
 // ---------------------------------------------------------------------------------------
 // register-level micro-ops.  E = 2^R elements per thread.  `creg` is a required-one mask over
 // the register index; it is the same for every thread of the grid, so tests on it are uniform
@@ -263,7 +253,7 @@ __host__ __device__ constexpr int mode_min_ctas(int R, int mode) { return mode =
 
 // One handler = one straight-line body; everything about it is known at compile time.
 template <int R, int H>
-__device__ __forceinline__ void run_handler(double2 (&e)[1 << R], double2& scal, const DevOp* __restrict__ op, uint32_t creg,
+__device__ __forceinline__ void run_handler(double2 (&e)[1 << R], const DevOp* __restrict__ op, uint32_t creg,
                                             int pool_off, int sel, uint32_t grow, const double* __restrict__ pool) {
     const double* const c = op->c;
     if constexpr ((H >= H_H && H < H_H + kJ) || (H >= H_HG && H < H_HG + kJ)) {
@@ -289,10 +279,6 @@ __device__ __forceinline__ void run_handler(double2 (&e)[1 << R], double2& scal,
         if constexpr (JA < R && JB < JA) op_swap<R, JA, JB, (H < H_SWAPG)>(e, creg, c[7]);
     } else if constexpr (H == H_U2) {
         op_u2<R>(e, pool + pool_off, creg);
-    } else if constexpr (H == H_DSCAL) {
-        bool const hi   = sel >= 0 && ((grow >> sel) & 1u);
-        double2 const d = hi ? make_double2(c[2], c[3]) : make_double2(c[0], c[1]);
-        scal            = cmul(scal, d);
     } else if constexpr (H >= H_DTABH && H < H_DTABH + kJ) {
         constexpr int J = H - H_DTABH;
         if constexpr (J < R) op_dtab_half<R, J>(e, reinterpret_cast<const double2*>(pool + pool_off));
@@ -308,16 +294,11 @@ __device__ __forceinline__ void run_handler(double2 (&e)[1 << R], double2& scal,
         const double2* const tab = reinterpret_cast<const double2*>(pool + pool_off);
 #pragma unroll
         for (int i = 0; i < (1 << R); ++i) cmul_inplace(e[i], tab[i]);
-    } else if constexpr (H == H_SAPPLY) {
-        double2 const sv = scal;
-#pragma unroll
-        for (int i = 0; i < (1 << R); ++i) cmul_inplace(e[i], sv);
-        scal = make_double2(1.0, 0.0);
     } else if constexpr (H == H_SCALN) {
         // every per-thread scalar of the stage, without a dispatch per gate
         const uint4* const ent = reinterpret_cast<const uint4*>(pool + pool_off);
         int const count        = op->j0;
-        double2 sv             = scal;
+        double2 sv             = make_double2(1.0, 0.0);
         for (int k = 0; k < count; ++k) {
             uint4 const w    = ent[3 * k];  // cother, czero, sel, pad
             bool const pass  = (grow & w.x) == w.x && (grow & w.y) == 0u;
@@ -328,20 +309,19 @@ __device__ __forceinline__ void run_handler(double2 (&e)[1 << R], double2& scal,
         }
 #pragma unroll
         for (int i = 0; i < (1 << R); ++i) cmul_inplace(e[i], sv);
-        scal = make_double2(1.0, 0.0);
     }
 }
 
 #define QSX_CASE(h)                                                                                   \
     case h:                                                                                           \
-        if constexpr (MODE != kLight || is_light_handler(h)) run_handler<R, h>(e, scal, op, creg, pool_off, sel, grow, pool); \
+        if constexpr (MODE != kLight || is_light_handler(h)) run_handler<R, h>(e, op, creg, pool_off, sel, grow, pool); \
         break;
 #define QSX_CASE8(b) QSX_CASE(b) QSX_CASE(b + 1) QSX_CASE(b + 2) QSX_CASE(b + 3) QSX_CASE(b + 4) QSX_CASE(b + 5) QSX_CASE(b + 6) QSX_CASE(b + 7)
 #define QSX_CASE16(b) QSX_CASE8(b) QSX_CASE8(b + 8)
 
 // hdr = {handler, cother, czero, pool}: the first 16 bytes of the op, loaded by the caller
 template <int R, int MODE>
-__device__ __forceinline__ void apply_op(double2 (&e)[1 << R], double2& scal, const DevOp* __restrict__ op, int4 hdr, uint32_t grow,
+__device__ __forceinline__ void apply_op(double2 (&e)[1 << R], const DevOp* __restrict__ op, int4 hdr, uint32_t grow,
                                          const double* __restrict__ pool) {
     uint32_t const cother = (uint32_t)hdr.y, czero = (uint32_t)hdr.z;
     if ((grow & cother) != cother || (grow & czero) != 0u) return;
@@ -369,8 +349,6 @@ __device__ __forceinline__ void apply_op(double2 (&e)[1 << R], double2& scal, co
             QSX_CASE16(80)
             QSX_CASE16(96)
             QSX_CASE16(112)
-            QSX_CASE(128)
-            QSX_CASE(129)
             default: break;
         }
     }
@@ -510,7 +488,6 @@ __global__ void __launch_bounds__(1 << mode_threads_log2(R, MODE), mode_min_ctas
 
         {
             int const ob = st->op_begin, oe = st->op_end;
-            double2 scal = make_double2(1.0, 0.0);  // per-thread product of the stage's K_DSCAL ops
             // (prefetching the next header was measured: the 8 extra live registers spill, -12 %)
             for (int o = ob; o < oe; ++o) {
 #if defined(QSX_EXP_DIRECT) && QSX_EXP_DIRECT == 1
@@ -521,7 +498,7 @@ __global__ void __launch_bounds__(1 << mode_threads_log2(R, MODE), mode_min_ctas
                 run_handler<R, H_H>(e, scal, ops + o, 0u, 0, 0, grow, pool);  // timing experiment: control test, no switch
 #else
                 int4 const hdr = *reinterpret_cast<const int4*>(ops + o);
-                apply_op<R, MODE>(e, scal, ops + o, hdr, grow, pool);
+                apply_op<R, MODE>(e, ops + o, hdr, grow, pool);
 #endif
             }
         }

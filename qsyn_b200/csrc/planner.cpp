@@ -33,12 +33,11 @@ int handler_of(MicroOp const& u) {
             return (g ? H_SWAPG : H_SWAP) + ja * kJ + jb;
         }
         case K_U2: return H_U2;
-        case K_DSCAL: return H_DSCAL;
         case K_DTABH: return H_DTABH + u.j0;
         case K_DTABF: return H_DTABF;
         case K_SCALN: return H_SCALN;
         case K_PHJ: return H_PHJ + u.j0;
-        default: return H_SAPPLY;
+        default: assert(false && "this micro-op kind is never sent to the device"); return -1;
     }
 }
 

@@ -9,15 +9,15 @@ namespace qsx::detail {
 
 // ---- micro-op emission ------------------------------------------------------------------
 //
-// Non-diagonal ops map 1:1 to register micro-ops.  Diagonal ops (PHASE/NEG/MULI/DIAG) commute
-// with each other and with any op that does not act non-diagonally on their bits, so they are
-// held back and merged:
+// Non-diagonal ops become register micro-ops (runs of uncontrolled single-qubit ops on one bit
+// are multiplied together first).  Diagonal ops (PHASE/NEG/MULI/DIAG) commute with each other
+// and with any op that does not act non-diagonally on their bits, so they are held back and merged:
 //   * a diagonal op whose bits are all OUTSIDE the registers multiplies every element a thread
-//     holds by the same number: it becomes one complex multiply of a per-thread scalar
-//     (K_DSCAL), applied to the registers once at the end of the stage (K_SAPPLY);
-//   * the others are multiplied together, per distinct thread-level condition, into a table
-//     indexed by the register index (K_DTABH when only elements with one register bit set are
-//     affected, K_DTABF otherwise).
+//     holds by the same number: a per-thread scalar; all scalars of a stage travel as ONE
+//     micro-op (K_SCALN) applied at the end of the stage;
+//   * the others are multiplied together, per distinct thread-level condition, into a factored
+//     table over the register index, emitted as K_PHJ (one phase on one bit), K_DTABH (the
+//     elements with one register bit set) or K_DTABF (all 2^R elements).
 
 namespace {
 

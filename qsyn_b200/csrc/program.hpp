@@ -56,10 +56,10 @@ enum MicroKind : int32_t {
     K_XC     = 4,   // X on register bit j0 controlled by register bit j1 (compile-time specialised CX)
     K_SWAP   = 5,   // swap register bits j0, j1
     K_U2     = 6,   // dense 4x4 on register bits (1,0); matrix at pool
-    K_DSCAL  = 7,   // per-thread scalar: s *= (sel >= 0 && row bit sel) ? d1 : d0    c = d0, d1
+    K_DSCAL  = 7,   // (scheduler-internal) one per-thread scalar: (sel >= 0 && row bit sel) ? d1 : d0, c = d0, d1;
+                    // never sent to the device on its own: a stage's scalars travel as ONE K_SCALN
     K_DTABH  = 8,   // e[i] *= tab[i without bit j0] for the 8 (2^(R-1)) elements with bit j0 set; table at pool
     K_DTABF  = 9,   // e[i] *= tab[i] for all 2^R elements; table at pool
-    K_SAPPLY = 10,  // e[i] *= s for all i ; s = 1
     K_PHJ    = 12,  // e[i] *= w for the elements with register bit j0 set (a K_DTABH whose entries are all equal)
     K_SCALN  = 11,  // all per-thread scalars of a stage in one micro-op: for k < j0 entries at pool
                     // {cother, czero, sel, pad, d0.re, d0.im, d1.re, d1.im} (48 B each):
@@ -90,11 +90,9 @@ enum Handler : int32_t {
     H_SWAP   = H_ADG + kJ,           // +JA*kJ+JB  (JA > JB)
     H_SWAPG  = H_SWAP + kJ * kJ,     // +JA*kJ+JB
     H_U2     = H_SWAPG + kJ * kJ,
-    H_DSCAL  = H_U2 + 1,
-    H_SAPPLY = H_DSCAL + 1,
-    H_COUNT  = H_SAPPLY + 1,
+    H_COUNT  = H_U2 + 1,
 };
-static_assert(H_COMMON == 52 && H_COUNT == 130, "the kernel's switch enumerates these ranges");
+static_assert(H_COMMON == 52 && H_COUNT == 128, "the kernel's switch enumerates these ranges");
 
 // Thread-level predicate of every micro-op: (row & cother) == cother && (row & czero) == 0, where
 // `row` is the thread's global row index with the register bits cleared.

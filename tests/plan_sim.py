@@ -94,9 +94,10 @@ def run_plan(dump, u):
 
 
 def run_plan_uops(dump, u):
-    """Executes the MICRO-ops the kernel runs (merged diagonals, per-thread scalars), with the
-    kernel's semantics: thread-level predicate on (cother, czero); K_DSCAL accumulates a
-    per-thread scalar that K_SAPPLY applies at the end of the stage."""
+    """Executes the MICRO-ops the kernel runs (fused single-qubit ops, merged diagonals, per-thread
+    scalars), with the kernel's semantics: thread-level predicate on (cother, czero); K_SCALN
+    carries all per-thread scalars of a stage.  (DSCAL / SAPPLY are a retired encoding that the
+    scheduler no longer emits; kept here so that old dumps still replay.)"""
     n = dump["n"]
     rows = np.arange(2**n)
     for sw in dump["sweeps"]:
