@@ -356,3 +356,39 @@ def test_async_apply_matches_sync_and_reuses_staging():
     for u, w in zip(us, want):
         assert np.array_equal(u.download().view(np.float64), w.view(np.float64))
         u.close()
+
+
+def _device_fuzz(seed, seconds, max_cases=10**9):
+    import time
+    rng = np.random.default_rng(seed)
+    t0, n_ok, worst = time.time(), 0, 0.0
+    while time.time() - t0 < seconds and n_ok < max_cases:
+        n, g, cseed = int(rng.integers(1, 11)), int(rng.integers(10, 300)), int(rng.integers(1 << 30))
+        qc = _rand_circuit(n, g, cseed, extra=bool(rng.integers(2)))
+        want = O.to_matrix_rowform(qc)
+        opts = dict(fuse=int(rng.integers(4) > 0), reg_qubits=int(rng.integers(1, 6)), tile_qubits=int(rng.integers(2, 11)),
+                    log2_tile_cols=int(rng.choice([-1, 1, 2, 3, 4])), max_ops_per_sweep=int(rng.choice([5, 17, 96, 300])),
+                    min_tail_ops=int(rng.choice([-1, 8])), search=int(rng.choice([-1, 2])), stage_search=int(rng.choice([-1, 1])),
+                    no_1q_fusion=int(rng.integers(2)), no_diag_conjugation=int(rng.integers(2)),
+                    no_perm_folding=int(rng.integers(3)), snap_tol=float(rng.choice([1e-15, -1.0])))
+        shards = int(rng.choice([1, 1, 2, 4])) if n >= 3 else 1
+        ncols = 2**n // shards
+        k = int(rng.integers(shards))
+        got = run_device(qc, Q.PlanOptions(**opts), k * ncols, ncols)
+        err = float(frob_rel(got, want[:, k * ncols:(k + 1) * ncols]))
+        assert err < TOL, (n, g, cseed, opts, shards, k, err)
+        worst = max(worst, err)
+        n_ok += 1
+    return n_ok, worst
+
+
+def test_random_circuits_times_random_options_on_device():
+    """Differential fuzz of the whole device path (scheduler options, every kernel instantiation,
+    column shards) against the oracle; `python -m tests.test_gpu_parity SEED SECONDS` runs it longer."""
+    n_ok, worst = _device_fuzz(20261019, 15.0, 300)
+    assert n_ok >= 30 and worst < TOL
+
+
+if __name__ == "__main__":
+    import sys
+    print(_device_fuzz(int(sys.argv[1]) if len(sys.argv) > 1 else 1, float(sys.argv[2]) if len(sys.argv) > 2 else 60.0))
