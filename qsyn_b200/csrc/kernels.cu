@@ -378,10 +378,11 @@ __device__ __forceinline__ void permute_rows(uint32_t (&rows)[R + 1], const DevP
     }
 }
 
-template <int R, int MODE>
+// IDENT: the unitary is (lazily) the identity -- the first stage synthesises it instead of reading it.
+template <int R, int MODE, bool IDENT>
 __global__ void __launch_bounds__(1 << mode_threads_log2(R, MODE), mode_min_ctas(R, MODE))
     sweep_kernel(double2* __restrict__ u, const unsigned char* __restrict__ gprog, uint32_t prog_bytes, int log2_ncols,
-                 int log2_ncb, uint32_t reverse) {
+                 int log2_ncb, uint32_t flags, uint32_t col0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // the sweep program (a few KB, read by every thread for every op) is staged in shared
     // memory once per CTA; the tile follows it
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(1 << mode_threads_log2(R, MODE), mode_min_ctas
     uint32_t const cw    = tid & ((1u << log2w) - 1u);
     uint32_t const trow  = tid >> log2w;
     // odd sweeps walk the tiles backwards: what the previous sweep wrote last is still in L2
-    uint64_t const tid64 = reverse ? (uint64_t)(gridDim.x - 1u - blockIdx.x) : (uint64_t)blockIdx.x;
+    uint64_t const tid64 = (flags & 1u) ? (uint64_t)(gridDim.x - 1u - blockIdx.x) : (uint64_t)blockIdx.x;
     uint64_t const cb    = tid64 & ((1ull << log2_ncb) - 1ull);
     uint32_t const rc    = (uint32_t)(tid64 >> log2_ncb);
 
@@ -462,13 +463,25 @@ __global__ void __launch_bounds__(1 << mode_threads_log2(R, MODE), mode_min_ctas
                 for (int j = 0; j < R; ++j) gc[j] = rows[1 + j] ^ rows[0];
             }
             const double2* const gp = u + col;
+            if constexpr (IDENT) {
+                uint32_t const gcol = col0 + (uint32_t)col;
 #pragma unroll
-            for (int i = 0; i < (1 << R); ++i) {
-                uint32_t r = gb;
+                for (int i = 0; i < (1 << R); ++i) {
+                    uint32_t r = gb;
 #pragma unroll
-                for (int j = 0; j < R; ++j)
-                    if ((i >> j) & 1) r ^= gc[j];
-                e[i] = __ldcg(gp + ((size_t)r << log2_ncols));
+                    for (int j = 0; j < R; ++j)
+                        if ((i >> j) & 1) r ^= gc[j];
+                    e[i] = make_double2(r == gcol ? 1.0 : 0.0, 0.0);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < (1 << R); ++i) {
+                    uint32_t r = gb;
+#pragma unroll
+                    for (int j = 0; j < R; ++j)
+                        if ((i >> j) & 1) r ^= gc[j];
+                    e[i] = __ldcg(gp + ((size_t)r << log2_ncols));
+                }
             }
         } else {
             uint32_t ss[R];
@@ -550,9 +563,9 @@ __global__ void __launch_bounds__(1 << mode_threads_log2(R, MODE), mode_min_ctas
     }
 }
 
-template <int R, int MODE>
+template <int R, int MODE, bool IDENT = false>
 cudaError_t launch_sweep_r(double2* u, int n, uint64_t ncols, const DevSweep& hs, const unsigned char* prog,
-                           size_t prog_bytes, bool reverse, cudaStream_t s) {
+                           size_t prog_bytes, uint32_t flags, uint32_t col0, cudaStream_t s) {
     (void)n;
     int const m        = hs.m;
     int const threads  = 1 << (m - R + hs.log2w);
@@ -569,11 +582,11 @@ cudaError_t launch_sweep_r(double2* u, int n, uint64_t ncols, const DevSweep& hs
     if (cudaError_t const rc = cudaGetDevice(&dev); rc != cudaSuccess) return rc;
     if (dev < 64 && !attr_set[dev]) {
         cudaError_t const rc =
-            cudaFuncSetAttribute(sweep_kernel<R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(sweep_kernel<R, MODE, IDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (rc != cudaSuccess) return rc;
         attr_set[dev] = true;
     }
-    sweep_kernel<R, MODE><<<(unsigned)nblocks, threads, smem, s>>>(u, prog, (uint32_t)prog_bytes, log2_ncols, log2_ncb, reverse ? 1u : 0u);
+    sweep_kernel<R, MODE, IDENT><<<(unsigned)nblocks, threads, smem, s>>>(u, prog, (uint32_t)prog_bytes, log2_ncols, log2_ncb, flags, col0);
     return cudaGetLastError();
 }
 
@@ -927,8 +940,11 @@ cudaError_t launch_set_identity(double2* u, int n, uint64_t col0, uint64_t ncols
 }
 
 cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, int R, const DevSweep& hs, const unsigned char* prog,
-                         size_t prog_bytes, bool reverse, cudaStream_t s) {
+                         size_t prog_bytes, bool reverse, bool from_identity, uint64_t col0, cudaStream_t s) {
+    uint32_t const flags = (reverse ? 1u : 0u) | (from_identity ? 2u : 0u);
+    uint32_t const c0    = (uint32_t)col0;
     if (hs.dense_k != 0) {
+        if (from_identity) return cudaErrorInvalidValue;  // (the runtime materialises the identity first)
         switch (hs.dense_k) {
             case 3: return launch_dense_k<3>(u, ncols, hs, prog, s);
             case 4: return launch_dense_k<4>(u, ncols, hs, prog, s);
@@ -946,20 +962,34 @@ cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, int R, const DevSwee
             light = light && is_light_handler(ops[i].handler);
         }
     }
-    if (lean && light) return launch_sweep_r<4, kLight>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
+    if (from_identity) {  // instantiated for the default register count only (sweep_can_start_from_identity)
+        if (R != 4 || !lean) return cudaErrorInvalidValue;
+        return light ? launch_sweep_r<4, kLight, true>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s)
+                     : launch_sweep_r<4, kLean, true>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
+    }
+    if (lean && light) return launch_sweep_r<4, kLight>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
     switch (R * 2 + (lean ? 1 : 0)) {
-        case 2: return launch_sweep_r<1, kFull>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
-        case 3: return launch_sweep_r<1, kLean>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
-        case 4: return launch_sweep_r<2, kFull>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
-        case 5: return launch_sweep_r<2, kLean>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
-        case 6: return launch_sweep_r<3, kFull>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
-        case 7: return launch_sweep_r<3, kLean>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
-        case 8: return launch_sweep_r<4, kFull>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
-        case 9: return launch_sweep_r<4, kLean>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
-        case 10: return launch_sweep_r<5, kFull>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
-        case 11: return launch_sweep_r<5, kLean>(u, n, ncols, hs, prog, prog_bytes, reverse, s);
+        case 2: return launch_sweep_r<1, kFull>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
+        case 3: return launch_sweep_r<1, kLean>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
+        case 4: return launch_sweep_r<2, kFull>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
+        case 5: return launch_sweep_r<2, kLean>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
+        case 6: return launch_sweep_r<3, kFull>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
+        case 7: return launch_sweep_r<3, kLean>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
+        case 8: return launch_sweep_r<4, kFull>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
+        case 9: return launch_sweep_r<4, kLean>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
+        case 10: return launch_sweep_r<5, kFull>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
+        case 11: return launch_sweep_r<5, kLean>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
         default: return cudaErrorInvalidValue;
     }
+}
+
+bool sweep_can_start_from_identity(int R, const DevSweep& hs) {
+    if (R != 4 || hs.dense_k != 0 || hs.fixed_one != 0) return false;
+    const unsigned char* const host = reinterpret_cast<const unsigned char*>(&hs);
+    const DevOp* const ops          = reinterpret_cast<const DevOp*>(host + sizeof(DevSweep));
+    for (int i = 0; i < hs.n_ops; ++i)
+        if (!is_common_handler(ops[i].handler)) return false;
+    return true;
 }
 
 size_t equiv_partials_doubles() { return (size_t)kEqBlocks * 16; }

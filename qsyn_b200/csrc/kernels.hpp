@@ -11,9 +11,11 @@ namespace qsx {
 // U[r, c] = (r == col0 + c) ? 1 : 0 over a 2^n x ncols shard (K2 of SURVEY 2.2)
 cudaError_t launch_set_identity(double2* u, int n, uint64_t col0, uint64_t ncols, cudaStream_t s);
 
+// may the sweep be launched with from_identity (the identity synthesised instead of read)?
+bool sweep_can_start_from_identity(int R, const DevSweep& hs);
 // one sweep (K1 a-e): `prog` is the device copy of a serialized DevSweep blob, `hs` its host copy
 cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, int R, const DevSweep& hs, const unsigned char* prog,
-                         size_t prog_bytes, bool reverse, cudaStream_t s);
+                         size_t prog_bytes, bool reverse, bool from_identity, uint64_t col0, cudaStream_t s);
 
 // fused equivalence reduction (K4): 8 compensated sums of a shard pair.
 // `partials` must hold equiv_partials_doubles() doubles of device scratch; out8 is device memory.

@@ -25,6 +25,9 @@ struct qsx_unitary {
     uint64_t col0     = 0;
     uint64_t ncols    = 0;
     double2* data     = nullptr;
+    // set_identity is lazy: the first sweep of the next gate stream synthesises the identity instead of
+    // reading it (saves one write and one read pass); anything else that looks at the data writes it first
+    bool     lazy_identity = false;
     uint64_t elems() const { return (1ull << n) * ncols; }
     uint64_t bytes() const { return elems() * 16ull; }
 };
@@ -108,6 +111,14 @@ int get_ctx(int device, DeviceCtx** out) {
     return QSX_OK;
 }
 
+int materialize(qsx_unitary* u, DeviceCtx* c) {
+    if (!u->lazy_identity) return QSX_OK;
+    QSX_CUDA(qsx::launch_set_identity(u->data, u->n, u->col0, u->ncols, c->stream));
+    u->lazy_identity = false;
+    return QSX_OK;
+}
+int materialize(const qsx_unitary* u, DeviceCtx* c) { return materialize(const_cast<qsx_unitary*>(u), c); }
+
 }  // namespace
 
 extern "C" {
@@ -164,9 +175,8 @@ int qsx_unitary_set_identity(qsx_unitary* u) {
     if (u == nullptr) return fail(QSX_ERR_BAD_ARG, "null unitary");
     DeviceCtx* c = nullptr;
     if (int rc = get_ctx(u->device, &c)) return rc;
-    // stream-ordered like every other operation on the unitary; host-visible results
-    // (download, equiv sums) synchronise on their own
-    QSX_CUDA(qsx::launch_set_identity(u->data, u->n, u->col0, u->ncols, c->stream));
+    (void)c;
+    u->lazy_identity = true;  // written by the first sweep of the next gate stream, or on first use
     return QSX_OK;
 }
 
@@ -175,6 +185,7 @@ int qsx_unitary_clone(const qsx_unitary* u, qsx_unitary** out) {
     if (int rc = qsx_unitary_create(u->device, u->n, u->col0, u->ncols, out)) return rc;
     DeviceCtx* c = nullptr;
     if (int rc = get_ctx(u->device, &c)) return rc;
+    if (int rc = materialize(u, c)) return rc;
     QSX_CUDA(cudaMemcpyAsync((*out)->data, u->data, u->bytes(), cudaMemcpyDeviceToDevice, c->stream));
     QSX_CUDA(cudaStreamSynchronize(c->stream));
     return QSX_OK;
@@ -195,6 +206,11 @@ int qsx_unitary_destroy(qsx_unitary* u) {
 
 int qsx_unitary_get_info(const qsx_unitary* u, qsx_unitary_info* info) {
     if (u == nullptr || info == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    if (u->lazy_identity) {  // the raw pointer is handed out: the data must be there
+        DeviceCtx* c = nullptr;
+        if (int rc = get_ctx(u->device, &c)) return rc;
+        if (int rc = materialize(u, c)) return rc;
+    }
     info->n_qubits = u->n;
     info->device   = u->device;
     info->col0     = u->col0;
@@ -210,6 +226,8 @@ int qsx_unitary_upload(qsx_unitary* u, uint64_t row0, uint64_t nrows, const doub
     if (row0 + nrows > (1ull << u->n)) return fail(QSX_ERR_BAD_ARG, "row range out of bounds");
     DeviceCtx* c = nullptr;
     if (int rc = get_ctx(u->device, &c)) return rc;
+    if (row0 == 0 && nrows == (1ull << u->n)) u->lazy_identity = false;  // everything is overwritten
+    if (int rc = materialize(u, c)) return rc;
     QSX_CUDA(cudaMemcpyAsync(u->data + row0 * u->ncols, host, nrows * u->ncols * 16ull, cudaMemcpyHostToDevice, c->stream));
     QSX_CUDA(cudaStreamSynchronize(c->stream));
     return QSX_OK;
@@ -220,6 +238,7 @@ int qsx_unitary_download(const qsx_unitary* u, uint64_t row0, uint64_t nrows, do
     if (row0 + nrows > (1ull << u->n)) return fail(QSX_ERR_BAD_ARG, "row range out of bounds");
     DeviceCtx* c = nullptr;
     if (int rc = get_ctx(u->device, &c)) return rc;
+    if (int rc = materialize(u, c)) return rc;
     QSX_CUDA(cudaMemcpyAsync(host, u->data + row0 * u->ncols, nrows * u->ncols * 16ull, cudaMemcpyDeviceToHost, c->stream));
     QSX_CUDA(cudaStreamSynchronize(c->stream));
     return QSX_OK;
@@ -299,10 +318,21 @@ int run_sweeps(qsx::Plan const& pl, qsx_unitary* u, DeviceCtx* c, unsigned char*
             }
         }
         qsx::DevSweep const& hs = *reinterpret_cast<qsx::DevSweep const*>(pl.blob.data() + pl.sweep_offset[s]);
+        bool from_identity = false;
+        if (u->lazy_identity) {
+            // an interpreted sweep that touches every tile can start from the synthesised identity
+            if (qsx::sweep_can_start_from_identity(pl.cfg.R, hs)) {
+                from_identity    = true;
+                u->lazy_identity = false;
+            } else {
+                if (int rc = materialize(u, c)) return rc;
+                ++launches;  // (the identity kernel counts as one of this run's launches)
+            }
+        }
         // serpentine: every other sweep walks the tiles backwards, so it starts with what the previous
         // sweep wrote last and is still in the 126 MB L2 (n = 12, memory-bound sweeps: 77.7 -> 71.6 us)
         QSX_CUDA(qsx::launch_sweep(u->data, u->n, u->ncols, pl.cfg.R, hs, dblob + pl.sweep_offset[s], pl.sweep_size[s],
-                                   (s & 1) != 0, c->stream));
+                                   (s & 1) != 0, from_identity, u->col0, c->stream));
         pending_bytes += pl.sweeps[s].alg_bytes;
         ++launches;
     }
@@ -418,6 +448,8 @@ int qsx_equiv_partial(const qsx_unitary* a, const qsx_unitary* b, double sums[8]
     if (a->device != b->device) return fail(QSX_ERR_SHAPE, "both shards must live on the same device");
     DeviceCtx* c = nullptr;
     if (int rc = get_ctx(a->device, &c)) return rc;
+    if (int rc = materialize(a, c)) return rc;
+    if (int rc = materialize(b, c)) return rc;
     double* const out8 = c->scratch + qsx::equiv_partials_doubles();
     QSX_CUDA(qsx::launch_equiv(a->data, b->data, a->elems(), c->scratch, out8, c->stream));
     QSX_CUDA(cudaMemcpyAsync(c->host8, out8, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -488,6 +520,7 @@ int qsx_unitary_adjoint_sharded(qsx_unitary* const* shards, int n_shards) {
     // everything queued on any shard must be done before a peer touches it
     for (int k = 0; k < n_shards; ++k) {
         QSX_CUDA(cudaSetDevice(shards[k]->device));
+        if (int rc = materialize(shards[k], ctx[(size_t)k])) return rc;
         QSX_CUDA(cudaStreamSynchronize(ctx[(size_t)k]->stream));
     }
     for (int i = 0; i < n_shards; ++i) {

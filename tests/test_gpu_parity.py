@@ -358,6 +358,50 @@ def test_async_apply_matches_sync_and_reuses_staging():
         u.close()
 
 
+def test_lazy_identity_is_invisible():
+    """qsx_unitary_set_identity only marks the shard; the first sweep of the next gate stream synthesises
+    the identity (sweep_kernel<.., IDENT>), every other consumer materialises it first."""
+    n = 9
+    dim = 2**n
+    eye = np.eye(dim)
+    qc, qc2 = _rand_circuit(n, 180, 77), _rand_circuit(n, 90, 78)
+    want, want2 = O.to_matrix_rowform(qc), O.to_matrix_rowform(qc2)
+    u = Q.Unitary(n)
+    # consumers of a never-written identity: clone, equiv, adjoint, partial upload
+    c = u.clone()
+    assert np.array_equal(c.download(), eye)
+    s = Q.Unitary(n).equiv_partial(Q.Unitary(n))
+    assert s[0] == dim and s[1] == 0 and s[2] == dim and s[3] == dim and s[4] == dim and s[6] == dim
+    a = Q.Unitary(n)
+    a.adjoint_inplace()
+    assert np.array_equal(a.download(), eye)
+    p = Q.Unitary(n)
+    rows = (np.arange(3 * dim).reshape(3, dim) + 1j).astype(np.complex128)
+    p.upload(rows, 5)
+    w = eye.astype(np.complex128)
+    w[5:8] = rows
+    assert np.array_equal(p.download(), w)
+    # a second gate stream continues from the data, not from the identity
+    u.apply(O.gate_stream(qc))
+    u.apply(O.gate_stream(qc2))
+    assert frob_rel(u.download(), want2 @ want) < TOL
+    # set_identity after gates, twice, then gates; and an empty stream in between
+    for opt in (None, Q.PlanOptions(reg_qubits=3), Q.PlanOptions(dense_block=4), Q.PlanOptions(fuse=0, tile_qubits=6)):
+        u.set_identity()
+        u.set_identity()
+        u.apply([], opt)
+        st = u.apply(O.gate_stream(qc), opt)
+        assert st.launches > 0
+        assert frob_rel(u.download(), want) < TOL
+    u.set_identity()
+    assert np.array_equal(u.download(), eye)
+    # column shard: the synthesised identity sits at global column col0 + c
+    for col0, ncols in ((dim // 2, dim // 4), (dim - 8, 8), (3, 1)):
+        sh = Q.Unitary(n, 0, col0, ncols)
+        sh.apply(O.gate_stream(qc))
+        assert frob_rel(sh.download(), want[:, col0:col0 + ncols]) < TOL
+
+
 def _device_fuzz(seed, seconds, max_cases=10**9):
     import time
     rng = np.random.default_rng(seed)
