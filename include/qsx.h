@@ -115,7 +115,12 @@ typedef struct qsx_plan_options {
     int32_t stage_search;  /* 1: choose each stage's register bits by trying every R-subset of the tile bits;
                               < 0: first come, first served; 0 (default): on when n >= 13 (costs ~2 ms of host
                               time per 2000 gates, pays once a sweep takes milliseconds)                        */
-    int32_t reserved[2];
+    int32_t l2_block_mib;  /* column blocking through the L2: every sweep of the plan is run on a block of columns of
+                              about this many MiB before the next block is touched, so only the first sweep reads a
+                              block from HBM and only the last write has to reach it.  0 (default): 64 MiB when the
+                              cost model says the plan is memory-bound (a few micro-ops per sweep at most);
+                              < 0: never; > 0: always, with this block size                                    */
+    int32_t reserved[1];
 } qsx_plan_options;
 
 typedef struct qsx_plan_stats {

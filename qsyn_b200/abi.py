@@ -56,7 +56,7 @@ class PlanOptions(C.Structure):
                 ("lookahead", C.c_int32), ("dense_block", C.c_int32), ("no_perm_folding", C.c_int32), ("min_tail_ops", C.c_int32),
                 ("search", C.c_int32), ("no_diag_conjugation", C.c_int32),
                 ("no_1q_fusion", C.c_int32), ("stage_search", C.c_int32),
-                ("reserved", C.c_int32 * 2)]
+                ("l2_block_mib", C.c_int32), ("reserved", C.c_int32 * 1)]
 
     def __init__(self, fuse: int = 1, **kw):
         super().__init__()

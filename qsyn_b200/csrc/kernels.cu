@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(1 << mode_threads_log2(R, MODE), mode_min_ctas
 }
 
 template <int R, int MODE, bool IDENT = false>
-cudaError_t launch_sweep_r(double2* u, int n, uint64_t ncols, const DevSweep& hs, const unsigned char* prog,
+cudaError_t launch_sweep_r(double2* u, int n, uint64_t ncols, uint64_t grid_ncols, const DevSweep& hs, const unsigned char* prog,
                            size_t prog_bytes, uint32_t flags, uint32_t col0, cudaStream_t s) {
     (void)n;
     int const m        = hs.m;
@@ -573,7 +573,9 @@ cudaError_t launch_sweep_r(double2* u, int n, uint64_t ncols, const DevSweep& hs
     if (prog_bytes % 16 != 0 || smem > 200 * 1024) return cudaErrorInvalidValue;
     int log2_ncols     = 0;
     while ((1ull << log2_ncols) < ncols) ++log2_ncols;
-    int const log2_ncb = log2_ncols - hs.log2w;
+    int log2_gcols     = 0;  // the grid covers grid_ncols columns starting at u (one L2 block, or the whole shard)
+    while ((1ull << log2_gcols) < grid_ncols) ++log2_gcols;
+    int const log2_ncb = log2_gcols - hs.log2w;
     uint64_t const nblocks = 1ull << (log2_ncb + hs.n_outer);
     if (threads < 1 || threads > (1 << mode_threads_log2(R, MODE)) || nblocks > 0x7fffffffull)
         return cudaErrorInvalidConfiguration;
@@ -939,12 +941,15 @@ cudaError_t launch_set_identity(double2* u, int n, uint64_t col0, uint64_t ncols
     return cudaGetLastError();
 }
 
-cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, int R, const DevSweep& hs, const unsigned char* prog,
-                         size_t prog_bytes, bool reverse, bool from_identity, uint64_t col0, cudaStream_t s) {
+cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, uint64_t grid_ncols, int R, const DevSweep& hs,
+                         const unsigned char* prog, size_t prog_bytes, bool reverse, bool from_identity, uint64_t col0,
+                         cudaStream_t s) {
+    if (grid_ncols == 0 || grid_ncols > ncols || (grid_ncols & (grid_ncols - 1)) != 0 || grid_ncols < (1ull << hs.log2w))
+        return cudaErrorInvalidValue;
     uint32_t const flags = (reverse ? 1u : 0u) | (from_identity ? 2u : 0u);
     uint32_t const c0    = (uint32_t)col0;
     if (hs.dense_k != 0) {
-        if (from_identity) return cudaErrorInvalidValue;  // (the runtime materialises the identity first)
+        if (from_identity || grid_ncols != ncols) return cudaErrorInvalidValue;  // (the runtime materialises the identity first)
         switch (hs.dense_k) {
             case 3: return launch_dense_k<3>(u, ncols, hs, prog, s);
             case 4: return launch_dense_k<4>(u, ncols, hs, prog, s);
@@ -964,21 +969,21 @@ cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, int R, const DevSwee
     }
     if (from_identity) {  // instantiated for the default register count only (sweep_can_start_from_identity)
         if (R != 4 || !lean) return cudaErrorInvalidValue;
-        return light ? launch_sweep_r<4, kLight, true>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s)
-                     : launch_sweep_r<4, kLean, true>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
+        return light ? launch_sweep_r<4, kLight, true>(u, n, ncols, grid_ncols, hs, prog, prog_bytes, flags, c0, s)
+                     : launch_sweep_r<4, kLean, true>(u, n, ncols, grid_ncols, hs, prog, prog_bytes, flags, c0, s);
     }
-    if (lean && light) return launch_sweep_r<4, kLight>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
+    if (lean && light) return launch_sweep_r<4, kLight>(u, n, ncols, grid_ncols, hs, prog, prog_bytes, flags, c0, s);
     switch (R * 2 + (lean ? 1 : 0)) {
-        case 2: return launch_sweep_r<1, kFull>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
-        case 3: return launch_sweep_r<1, kLean>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
-        case 4: return launch_sweep_r<2, kFull>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
-        case 5: return launch_sweep_r<2, kLean>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
-        case 6: return launch_sweep_r<3, kFull>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
-        case 7: return launch_sweep_r<3, kLean>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
-        case 8: return launch_sweep_r<4, kFull>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
-        case 9: return launch_sweep_r<4, kLean>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
-        case 10: return launch_sweep_r<5, kFull>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
-        case 11: return launch_sweep_r<5, kLean>(u, n, ncols, hs, prog, prog_bytes, flags, c0, s);
+        case 2: return launch_sweep_r<1, kFull>(u, n, ncols, grid_ncols, hs, prog, prog_bytes, flags, c0, s);
+        case 3: return launch_sweep_r<1, kLean>(u, n, ncols, grid_ncols, hs, prog, prog_bytes, flags, c0, s);
+        case 4: return launch_sweep_r<2, kFull>(u, n, ncols, grid_ncols, hs, prog, prog_bytes, flags, c0, s);
+        case 5: return launch_sweep_r<2, kLean>(u, n, ncols, grid_ncols, hs, prog, prog_bytes, flags, c0, s);
+        case 6: return launch_sweep_r<3, kFull>(u, n, ncols, grid_ncols, hs, prog, prog_bytes, flags, c0, s);
+        case 7: return launch_sweep_r<3, kLean>(u, n, ncols, grid_ncols, hs, prog, prog_bytes, flags, c0, s);
+        case 8: return launch_sweep_r<4, kFull>(u, n, ncols, grid_ncols, hs, prog, prog_bytes, flags, c0, s);
+        case 9: return launch_sweep_r<4, kLean>(u, n, ncols, grid_ncols, hs, prog, prog_bytes, flags, c0, s);
+        case 10: return launch_sweep_r<5, kFull>(u, n, ncols, grid_ncols, hs, prog, prog_bytes, flags, c0, s);
+        case 11: return launch_sweep_r<5, kLean>(u, n, ncols, grid_ncols, hs, prog, prog_bytes, flags, c0, s);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -14,8 +14,11 @@ cudaError_t launch_set_identity(double2* u, int n, uint64_t col0, uint64_t ncols
 // may the sweep be launched with from_identity (the identity synthesised instead of read)?
 bool sweep_can_start_from_identity(int R, const DevSweep& hs);
 // one sweep (K1 a-e): `prog` is the device copy of a serialized DevSweep blob, `hs` its host copy
-cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, int R, const DevSweep& hs, const unsigned char* prog,
-                         size_t prog_bytes, bool reverse, bool from_identity, uint64_t col0, cudaStream_t s);
+// `u` points at the first column of the block of `grid_ncols` columns to process (a power of two, at most
+// `ncols` = the row stride of the shard); col0 is the global column index of that first column
+cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, uint64_t grid_ncols, int R, const DevSweep& hs,
+                         const unsigned char* prog, size_t prog_bytes, bool reverse, bool from_identity, uint64_t col0,
+                         cudaStream_t s);
 
 // fused equivalence reduction (K4): 8 compensated sums of a shard pair.
 // `partials` must hold equiv_partials_doubles() doubles of device scratch; out8 is device memory.

@@ -210,6 +210,39 @@ void serialize(Plan& plan) {
 
 }  // namespace
 
+// Column blocking through the L2 (qsx_plan_options.l2_block_mib).  Columns are independent, so the runtime may
+// run ALL sweeps on one block of columns before it touches the next block: with a block that fits the 126 MB L2
+// only the first sweep reads it from HBM and only the final state has to be written back.  That pays when the
+// sweeps are memory-bound; a compute-bound plan only loses (more launches, shorter grids), so the default is
+// decided with the measured model of DESIGN.md 3.1: per sweep, 32 + 23 (stages - 1) + ~3.6 per micro-op
+// against a memory floor of 90 (us at n = 12; both sides scale with the shard).
+static void choose_l2_blocking(Plan& plan, int32_t opt_mib) {
+    PlanConfig& cfg    = plan.cfg;
+    cfg.l2_block_mib   = opt_mib;
+    cfg.block_cols     = 0;
+    if (opt_mib < 0 || cfg.dense_k != 0 || plan.sweeps.empty()) return;
+    if (opt_mib == 0) {
+        if (plan.sweeps.size() < 2) return;  // nothing is read twice
+        double compute = 0.0, memory = 0.0;
+        for (PlannedSweep const& sw : plan.sweeps) {
+            double c = 32.0 + 23.0 * ((double)sw.stages.size() - 1.0);
+            for (PlannedStage const& st : sw.stages) c += 3.6 * (double)st.uops.size();
+            double const share = sw.alg_bytes / (32.0 * std::ldexp(1.0, cfg.n) * (double)cfg.ncols);  // skipped tiles
+            compute += c * share;
+            memory += 90.0 * share;
+        }
+        // measured (profiles/r1_l2_block_probe.jsonl): 2.5 micro-ops per sweep -11..-18 %, 5 per sweep +-2 %, 20 per sweep +5..+17 %
+        if (compute > 0.5 * memory) return;
+    }
+    // 64 MiB: half of the 126 MB L2; 32 MiB blocks are grids of 1.4 waves and measured slower than no blocking
+    double const mib        = opt_mib > 0 ? (double)opt_mib : 64.0;
+    double const col_bytes  = 16.0 * std::ldexp(1.0, cfg.n);
+    uint64_t const w        = 1ull << cfg.log2w;
+    uint64_t cols           = w;
+    while (cols * 2 <= cfg.ncols && (double)(cols * 2) * col_bytes <= mib * 1048576.0) cols *= 2;
+    if (cols < cfg.ncols) cfg.block_cols = cols;
+}
+
 int build_plan(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gates, const qsx_plan_options* opt,
                Plan& plan, std::string& msg) {
     auto const t_begin = std::chrono::steady_clock::now();
@@ -294,6 +327,7 @@ int build_plan(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gat
     else
         schedule(plan);
     plan.stats.n_sweeps = plan.sweeps.size();
+    choose_l2_blocking(plan, o.l2_block_mib);
     serialize(plan);
     plan.stats.plan_host_ms =
         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
@@ -305,7 +339,7 @@ std::string dump_plan_json(const Plan& plan) {
     std::ostringstream os;
     os.precision(17);
     os << "{\"n\":" << plan.cfg.n << ",\"ncols\":" << plan.cfg.ncols << ",\"R\":" << plan.cfg.R
-       << ",\"log2w\":" << plan.cfg.log2w << ",\"m_cap\":" << plan.cfg.m_cap << ",\"sweeps\":[";
+       << ",\"log2w\":" << plan.cfg.log2w << ",\"m_cap\":" << plan.cfg.m_cap << ",\"block_cols\":" << plan.cfg.block_cols << ",\"sweeps\":[";
     for (size_t s = 0; s < plan.sweeps.size(); ++s) {
         PlannedSweep const& sw = plan.sweeps[s];
         os << (s ? "," : "") << "{\"tile_bits\":[";

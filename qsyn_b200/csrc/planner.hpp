@@ -77,6 +77,8 @@ struct PlanConfig {
     bool conjugate_diagonals = true;  // carry pending diagonal tables through in-register permutations
     int  dense_k = 0;  // >= 3: fold the gate stream into dense k-qubit blocks (FP64 tensor pipe)  // never swap registers: an X-type op that cannot be hoisted ends the stage
     double snap_tol = 1e-15;
+    int  l2_block_mib = 0;        // option as given: 0 auto, < 0 off, > 0 forced
+    uint64_t block_cols = 0;      // columns per L2 block (0: the sweeps run over the whole shard)
 };
 
 struct Plan {

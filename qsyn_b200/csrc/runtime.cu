@@ -302,39 +302,52 @@ int run_sweeps(qsx::Plan const& pl, qsx_unitary* u, DeviceCtx* c, unsigned char*
     bool const async = (flags & QSX_RUN_ASYNC) != 0;
     if (!async) QSX_CUDA(cudaEventRecord(c->ev0, c->stream));
     uint64_t launches = 0;
+    // Column blocking through the L2 (plan option l2_block_mib): all sweeps run on one block of columns before
+    // the next block is touched.  Columns are independent, so any order of (block, sweep) pairs that keeps the
+    // sweep order within a block is the same computation.
+    uint64_t const block_cols = (pl.cfg.block_cols != 0 && pl.cfg.block_cols < u->ncols) ? pl.cfg.block_cols : u->ncols;
+    bool identity_per_block   = false;
+    if (u->lazy_identity && !pl.sweeps.empty()) {
+        // an interpreted sweep that touches every tile can start from the synthesised identity
+        qsx::DevSweep const& first = *reinterpret_cast<qsx::DevSweep const*>(pl.blob.data() + pl.sweep_offset[0]);
+        if (qsx::sweep_can_start_from_identity(pl.cfg.R, first)) {
+            identity_per_block = true;
+            u->lazy_identity   = false;
+        } else {
+            if (int rc = materialize(u, c)) return rc;
+            ++launches;  // (the identity kernel counts as one of this run's launches)
+        }
+    }
     // with a stop callback, drain the stream every few sweeps so SIGINT is honoured promptly
     // (the reference polls stop_requested() once per gate, qcir_to_tensor.cpp:174-177)
     double pending_bytes = 0.0;
-    for (size_t s = 0; s < pl.sweeps.size(); ++s) {
-        if (should_stop != nullptr) {
-            if (pending_bytes > 64e9) {  // ~10 ms of HBM traffic
-                QSX_CUDA(cudaStreamSynchronize(c->stream));
-                pending_bytes = 0.0;
+    double const share   = (double)block_cols / (double)u->ncols;
+    for (uint64_t cb0 = 0; cb0 < u->ncols; cb0 += block_cols) {
+        for (size_t s = 0; s < pl.sweeps.size(); ++s) {
+            if (should_stop != nullptr) {
+                if (pending_bytes > 64e9) {  // ~10 ms of HBM traffic
+                    QSX_CUDA(cudaStreamSynchronize(c->stream));
+                    pending_bytes = 0.0;
+                }
+                if (should_stop(stop_arg)) {
+                    cudaStreamSynchronize(c->stream);
+                    if (stats != nullptr) stats->launches = launches;
+                    if (identity_per_block) {
+                        // blocks that were not reached yet hold no data: leave a defined state behind
+                        u->lazy_identity = true;
+                    }
+                    return fail(QSX_ERR_INTERRUPTED, "interrupted by the stop callback");
+                }
             }
-            if (should_stop(stop_arg)) {
-                cudaStreamSynchronize(c->stream);
-                if (stats != nullptr) stats->launches = launches;
-                return fail(QSX_ERR_INTERRUPTED, "interrupted by the stop callback");
-            }
+            qsx::DevSweep const& hs = *reinterpret_cast<qsx::DevSweep const*>(pl.blob.data() + pl.sweep_offset[s]);
+            // serpentine: every other sweep walks the tiles backwards, so it starts with what the previous
+            // sweep wrote last and is still in the 126 MB L2 (n = 12, memory-bound sweeps: 77.7 -> 71.6 us)
+            QSX_CUDA(qsx::launch_sweep(u->data + cb0, u->n, u->ncols, block_cols, pl.cfg.R, hs, dblob + pl.sweep_offset[s],
+                                       pl.sweep_size[s], (s & 1) != 0, identity_per_block && s == 0, u->col0 + cb0,
+                                       c->stream));
+            pending_bytes += pl.sweeps[s].alg_bytes * share;
+            ++launches;
         }
-        qsx::DevSweep const& hs = *reinterpret_cast<qsx::DevSweep const*>(pl.blob.data() + pl.sweep_offset[s]);
-        bool from_identity = false;
-        if (u->lazy_identity) {
-            // an interpreted sweep that touches every tile can start from the synthesised identity
-            if (qsx::sweep_can_start_from_identity(pl.cfg.R, hs)) {
-                from_identity    = true;
-                u->lazy_identity = false;
-            } else {
-                if (int rc = materialize(u, c)) return rc;
-                ++launches;  // (the identity kernel counts as one of this run's launches)
-            }
-        }
-        // serpentine: every other sweep walks the tiles backwards, so it starts with what the previous
-        // sweep wrote last and is still in the 126 MB L2 (n = 12, memory-bound sweeps: 77.7 -> 71.6 us)
-        QSX_CUDA(qsx::launch_sweep(u->data, u->n, u->ncols, pl.cfg.R, hs, dblob + pl.sweep_offset[s], pl.sweep_size[s],
-                                   (s & 1) != 0, from_identity, u->col0, c->stream));
-        pending_bytes += pl.sweeps[s].alg_bytes;
-        ++launches;
     }
     if (stats != nullptr) stats->launches = launches;
     if (!async) {

@@ -159,6 +159,26 @@ def test_qft_needs_few_sweeps():
     assert st.n_gates == 105 and st.n_sweeps <= 2
 
 
+def test_l2_column_blocking_decision():
+    """qsx_plan_options.l2_block_mib: off / forced sizes are powers of two between the tile width and the
+    shard; the default only blocks plans the cost model calls memory-bound (few micro-ops per sweep)."""
+    n = 12
+    qc = _rand_circuit(n, 300, 5)
+    gs = O.gate_stream(qc)
+    assert Q.Plan(n, 2**n, gs).dump()["block_cols"] == 0                      # compute-bound: not blocked
+    assert Q.Plan(n, 2**n, gs, Q.PlanOptions(l2_block_mib=-1)).dump()["block_cols"] == 0
+    col_bytes = 16 * 2**n
+    for mib in (1, 2, 32, 64):
+        bc = Q.Plan(n, 2**n, gs, Q.PlanOptions(l2_block_mib=mib)).dump()["block_cols"]
+        assert bc == min(mib * 2**20 // col_bytes, 2**n) % 2**n               # (== shard: reported as 0)
+    assert Q.Plan(n, 2**n, gs, Q.PlanOptions(l2_block_mib=4096)).dump()["block_cols"] == 0
+    assert Q.Plan(n, 8, gs, Q.PlanOptions(l2_block_mib=1)).dump()["block_cols"] == 0   # one tile width: nothing to split
+    assert Q.Plan(n, 2**n, gs, Q.PlanOptions(l2_block_mib=1, dense_block=4)).dump()["block_cols"] == 0
+    # one gate per sweep (fuse = 0) is the memory-bound extreme: blocked by default
+    assert Q.Plan(n, 2**n, gs, Q.PlanOptions(fuse=0)).dump()["block_cols"] == 64 * 2**20 // col_bytes
+    assert Q.Plan(n, 2**n, gs[:1], Q.PlanOptions(fuse=0)).dump()["block_cols"] == 0    # a single sweep reads nothing twice
+
+
 @pytest.mark.parametrize("case", ["t_x_t_x", "rz_small", "qft3crz", "zero_sum"])
 def test_equiv_finish_matches_oracle(case, goldens):
     if case == "t_x_t_x":

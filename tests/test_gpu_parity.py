@@ -402,6 +402,40 @@ def test_lazy_identity_is_invisible():
         assert frob_rel(sh.download(), want[:, col0:col0 + ncols]) < TOL
 
 
+@pytest.mark.parametrize("mib_per_n", [{10: 1}, {10: 4}])
+def test_l2_column_blocking_is_the_same_computation(mib_per_n):
+    """l2_block_mib runs all sweeps on one block of columns before the next: bit-identical to the unblocked run
+    (same tiles, same programs; only the order of (block, sweep) pairs changes), also from a lazy identity,
+    on a column shard, and for a second gate stream on existing data."""
+    qc10, qc10b = O.qcir_from_qasm_text(O.random_clifford_t_qasm(10, 500, 5)), _rand_circuit(10, 120, 8, extra=True)
+    n = 10
+    base = Q.Unitary(n)
+    base.apply(O.gate_stream(qc10), Q.PlanOptions(l2_block_mib=-1))
+    base.apply(O.gate_stream(qc10b), Q.PlanOptions(l2_block_mib=-1))
+    want = base.download()
+    assert frob_rel(want, O.to_matrix_rowform(qc10b) @ O.to_matrix_rowform(qc10)) < TOL
+    for opt in (Q.PlanOptions(l2_block_mib=mib_per_n[10]), Q.PlanOptions(l2_block_mib=mib_per_n[10], fuse=0)):
+        u = Q.Unitary(n)
+        plan = Q.Plan(n, 2**n, O.gate_stream(qc10), opt)
+        assert plan.dump()["block_cols"] == mib_per_n[10] * 2**20 // (16 * 2**n)
+        st = plan.run(u)
+        assert 0 <= st.launches - plan.stats().n_sweeps * (2**n // plan.dump()["block_cols"]) <= 1
+        u.apply(O.gate_stream(qc10b), opt)
+        got = u.download()
+        if opt.fuse:
+            assert np.array_equal(got.view(np.float64), want.view(np.float64))
+        else:
+            assert frob_rel(got, want) < TOL
+        u.close()
+    # column shard (col0 != 0) with blocks of one tile width, reg_qubits != 4 (identity materialised first)
+    col0, ncols = 256, 256
+    for opt in (Q.PlanOptions(l2_block_mib=1), Q.PlanOptions(l2_block_mib=1, reg_qubits=3, tile_qubits=7)):
+        sh = Q.Unitary(n, 0, col0, ncols)
+        sh.apply(O.gate_stream(qc10), opt)
+        assert frob_rel(sh.download(), O.to_matrix_rowform(qc10)[:, col0:col0 + ncols]) < TOL
+        sh.close()
+
+
 def _device_fuzz(seed, seconds, max_cases=10**9):
     import time
     rng = np.random.default_rng(seed)
@@ -414,7 +448,8 @@ def _device_fuzz(seed, seconds, max_cases=10**9):
                     log2_tile_cols=int(rng.choice([-1, 1, 2, 3, 4])), max_ops_per_sweep=int(rng.choice([5, 17, 96, 300])),
                     min_tail_ops=int(rng.choice([-1, 8])), search=int(rng.choice([-1, 2])), stage_search=int(rng.choice([-1, 1])),
                     no_1q_fusion=int(rng.integers(2)), no_diag_conjugation=int(rng.integers(2)),
-                    no_perm_folding=int(rng.integers(3)), snap_tol=float(rng.choice([1e-15, -1.0])))
+                    no_perm_folding=int(rng.integers(3)), snap_tol=float(rng.choice([1e-15, -1.0])),
+                    l2_block_mib=int(rng.choice([-1, 0, 1, 1, 2])))
         shards = int(rng.choice([1, 1, 2, 4])) if n >= 3 else 1
         ncols = 2**n // shards
         k = int(rng.integers(shards))
