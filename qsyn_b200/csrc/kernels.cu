@@ -386,10 +386,15 @@ __global__ void __launch_bounds__(1 << mode_threads_log2(R, MODE), mode_min_ctas
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // the sweep program (a few KB, read by every thread for every op) is staged in shared
     // memory once per CTA; the tile follows it
+    // (asynchronous copies: every 16-byte piece is in flight at once, ONE L2 round trip per CTA whatever the
+    // program size; a register-staged copy loop was compiled to one dependent LDG -> STS round trip per iteration
+    // for the usual 2..3 iterations, plus an integer division for its trip count)
     {
-        const uint4* const src = reinterpret_cast<const uint4*>(gprog);
-        uint4* const dst       = reinterpret_cast<uint4*>(smem_raw);
-        for (uint32_t i = threadIdx.x; i < prog_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+        uint32_t const dst = (uint32_t)__cvta_generic_to_shared(smem_raw);
+#pragma unroll 1
+        for (uint32_t off = threadIdx.x * 16u; off < prog_bytes; off += blockDim.x * 16u)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + off), "l"(gprog + off) : "memory");
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     const unsigned char* const prog = smem_raw;
