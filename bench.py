@@ -301,7 +301,7 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit_result(out)
 
 
 # FP64-pipe instructions per element of every micro-op kind (kernels.cu handlers): h = DMUL + 2 DFMA
@@ -416,7 +416,7 @@ def run_reference(args):
         return
     n, gen, g_total, seed, desc = WORKLOADS[args.workload]
     if n > 14:
-        print(json.dumps({"impl": "reference", "unavailable": f"the CPU tensordot path needs ~3x16x4^{n} B RAM and minutes per gate at n={n}"}))
+        emit_result({"impl": "reference", "unavailable": f"the CPU tensordot path needs ~3x16x4^{n} B RAM and minutes per gate at n={n}"})
         return
     per_gate = 0.18 * 4.0 ** (n - 12)
     g = min(g_total, max(2 if n > 13 else 4, int(8.0 / per_gate)))
@@ -441,7 +441,7 @@ def run_reference(args):
                          "sample": f"{g} of {g_total} gates per step; restatement of the reference algorithm, not the reference binary"},
         "e2e": {"value": round(value, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    emit_result(out)
 
 
 def main():
@@ -460,10 +460,29 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 on their own (NCCL prints its version
+    # banner there) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for line in _RESULT_LINES:
+        print(line, flush=True)
+
+
+_RESULT_LINES = []
+
+
+def emit_result(obj):
+    _RESULT_LINES.append(json.dumps(obj))
 
 
 if __name__ == "__main__":
