@@ -378,12 +378,61 @@ __device__ __forceinline__ void permute_rows(uint32_t (&rows)[R + 1], const DevP
     }
 }
 
+// What the first stage's global load needs, passed BY VALUE (kernel parameters live in the constant bank: no
+// memory latency), so that a CTA's tile loads are in flight while its program is still being staged.  The
+// interpreter is latency-bound per CTA; this takes the program's L2 round trip off the path to the first load.
+constexpr int kEarlyPerms = 8, kEarlyRuns = 4;
+struct FirstLoad {
+    uint32_t fixed_one;
+    int32_t  log2w;
+    int32_t  n_pre;                     // folded permutation steps of the load boundary; < 0: take the staged path
+    // bit deposits as runs of consecutive bits: row |= (x & mask[k]) << shift[k]; x = tile row index / thread row index
+    uint32_t omask[kEarlyRuns], oshift[kEarlyRuns];
+    uint32_t tmask[kEarlyRuns], tshift[kEarlyRuns];
+    int32_t  rg[kMaxRegBits];
+    // the steps in the order the LOAD side applies them (reversed list), global row bits, no outer condition
+    uint32_t pre_cml[kEarlyPerms], pre_tml[kEarlyPerms];
+};
+
 // IDENT: the unitary is (lazily) the identity -- the first stage synthesises it instead of reading it.
 template <int R, int MODE, bool IDENT>
 __global__ void __launch_bounds__(1 << mode_threads_log2(R, MODE), mode_min_ctas(R, MODE))
     sweep_kernel(double2* __restrict__ u, const unsigned char* __restrict__ gprog, uint32_t prog_bytes, int log2_ncols,
-                 int log2_ncb, uint32_t flags, uint32_t col0) {
+                 int log2_ncb, uint32_t flags, uint32_t col0, const __grid_constant__ FirstLoad fl) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 e[1 << R];
+    bool const early = !IDENT && fl.n_pre >= 0;  // uniform
+    if (early) {
+        // the first stage's loads, addressed from the constant bank alone
+        uint32_t const cw0   = threadIdx.x & ((1u << fl.log2w) - 1u);
+        uint32_t const trow0 = threadIdx.x >> fl.log2w;
+        uint64_t const t64   = (flags & 1u) ? (uint64_t)(gridDim.x - 1u - blockIdx.x) : (uint64_t)blockIdx.x;
+        uint64_t const cb0   = t64 & ((1ull << log2_ncb) - 1ull);
+        uint32_t const rc0   = (uint32_t)(t64 >> log2_ncb);
+        uint32_t g0          = fl.fixed_one;
+#pragma unroll
+        for (int k = 0; k < kEarlyRuns; ++k) g0 |= ((rc0 & fl.omask[k]) << fl.oshift[k]) | ((trow0 & fl.tmask[k]) << fl.tshift[k]);
+        uint32_t rows[R + 1];
+        rows[0] = g0;
+#pragma unroll
+        for (int j = 0; j < R; ++j) rows[1 + j] = g0 | (1u << fl.rg[j]);
+#pragma unroll
+        for (int k = 0; k < kEarlyPerms; ++k) {
+            if (k >= fl.n_pre) break;  // uniform
+            uint32_t const cml = fl.pre_cml[k], tml = fl.pre_tml[k];
+#pragma unroll
+            for (int v = 0; v <= R; ++v) rows[v] ^= ((rows[v] & cml) == cml) ? tml : 0u;
+        }
+        const double2* const gp = u + ((cb0 << fl.log2w) + cw0);
+#pragma unroll
+        for (int i = 0; i < (1 << R); ++i) {
+            uint32_t r = rows[0];
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+                if ((i >> j) & 1) r ^= rows[1 + j] ^ rows[0];
+            e[i] = __ldcg(gp + ((size_t)r << log2_ncols));
+        }
+    }
     // the sweep program (a few KB, read by every thread for every op) is staged in shared
     // memory once per CTA; the tile follows it
     // (asynchronous copies: every 16-byte piece is in flight at once, ONE L2 round trip per CTA whatever the
@@ -425,8 +474,6 @@ __global__ void __launch_bounds__(1 << mode_threads_log2(R, MODE), mode_min_ctas
     }
     uint64_t const col = (cb << log2w) + cw;
 
-    double2 e[1 << R];
-
     for (int s = 0; s < n_stages; ++s) {
         const DevStage* const st = stages + s;
         // this thread's rows: tile-local index (register bits = 0) and the global row it maps to
@@ -450,7 +497,9 @@ __global__ void __launch_bounds__(1 << mode_threads_log2(R, MODE), mode_min_ctas
             rg[j] = st->rg[j];
         }
 
-        if (s == 0) {
+        if (s == 0 && early) {
+            // (already in flight since before the program was staged)
+        } else if (s == 0) {
             // global load; X-type ops scheduled before the first register op are folded into the addresses
             uint32_t gb = grow, gc[R];
             int const pb = st->pre_begin, pe = st->pre_end;
@@ -593,7 +642,45 @@ cudaError_t launch_sweep_r(double2* u, int n, uint64_t ncols, uint64_t grid_ncol
         if (rc != cudaSuccess) return rc;
         attr_set[dev] = true;
     }
-    sweep_kernel<R, MODE, IDENT><<<(unsigned)nblocks, threads, smem, s>>>(u, prog, (uint32_t)prog_bytes, log2_ncols, log2_ncb, flags, col0);
+    FirstLoad fl{};
+    fl.n_pre = -1;
+    if (!IDENT && hs.n_stages >= 1) {
+        const unsigned char* const host = reinterpret_cast<const unsigned char*>(&hs);
+        const DevOp* const ops          = reinterpret_cast<const DevOp*>(host + sizeof(DevSweep));
+        const DevStage* const st0       = reinterpret_cast<const DevStage*>(ops + hs.n_ops);
+        const DevPerm* const perms      = reinterpret_cast<const DevPerm*>(st0 + hs.n_stages);
+        int const np                    = st0->pre_end - st0->pre_begin;
+        bool ok                         = np >= 0 && np <= kEarlyPerms && st0->n_t >= 0 && st0->n_t <= kMaxTileBits;
+        for (int k = 0; ok && k < np; ++k) {
+            DevPerm const& pm = perms[st0->pre_end - 1 - k];  // load side: reversed
+            ok                = pm.cmo == 0;
+            fl.pre_cml[k] = pm.cml, fl.pre_tml[k] = pm.tml;
+        }
+        // source bit k -> row bit pos[k] (ascending) as runs of equal shift
+        auto runs = [](const int32_t* pos, int count, uint32_t* mask, uint32_t* shift) {
+            int n_runs = 0;
+            for (int k = 0; k < count; ++k) {
+                if (pos[k] < k || pos[k] >= 32) return false;
+                uint32_t const sh = (uint32_t)(pos[k] - k);
+                if (n_runs == 0 || shift[n_runs - 1] != sh) {
+                    if (n_runs == kEarlyRuns) return false;
+                    mask[n_runs] = 0u, shift[n_runs] = sh, ++n_runs;
+                }
+                mask[n_runs - 1] |= 1u << k;
+            }
+            return true;
+        };
+        ok = ok && hs.n_outer >= 0 && hs.n_outer <= kMaxRowBits && runs(hs.outer, hs.n_outer, fl.omask, fl.oshift) &&
+             runs(st0->tg, st0->n_t, fl.tmask, fl.tshift);
+        if (ok) {
+            fl.fixed_one = hs.fixed_one, fl.log2w = hs.log2w, fl.n_pre = np;
+            for (int k = 0; k < kMaxRegBits; ++k) fl.rg[k] = st0->rg[k];
+        }
+    }
+#ifdef QSX_NO_EARLY_LOAD
+    fl.n_pre = -1;
+#endif
+    sweep_kernel<R, MODE, IDENT><<<(unsigned)nblocks, threads, smem, s>>>(u, prog, (uint32_t)prog_bytes, log2_ncols, log2_ncb, flags, col0, fl);
     return cudaGetLastError();
 }
 
