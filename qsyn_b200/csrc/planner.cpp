@@ -298,6 +298,7 @@ int build_plan(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gat
     plan.stats          = qsx_plan_stats{};
     plan.stats.n_gates  = n_gates;
     double const shard_elems = std::ldexp(1.0, n_qubits) * (double)ncols;
+    plan.ops.reserve(n_gates + n_gates / 8);
     for (size_t i = 0; i < n_gates; ++i) {
         size_t const before = plan.ops.size();
         int const rc        = lower_gate(n_qubits, gates[i], (int)i, cfg.snap_tol, plan.ops, msg);

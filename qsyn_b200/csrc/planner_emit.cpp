@@ -53,6 +53,8 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
     // per-thread scalars commute with every register op of the stage: they are all collected
     // into ONE micro-op at the end of the stage
     std::vector<MicroOp> scalars;
+    scalars.reserve(16);
+    st.uops.reserve(st.ops.size() + 8);
 
     // The diagonal ops seen so far and not yet applied, multiplied together: one table over the
     // register index per distinct thread-level condition.  A table stays live across
@@ -63,20 +65,23 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
     // A group is kept factored: value(i) = tab[i] * prod_j f[j][bit j of i].  Single-bit diagonals
     // (z, s, t, rz, p ...) go to the factors, so that before an op on bit j only the factor of j has
     // to be applied (one phase, K_PHJ) or absorbed (general 2x2), while the rest stays live.
+    // (fixed-size storage: a Group is copied, permuted and flushed for almost every op of a stage, and
+    // heap-backed tables made the allocator the largest item of the planner's profile)
+    constexpr int kMaxE = 1 << kMaxRegBits;
     struct Group {
         uint32_t cother, czero;
-        std::vector<Cx> tab;
+        Cx tab[kMaxE];
         Cx f[kMaxRegBits][2];
     };
     std::vector<Group> groups;
+    groups.reserve(8);
     auto group_for = [&](uint32_t cother, uint32_t czero) -> Group& {
         for (Group& g : groups)
             if (g.cother == cother && g.czero == czero) return g;
-        Group g;
+        groups.emplace_back();
+        Group& g = groups.back();
         g.cother = cother, g.czero = czero;
-        g.tab.assign((size_t)E, Cx{});
-        groups.push_back(std::move(g));
-        return groups.back();
+        return g;
     };
     auto is_unit = [](Cx z) { return z.re == 1.0 && z.im == 0.0; };
     auto same    = [](Cx a, Cx b) { return a.re == b.re && a.im == b.im; };
@@ -192,8 +197,9 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
     // applies whatever depends on one of the register bits in jmask: the whole group when its
     // table does, else only the factors of those bits (a phase on one register bit each)
     auto flush = [&](uint32_t jmask) {
-        std::vector<Group> keep;
-        for (Group& g : groups) {
+        size_t n_keep = 0;  // compacted in place
+        for (size_t gi = 0; gi < groups.size(); ++gi) {
+            Group& g = groups[gi];
             bool whole = false;
             for (int j = 0; j < R && !whole; ++j)
                 if ((jmask >> j) & 1u) whole = table_depends_on(g, j) || (!same(g.f[j][0], g.f[j][1]) && !is_unit(g.f[j][0]));
@@ -213,9 +219,10 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
                 g.f[j][1]  = Cx{};
                 fus[j].idx = -1;
             }
-            keep.push_back(std::move(g));
+            if (n_keep != gi) groups[n_keep] = g;
+            ++n_keep;
         }
-        groups.swap(keep);
+        groups.resize(n_keep);
     };
     auto conjugate_tables = [&](bool is_swap, uint32_t creg, int j0, int j1) {
         for (Group& g : groups) {
@@ -228,7 +235,7 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
             } else {
                 std::swap(g.f[j0][0], g.f[j0][1]);
             }
-            std::vector<Cx> t((size_t)E);
+            Cx t[kMaxE];
             for (int i = 0; i < E; ++i) {
                 int pi = i;
                 if (((uint32_t)i & creg) == creg) {
@@ -237,9 +244,9 @@ void emit_uops(Plan const& plan, PlannedStage& st) {
                     else if (((i >> j0) & 1) != ((i >> j1) & 1))
                         pi = i ^ (1 << j0) ^ (1 << j1);
                 }
-                t[(size_t)pi] = g.tab[i];
+                t[pi] = g.tab[i];
             }
-            g.tab.swap(t);
+            for (int i = 0; i < E; ++i) g.tab[i] = t[i];
         }
     };
     auto matrix_of = [&](LoweredOp const& op, Cx (&m)[4]) {
