@@ -272,7 +272,8 @@ def run_ours(args):
                 "schedule": {"sweeps_A": st_a.n_sweeps, "stages_A": st_a.n_stages, "micro_ops_A": st_a.n_micro_ops,
                              "max_ops_per_sweep": args.cap, "tile_qubits": args.tile, "reg_qubits": args.reg,
                              "dense_block": args.dense, "dense_blocks_A": st_a.n_dense_blocks,
-                             "l2_block_mib": args.l2_block, "l2_block_columns": plan_a.dump()["block_cols"]},
+                             "l2_block_mib": args.l2_block, "l2_block_columns": plan_a.dump()["block_cols"],
+                             "plan_host_ms_A": round(st_a.plan_host_ms, 3), "plan_host_ms_B": round(st_b.plan_host_ms, 3)},
             },
             "construct_ms_A": round(sweep_ms, 4),
             "equiv_ms": round(equiv_ms, 4),
