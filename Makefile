@@ -79,6 +79,16 @@ $(LIBQSX): $(OBJS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
 
+# A/B builds of the kernels: make variant NAME=wide DEFS="-DQSX_EARLY_PERMS=16 -DQSX_EARLY_ORUNS=8"
+#   -> build/variants/$(NAME)/libqsx.so (+ libqsxhost.so beside it); time them with scripts/ab_probe.py
+variant: $(LIBQSX) $(LIBHOST)
+	@test -n "$(NAME)" || (echo "usage: make variant NAME=<name> DEFS=<-D flags>"; exit 1)
+	@mkdir -p build/variants/$(NAME)
+	$(NVCC) -O3 -std=c++20 -lineinfo $(ARCH) -Xcompiler -fPIC $(DEFS) -c $(CSRC)/kernels.cu -o build/variants/$(NAME)/kernels.o
+	$(NVCC) $(ARCH) -shared -o build/variants/$(NAME)/libqsx.so build/variants/$(NAME)/kernels.o $(filter-out $(OBJDIR)/kernels.o,$(OBJS)) -lcudart
+	cp $(LIBHOST) build/variants/$(NAME)/
+	rm build/variants/$(NAME)/kernels.o
+
 oracle: oracle/_build/liboracle_c.so
 
 oracle/_build/liboracle_c.so: oracle/oracle_c.c
@@ -88,4 +98,4 @@ oracle/_build/liboracle_c.so: oracle/oracle_c.c
 clean:
 	rm -rf build $(LIBDIR) bin oracle/_build
 
-.PHONY: all clean oracle
+.PHONY: variant all clean oracle

@@ -381,13 +381,20 @@ __device__ __forceinline__ void permute_rows(uint32_t (&rows)[R + 1], const DevP
 // What the first stage's global load needs, passed BY VALUE (kernel parameters live in the constant bank: no
 // memory latency), so that a CTA's tile loads are in flight while its program is still being staged.  The
 // interpreter is latency-bound per CTA; this takes the program's L2 round trip off the path to the first load.
-constexpr int kEarlyPerms = 8, kEarlyRuns = 4;
+// (sizes overridable at build time for A/B runs: make variant NAME=wide DEFS="-DQSX_EARLY_PERMS=16 -DQSX_EARLY_ORUNS=8")
+#ifndef QSX_EARLY_PERMS
+#define QSX_EARLY_PERMS 8
+#endif
+#ifndef QSX_EARLY_ORUNS
+#define QSX_EARLY_ORUNS 4
+#endif
+constexpr int kEarlyPerms = QSX_EARLY_PERMS, kEarlyRuns = 4, kEarlyORuns = QSX_EARLY_ORUNS;
 struct FirstLoad {
     uint32_t fixed_one;
     int32_t  log2w;
     int32_t  n_pre;                     // folded permutation steps of the load boundary; < 0: take the staged path
     // bit deposits as runs of consecutive bits: row |= (x & mask[k]) << shift[k]; x = tile row index / thread row index
-    uint32_t omask[kEarlyRuns], oshift[kEarlyRuns];
+    uint32_t omask[kEarlyORuns], oshift[kEarlyORuns];
     uint32_t tmask[kEarlyRuns], tshift[kEarlyRuns];
     int32_t  rg[kMaxRegBits];
     // the steps in the order the LOAD side applies them (reversed list), global row bits, no outer condition
@@ -410,8 +417,15 @@ __global__ void __launch_bounds__(1 << mode_threads_log2(R, MODE), mode_min_ctas
         uint64_t const cb0   = t64 & ((1ull << log2_ncb) - 1ull);
         uint32_t const rc0   = (uint32_t)(t64 >> log2_ncb);
         uint32_t g0          = fl.fixed_one;
+        if constexpr (kEarlyORuns == kEarlyRuns) {
 #pragma unroll
-        for (int k = 0; k < kEarlyRuns; ++k) g0 |= ((rc0 & fl.omask[k]) << fl.oshift[k]) | ((trow0 & fl.tmask[k]) << fl.tshift[k]);
+            for (int k = 0; k < kEarlyRuns; ++k) g0 |= ((rc0 & fl.omask[k]) << fl.oshift[k]) | ((trow0 & fl.tmask[k]) << fl.tshift[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kEarlyORuns; ++k) g0 |= (rc0 & fl.omask[k]) << fl.oshift[k];
+#pragma unroll
+            for (int k = 0; k < kEarlyRuns; ++k) g0 |= (trow0 & fl.tmask[k]) << fl.tshift[k];
+        }
         uint32_t rows[R + 1];
         rows[0] = g0;
 #pragma unroll
@@ -657,21 +671,21 @@ cudaError_t launch_sweep_r(double2* u, int n, uint64_t ncols, uint64_t grid_ncol
             fl.pre_cml[k] = pm.cml, fl.pre_tml[k] = pm.tml;
         }
         // source bit k -> row bit pos[k] (ascending) as runs of equal shift
-        auto runs = [](const int32_t* pos, int count, uint32_t* mask, uint32_t* shift) {
+        auto runs = [](const int32_t* pos, int count, uint32_t* mask, uint32_t* shift, int max_runs) {
             int n_runs = 0;
             for (int k = 0; k < count; ++k) {
                 if (pos[k] < k || pos[k] >= 32) return false;
                 uint32_t const sh = (uint32_t)(pos[k] - k);
                 if (n_runs == 0 || shift[n_runs - 1] != sh) {
-                    if (n_runs == kEarlyRuns) return false;
+                    if (n_runs == max_runs) return false;
                     mask[n_runs] = 0u, shift[n_runs] = sh, ++n_runs;
                 }
                 mask[n_runs - 1] |= 1u << k;
             }
             return true;
         };
-        ok = ok && hs.n_outer >= 0 && hs.n_outer <= kMaxRowBits && runs(hs.outer, hs.n_outer, fl.omask, fl.oshift) &&
-             runs(st0->tg, st0->n_t, fl.tmask, fl.tshift);
+        ok = ok && hs.n_outer >= 0 && hs.n_outer <= kMaxRowBits && runs(hs.outer, hs.n_outer, fl.omask, fl.oshift, kEarlyORuns) &&
+             runs(st0->tg, st0->n_t, fl.tmask, fl.tshift, kEarlyRuns);
         if (ok) {
             fl.fixed_one = hs.fixed_one, fl.log2w = hs.log2w, fl.n_pre = np;
             for (int k = 0; k < kMaxRegBits; ++k) fl.rg[k] = st0->rg[k];
