@@ -93,7 +93,8 @@ oracle: oracle/_build/liboracle_c.so
 
 oracle/_build/liboracle_c.so: oracle/oracle_c.c
 	@mkdir -p oracle/_build
-	gcc -O3 -march=native -std=c11 -fPIC -shared -Wall -Wextra -o $@ $< -lm
+	@# no -march=native: the built library travels to the GPU box, whose host CPU may differ
+	gcc -O3 -std=c11 -fPIC -shared -Wall -Wextra -o $@ $< -lm
 
 clean:
 	rm -rf build $(LIBDIR) bin oracle/_build
