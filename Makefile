@@ -15,7 +15,8 @@ OBJDIR    := build/obj
 
 LIBQSX    := $(LIBDIR)/libqsx.so
 OBJS      := $(OBJDIR)/kernels.o $(OBJDIR)/runtime.o $(OBJDIR)/planner.o $(OBJDIR)/planner_lower.o \
-             $(OBJDIR)/planner_schedule.o $(OBJDIR)/planner_emit.o
+             $(OBJDIR)/planner_schedule.o $(OBJDIR)/planner_emit.o $(OBJDIR)/comm.o
+CUDAINC   := -I/usr/local/cuda/include
 
 HOST      := qsyn_b200/host
 SHIM      := bin/qsyn-b200
@@ -73,11 +74,11 @@ $(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.hpp) include/qsx.h $(wildcard q
 
 $(OBJDIR)/%.o: $(CSRC)/%.cpp $(wildcard $(CSRC)/*.hpp) include/qsx.h
 	@mkdir -p $(OBJDIR)
-	$(CXX) $(CXXFLAGS) -c $< -o $@
+	$(CXX) $(CXXFLAGS) $(CUDAINC) -c $< -o $@
 
 $(LIBQSX): $(OBJS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart -ldl
 
 # A/B builds of the kernels: make variant NAME=wide DEFS="-DQSX_EARLY_PERMS=16 -DQSX_EARLY_ORUNS=8"
 #   -> build/variants/$(NAME)/libqsx.so (+ libqsxhost.so beside it); time them with scripts/ab_probe.py
@@ -85,7 +86,7 @@ variant: $(LIBQSX) $(LIBHOST)
 	@test -n "$(NAME)" || (echo "usage: make variant NAME=<name> DEFS=<-D flags>"; exit 1)
 	@mkdir -p build/variants/$(NAME)
 	$(NVCC) -O3 -std=c++20 -lineinfo $(ARCH) -Xcompiler -fPIC $(DEFS) -c $(CSRC)/kernels.cu -o build/variants/$(NAME)/kernels.o
-	$(NVCC) $(ARCH) -shared -o build/variants/$(NAME)/libqsx.so build/variants/$(NAME)/kernels.o $(filter-out $(OBJDIR)/kernels.o,$(OBJS)) -lcudart
+	$(NVCC) $(ARCH) -shared -o build/variants/$(NAME)/libqsx.so build/variants/$(NAME)/kernels.o $(filter-out $(OBJDIR)/kernels.o,$(OBJS)) -lcudart -ldl
 	cp $(LIBHOST) build/variants/$(NAME)/
 	rm build/variants/$(NAME)/kernels.o
 

@@ -9,16 +9,23 @@ reference does for `qc2ts; qc2ts; tensor equiv 0 1`:
     build U_B for circuit B   (A followed by t,x,t,x on qubit 0 -> equivalent, global phase pi/4)
     fused equivalence reduction of (U_A, U_B) + host finish (verdict / norm / phase)
 The unitary's columns are sharded over the N ranks (one process per GPU, no communication
-during construction); the 8 partial sums are combined with ONE all-reduce (NCCL).
+during construction); the 8 partial sums are combined with ONE ncclAllReduce issued by the library
+(qsx_equiv_reduce; communicators from qsx_comm_init_rank).
+
+Default workload: C4 (n = 15, 10 000 Clifford+T gates, 16 GiB unitary): HBM-resident on every GPU count
+(2 GiB per GPU at N = 8).  `extra.c2` repeats the measurement on C2 (256 MiB: L2-assisted, the small end of the
+metric's range) and, on 8 GPUs, `extra.c5` on the north-star target C5 (n = 16, 64 GiB).
 
 metric `value` = effective gate-apply throughput: sum over GATES of the algorithmic bytes the
 reference touches for that gate (f * 32 B * 4^n) divided by the device time of
 the whole step (construction of both operands + equivalence), inputs resident in HBM
-(schedules prebuilt and uploaded).  `e2e` = the same metric through the C ABI from HOST
-gate arrays: scheduling, program upload (H2D) and the verdict read-back (D2H) are inside the
-timed region.  `roofline` = the dominant kernel (sweep_kernel) against measured HBM copy
-bandwidth.  `cpu_baseline` = the oracle restatement of the reference's per-gate tensordot
-algorithm (numpy/OpenBLAS, all host threads) on a bounded sample of the same workload.
+(schedules prebuilt and uploaded).  `e2e` = the same job through the reference-facing host layer from QASM TEXT:
+qsxh_circuit_from_qasm_text -> qsxh_qc2ts (A), (B) -> qsxh_tensor_equiv -> verdict text, everything (parsing,
+gate lowering through the QTensor builders, scheduling, program upload, the synchronous to_tensor with its stop
+callback, device allocation, the verdict read-back) inside the timed region.  `roofline` = the dominant kernel
+(the sweep kernel) against measured HBM copy bandwidth.  `cpu_baseline` = the oracle restatement of the
+reference's per-gate tensordot algorithm (numpy/OpenBLAS, all host threads) on a bounded sample of the same
+workload.
 """
 from __future__ import annotations
 
@@ -33,19 +40,19 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+TAIL = "t q[0];\nx q[0];\nt q[0];\nx q[0];\n"  # B = A . t x t x on qubit 0: Equivalent, global phase pi/4
+
+
 def build_workload(name):
     """Circuits A and B of the verification job through the PRODUCT's own front end: the synthetic
     QASM text (qsyn_b200.workloads) is parsed and lowered by the C++ host layer (libqsxhost.so:
-    qsyn-shaped QASM reader, QCir, per-gate matrices with the reference formulas).  B = A followed
-    by t,x,t,x on qubit 0 (Equivalent, global phase pi/4).  Nothing here touches oracle/."""
+    qsyn-shaped QASM reader, QCir, per-gate matrices with the reference formulas).  Nothing here touches oracle/."""
     from qsyn_b200 import host, workloads
 
     n, desc, text = workloads.workload_qasm(name)
     ca = host.Circuit(qasm_text=text)
-    cb = host.Circuit(qasm_text=text)
-    for nm in "txtx":
-        cb.append(nm, [0])
-    return n, desc, ca, cb
+    cb = host.Circuit(qasm_text=text + TAIL)
+    return n, desc, ca, cb, text
 
 
 # ------------------------------------------------------------------------------------------
@@ -91,106 +98,136 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _fp64_peak():
+    p = os.path.join(ROOT, "profiles", "r1_fp64_peak.json")
+    try:
+        d = json.load(open(p))
+        return float(d["dfma_tflops"]), "measured (bin/fp64_peak, profiles/r1_fp64_peak.json)"
+    except Exception:
+        return 36.66, "fallback (round-1 measurement of this pool's B200)"
+
+
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
-def run_ours(args):
-    import numpy as np
+class Ctx:
+    pass
+
+
+def setup(args):
     import torch
     import torch.distributed as dist
 
     import qsyn_b200 as Q
-    from qsyn_b200 import abi, sharding
+    from qsyn_b200 import abi, host
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    c = Ctx()
+    c.world = int(os.environ.get("WORLD_SIZE", "1"))
+    c.rank = int(os.environ.get("RANK", "0"))
+    c.local = int(os.environ.get("LOCAL_RANK", "0"))
+    if c.world != args.gpus and c.world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
     if Q.device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(c.local)
+    c.cuda = torch.device("cuda", c.local)
+    if c.world > 1:
+        dist.init_process_group("nccl", device_id=c.cuda)
+        # the library's own communicator (ncclCommInitRank): the id travels through torchrun's process group
+        uid = [abi.comm_get_unique_id() if c.rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0, device=c.cuda)
+        abi.comm_init_rank(c.local, c.world, c.rank, uid[0])
+        host._check(host.lib().qsxh_set_process_shard(c.rank, c.world, c.local))
+    c.stream = torch.cuda.ExternalStream(abi.device_stream(c.local), device=c.cuda)
+    c.torch, c.dist, c.Q, c.abi, c.host = torch, dist, Q, abi, host
+    return c
 
-    n, desc, circ_a, circ_b = build_workload(args.workload)
+
+def barrier(c):
+    if c.world > 1:
+        c.dist.barrier()
+    c.torch.cuda.synchronize()
+    c.abi.device_synchronize(c.local)
+
+
+def max_over_ranks(c, x: float) -> float:
+    t = c.torch.tensor([x], dtype=c.torch.float64, device="cuda")
+    if c.world > 1:
+        c.dist.all_reduce(t, op=c.dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def measure(c, args, workload, steps, warmup, e2e_steps, main_line):
+    """One workload on this job's GPUs -> the result dict (rank 0) or None."""
+    from qsyn_b200 import sharding
+
+    Q, abi, host, torch = c.Q, c.abi, c.host, c.torch
+    n, desc, circ_a, circ_b, text_a = build_workload(workload)
+    text_b = text_a + TAIL
     gs_a, gs_b = circ_a.gate_array(), circ_b.gate_array()  # (qsx_gate*, count): host buffers of the C ABI
+    na, nb = gs_a[1], gs_b[1]
     dim = 2**n
-    col0, ncols = sharding.shard_columns(n, rank, world)
+    col0, ncols = sharding.shard_columns(n, c.rank, c.world)
     opt = Q.PlanOptions(max_ops_per_sweep=args.cap, tile_qubits=args.tile, reg_qubits=args.reg, log2_tile_cols=args.log2w,
                         dense_block=args.dense, l2_block_mib=args.l2_block)
-
-    stream = torch.cuda.ExternalStream(abi.device_stream(local), device=torch.device("cuda", local))
-    ua = Q.Unitary(n, local, col0, ncols)
-    ub = Q.Unitary(n, local, col0, ncols)
+    ua = Q.Unitary(n, c.local, col0, ncols)
+    ub = Q.Unitary(n, c.local, col0, ncols)
     plan_a = Q.Plan(n, ncols, gs_a, opt)
     plan_b = Q.Plan(n, ncols, gs_b, opt)
     st_a, st_b = plan_a.stats(), plan_b.stats()
     launches = {"n": 0}
-    cuda = torch.device("cuda", local)
-
-    def combine(sums):
-        # ONE all-reduce of 8 doubles over NVLink; identity at world size 1
-        return sharding.allreduce_sums(sums, cuda)
 
     def step_resident():
-        """inputs resident: prebuilt schedules, device-side identity, async sweeps."""
+        """inputs resident: prebuilt schedules, device-side identity, async sweeps, ONE reduce call."""
         ua.set_identity()
         ra = plan_a.run(ua, flags=abi.QSX_RUN_ASYNC)
         ub.set_identity()
         rb = plan_b.run(ub, flags=abi.QSX_RUN_ASYNC)
-        sums = combine(ua.equiv_partial(ub))
+        sums = Q.equiv_reduce([ua], [ub])  # partial + finish kernels, ncclAllReduce(8 doubles) when world > 1, 64 B read-back
         launches["n"] += ra.launches + rb.launches + 2  # (the identity is synthesised by the first sweep of each operand)
         return Q.equiv_finish(sums, 1e-6, False)
 
-    # host-side input buffers of the C ABI (array of qsx_gate + matrices, owned by the host-layer circuits)
-    import ctypes as C
-    (arr_a, na), (arr_b, nb) = gs_a, gs_b
-    null_stop = C.cast(None, abi.STOP_FN)
-
     def step_e2e():
-        """through the C ABI from host gate arrays: schedule + program upload + sweeps + verdict."""
-        L = Q.lib()
-        ua.set_identity()
-        # async variant: B is scheduled on the host while A is being built on the device
-        abi._check(L.qsx_apply_gates_async(ua._h, arr_a, na, C.byref(opt), None))
-        ub.set_identity()
-        abi._check(L.qsx_apply_gates_async(ub._h, arr_b, nb, C.byref(opt), None))
-        return Q.equiv_finish(combine(ua.equiv_partial(ub)), 1e-6, False)
+        """the drop-in path, from QASM text to the verdict text, through the reference-shaped host layer."""
+        ca = host.Circuit(qasm_text=text_a)   # qsxh_circuit_from_qasm_text: reader + QCir
+        ta = ca.qc2ts()                       # qsxh_qc2ts: to_tensor(QCir) -> qsx_apply_gates (synchronous, stop callback)
+        cb = host.Circuit(qasm_text=text_b)
+        tb = cb.qc2ts()
+        r, text = ta.equiv(tb)                # qsxh_tensor_equiv: qsx_equiv_reduce + the text qsyn prints
+        for x in (ta, tb, ca, cb):
+            x.close()
+        return r, text
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        abi.device_synchronize(local)
-
-    # ---- correctness of the thing we time (cheap, size independent) ----
+    # ---- correctness of the thing we time (cheap, size independent; the element-wise parity of these configs against
+    #      the oracle is tests/test_gpu_baseline_parity.py) ----
     r = step_resident()
     assert r.equivalent == 1 and (r.phase_num, r.phase_den) == (1, 4) and abs(r.norm - 1) < 1e-9, \
         (r.equivalent, r.phase_num, r.phase_den, r.norm)
 
-    for _ in range(max(args.warmup, 3) - 1):
+    for _ in range(max(warmup, 3) - 1):
         step_resident()
 
     # ---- device-resident timing: CUDA events on the library stream ----
-    sampler = ClockSampler(local)
-    barrier()
-    if rank == 0:
+    sampler = ClockSampler(c.local)
+    barrier(c)
+    if c.rank == 0 and main_line:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches["n"] = 0
-    ev0.record(stream)
-    for _ in range(args.steps):
+    ev0.record(c.stream)
+    for _ in range(steps):
         step_resident()
-    ev1.record(stream)
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    ev1.record(c.stream)
+    barrier(c)
+    ms_step = max_over_ranks(c, ev0.elapsed_time(ev1)) / steps
+    clocks = sampler.stop() if (c.rank == 0 and main_line) else None
     gpu_launches = launches["n"]
 
     # ---- dominant kernel, timed live with CUDA events around the sweep launches only ----
@@ -201,63 +238,52 @@ def run_ours(args):
         if k > 0:
             kr.append(rs.device_ms)
             n_launch = rs.launches
-    sweep_ms = min(kr)
-    t = torch.tensor([sweep_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    sweep_ms = float(t.item())
+    sweep_ms = max_over_ranks(c, min(kr))
 
-    unfused = _unfused_probe(Q, n, ncols, ua, json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-                             if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0) if rank == 0 else None
+    peak, peak_src = _peaks()
+    unfused = _unfused_probe(Q, n, ncols, ua, peak) if (c.rank == 0 and main_line) else None
 
-    # equivalence alone (wall, includes the 64-byte read-back and the all-reduce)
-    barrier()
+    # equivalence alone (wall: kernels + all-reduce + the 64-byte read-back)
+    barrier(c)
     t0 = time.perf_counter()
     for _ in range(5):
-        combine(ua.equiv_partial(ub))
-    barrier()
-    equiv_ms = (time.perf_counter() - t0) / 5 * 1e3
+        Q.equiv_reduce([ua], [ub])
+    barrier(c)
+    equiv_ms = max_over_ranks(c, (time.perf_counter() - t0) / 5 * 1e3)
 
-    # ---- end-to-end through the C ABI from host buffers ----
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    # ---- end-to-end through the host layer from QASM text ----
+    e2e_s, verdict_text = None, None
+    if e2e_steps > 0:
+        for _ in range(2):
+            r2, verdict_text = step_e2e()
+        assert r2.equivalent == 1 and (r2.phase_num, r2.phase_den) == (1, 4), verdict_text
+        barrier(c)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e()
+        barrier(c)
+        e2e_s = max_over_ranks(c, (time.perf_counter() - t0) / e2e_steps)
 
     # per-gate algorithmic bytes of the WHOLE job (all shards): both operands
-    gate_bytes = (st_a.gate_bytes_per_run + st_b.gate_bytes_per_run) * world
+    gate_bytes = (st_a.gate_bytes_per_run + st_b.gate_bytes_per_run) * c.world
     value = gate_bytes / (ms_step * 1e-3) / 1e9
-    e2e_value = gate_bytes / e2e_s / 1e9
-    h2d = int(_plan_blob_bytes(plan_a) + _plan_blob_bytes(plan_b))
-
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = st_a.alg_bytes_per_run / (sweep_ms * 1e-3) / 1e9  # per GPU
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.workload)
+        # ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, per workload AND per GPU count (or absent)
+        traffic = json.load(open(tpath)).get(f"{workload}@{c.world}")
 
     out = None
-    if rank == 0:
+    if c.rank == 0:
+        shard_mib = 16 * dim * ncols / 2**20
         out = {
             "metric": "qcir2unitary_gate_apply_effective_GBps",
             "value": round(value, 2),
             "unit": "GB/s",
-            "n_gpus": world,
-            "steps": args.steps,
-            "warmup": max(args.warmup, 3),
+            "n_gpus": c.world,
+            "steps": steps,
+            "warmup": max(warmup, 3),
             "ms_per_step": round(ms_step, 4),
             "higher_is_better": True,
             "scaling": "strong",
@@ -269,9 +295,9 @@ def run_ours(args):
                 "n_qubits": n,
                 "gates_A": na, "gates_B": nb,
                 "columns_per_gpu": ncols,
-                "step": "identity+construct A, identity+construct B, fused equiv + host finish (verdict Equivalent, phase pi/4)",
+                "step": "identity+construct A, identity+construct B, fused equiv (one ncclAllReduce of 8 doubles) + host finish (verdict Equivalent, phase pi/4)",
                 "l2": "unitary shard per GPU is %.0f MiB; L2 is 126 MB: %s" % (
-                    16 * dim * ncols / 2**20, "inputs larger than L2" if 16 * dim * ncols > 126e6 else "shard fits in L2 (strong scaling), no flush"),
+                    shard_mib, "inputs larger than L2" if 16 * dim * ncols > 126e6 else "shard fits in L2 (strong scaling), no flush"),
                 "schedule": {"sweeps_A": st_a.n_sweeps, "stages_A": st_a.n_stages, "micro_ops_A": st_a.n_micro_ops,
                              "max_ops_per_sweep": args.cap, "tile_qubits": args.tile, "reg_qubits": args.reg,
                              "dense_block": args.dense, "dense_blocks_A": st_a.n_dense_blocks,
@@ -282,39 +308,67 @@ def run_ours(args):
             "equiv_ms": round(equiv_ms, 4),
             "equiv_GBps": round(2 * 16 * dim * dim / (equiv_ms * 1e-3) / 1e9, 1),
             "gpu_launches": gpu_launches,
-            "clocks": clocks,
-            "e2e": {"value": round(e2e_value, 2), "unit": "GB/s", "ms_per_step": round(e2e_s * 1e3, 4),
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64,
-                    "note": "host gate arrays -> qsx_apply_gates_async (schedule + program upload + sweeps) x2 -> qsx_equiv_partial -> verdict"},
-            "roofline": {"bound": "hbm", "kernel": ("dense_kernel<%d>" % args.dense) if args.dense else ("sweep_kernel<%d, *>" % args.reg), "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": ("dense_kernel<%d>" % args.dense) if args.dense else ("sweep_kernel<%d, *>" % args.reg),
+                         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": st_a.alg_bytes_per_run / max(n_launch, 1),
                          "launches": n_launch, "avg_launch_us": round(sweep_ms * 1e3 / max(n_launch, 1), 2)},
         }
+        if clocks is not None:
+            out["clocks"] = clocks
+        if e2e_s is not None:
+            out["e2e"] = {"value": round(gate_bytes / e2e_s / 1e9, 2), "unit": "GB/s", "ms_per_step": round(e2e_s * 1e3, 4),
+                          "steps": e2e_steps,
+                          "h2d_bytes_per_step": int(_plan_blob_bytes(plan_a) + _plan_blob_bytes(plan_b)), "d2h_bytes_per_step": 64,
+                          "host_input_bytes_per_step": len(text_a) + len(text_b),
+                          "verdict_text": verdict_text,
+                          "note": "QASM text -> qsxh_circuit_from_qasm_text -> qsxh_qc2ts (to_tensor(QCir): gate lowering, scheduling, program "
+                                  "upload, synchronous qsx_apply_gates with the stop callback) x2 -> qsxh_tensor_equiv (qsx_equiv_reduce) -> text"}
         if not args.dense:
             # the fused sweeps are co-limited by the FP64 FMA pipe: the same launches against that roof
-            fp64_peak_tflops = 36.66  # measured DFMA peak of this pool's B200 (bin/fp64_peak, profiles/r1_fp64_peak.json)
+            fp64_peak_tflops, fp64_src = _fp64_peak()
             instr = _fp64_instructions_per_run(plan_a, float(dim) * ncols)
             ach = 2.0 * instr / (sweep_ms * 1e-3) / 1e12  # an FP64 pipe slot is worth 2 flop at the DFMA peak
             out["roofline_fp64"] = {"bound": "fp64_pipe", "kernel": "sweep_kernel<%d, *>" % args.reg, "achieved": round(ach, 2),
-                                    "peak": fp64_peak_tflops, "unit": "TFLOP/s (FP64 pipe slots x 2)", "frac": round(ach / fp64_peak_tflops, 4),
+                                    "peak": fp64_peak_tflops, "peak_source": fp64_src, "unit": "TFLOP/s (FP64 pipe slots x 2)",
+                                    "frac": round(ach / fp64_peak_tflops, 4),
                                     "fp64_instructions_per_element_per_launch": round(instr / (float(dim) * ncols) / max(st_a.n_sweeps, 1), 2)}
         if unfused is not None:
             out["roofline_unfused"] = unfused
-        if world == 1 and not args.no_cpu_baseline:
+    for x in (plan_a, plan_b, ua, ub):
+        x.close()
+    return out
+
+
+def run_ours(args):
+    c = setup(args)
+    out = measure(c, args, args.workload, args.steps, args.warmup, min(args.steps, args.e2e_steps), True)
+    extras = [x for x in args.extras.split(",") if x] if args.extras != "auto" else \
+        ([] if args.workload == "c2" else ["c2"]) + (["c5"] if c.world >= 8 and args.workload != "c5" else [])
+    extra = {}
+    for w in extras:
+        few = w in ("c4", "c5")
+        r = measure(c, args, w, 3 if few else 20, 3, 2 if few else 10, False)
+        if r is not None:
+            extra[w] = {k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "config", "construct_ms_A", "equiv_ms",
+                                          "gpu_launches", "roofline", "roofline_fp64", "e2e") if k in r}
+    if c.rank == 0:
+        if extra:
+            out["extra"] = extra
+        if c.world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args.workload, budget_s=args.cpu_budget)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    if rank == 0:
+    if c.world > 1:
+        c.dist.barrier()
+        c.abi.shutdown()
+        c.dist.destroy_process_group()
+    if c.rank == 0:
         emit_result(out)
 
 
 def _unfused_probe(Q, n, ncols, u, peak):
     """The memory-bound end of the same kernel, measured live: three single-gate sweeps (h on the first, a middle
     and the last qubit; one gate per launch, no fusion) on the resident shard.  This is the north_star's
-    'gate-apply against the HBM roofline' in its literal, one-pass-per-gate form; the fused sweeps of the job
-    carry ~20 micro-ops per pass and are bound by the FP64 pipe and latency instead (roofline_fp64)."""
+    'gate-apply against the HBM roofline' in its literal, one-pass-per-gate form."""
     try:
         from qsyn_b200 import host
         qubits = sorted({0, n // 2, n - 1})
@@ -385,10 +439,17 @@ def _gate_fraction(op):
     return f
 
 
+def _sample_columns(n: int) -> int:
+    """Columns of the bounded sample: all of them up to n = 13; beyond that a column block of <= 1 GiB (the tensordot
+    scheme needs ~3 copies of the tensor: 48 GiB of host RAM for the whole matrix at n = 15, 192 GiB at n = 16).  The
+    input axes are never contracted, so the reference's cost is linear in the number of columns."""
+    return 2**n if n <= 13 else 2 ** (26 - n)
+
+
 def cpu_reference_sample(workload: str, n_gates: int):
     """Times the literal per-gate tensordot loop of qcir_to_tensor.cpp:173-194 (numpy tensordot =
-    transpose + zgemm on OpenBLAS, all host threads) for the first n_gates of the workload,
-    then the 8-pass equivalence of tensor_cmd.cpp:152-154 (single-thread C port)."""
+    transpose + zgemm on OpenBLAS, all host threads) for the first n_gates of the workload on the sample's
+    columns, then the 8-pass equivalence of tensor_cmd.cpp:152-154 (single-thread C port) on the same block."""
     import numpy as np
 
     from oracle import oracle as O
@@ -401,63 +462,69 @@ def cpu_reference_sample(workload: str, n_gates: int):
     sub = O.QCir(n)
     for g in qc_a.topological_order()[:n_gates]:
         sub.append(g.op, g.qubits)
+    ncols = _sample_columns(n)
     # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
     from threadpoolctl import threadpool_info, threadpool_limits
     with threadpool_limits(limits=os.cpu_count()):
         threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
         t0 = time.perf_counter()
-        t = O.to_tensor_literal(sub)
-        m = O.interleaved_to_matrix(t)
+        if ncols == 2**n:
+            m = O.interleaved_to_matrix(O.to_tensor_literal(sub))
+        else:
+            m = O.to_tensor_literal_columns(sub, 0, ncols)
         t_construct = time.perf_counter() - t0
-    ident = np.eye(2**n, dtype=np.complex128)
+    ident = np.zeros_like(m)
+    ident[np.arange(ncols), np.arange(ncols)] = 1.0
     t0 = time.perf_counter()
     oracle_c.equiv_reference_passes(ident, m)
     t_equiv = time.perf_counter() - t0
-    gate_bytes = sum(_gate_fraction(g.op) * 32.0 * 4.0**n for g in sub.gates)
-    return {"n": n, "gates": len(sub.gates), "construct_s": t_construct, "equiv_s": t_equiv, "gate_bytes": gate_bytes,
-            "desc": desc, "threads": threads}
+    share = ncols / 2.0**n
+    gate_bytes = sum(_gate_fraction(g.op) * 32.0 * 4.0**n * share for g in sub.gates)
+    return {"n": n, "gates": len(sub.gates), "ncols": ncols, "construct_s": t_construct, "equiv_s": t_equiv, "gate_bytes": gate_bytes,
+            "equiv_bytes": 8 * 16.0 * 2.0**n * ncols, "desc": desc, "threads": threads}
 
 
-def cpu_baseline(workload: str, budget_s: float = 20.0):
+def _per_gate_s(n: int) -> float:
+    # measured ballpark: ~0.18 s per gate at n = 12 on 16 cores, x4 per extra qubit, linear in columns
+    return 0.18 * 4.0 ** (n - 12) * _sample_columns(n) / 2.0**n
+
+
+def _sample_text(s, g_total):
+    cols = "all columns" if s["ncols"] == 2 ** s["n"] else f"the first {s['ncols']} of {2 ** s['n']} columns (cost is linear in columns)"
+    return (f"first {s['gates']} of {g_total} gates of the same n={s['n']} circuit on {cols} through the oracle's literal per-gate "
+            f"numpy.tensordot loop (OpenBLAS, all host threads): {s['construct_s']:.2f} s; 8-pass equivalence "
+            f"(single-thread C port) on that block: {s['equiv_s']:.2f} s; restatement of the reference algorithm, not the reference binary")
+
+
+def cpu_baseline(workload: str, budget_s: float = 15.0):
     from qsyn_b200.workloads import WORKLOADS
 
-    n = WORKLOADS[workload][0]
-    # measured ballpark: ~0.18 s per gate at n=12, x4 per extra qubit
-    per_gate = 0.18 * 4.0 ** (n - 12)
-    if n > 13:
-        return {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "port",
-                "sample": f"not run: the tensordot scheme needs ~3 x 16 x 4^{n} B of host RAM and ~{per_gate:.0f} s per gate at n={n}"}
-    g = min(WORKLOADS[workload][2], max(4, int(budget_s / per_gate)))
+    n, _, g_total = WORKLOADS[workload][:3]
+    g = min(g_total, max(2, int(budget_s / _per_gate_s(n))))
     s = cpu_reference_sample(workload, g)
     return {"value": round(s["gate_bytes"] / s["construct_s"] / 1e9, 3), "unit": "GB/s", "cores": s["threads"],
-            "kind": "port",
-            "sample": f"first {s['gates']} gates of the same n={s['n']} circuit through the oracle's literal per-gate "
-                      f"numpy.tensordot loop (OpenBLAS, all host threads): {s['construct_s']:.2f} s; "
-                      f"8-pass equivalence (single-thread C port): {s['equiv_s']:.2f} s",
-            "ms_per_gate": round(s["construct_s"] / s["gates"] * 1e3, 2), "equiv_s": round(s["equiv_s"], 3)}
+            "kind": "port", "sample": _sample_text(s, g_total),
+            "ms_per_gate_full_matrix": round(s["construct_s"] / s["gates"] * 1e3 * 2.0**n / s["ncols"], 2),
+            "equiv_s_full_matrix": round(s["equiv_s"] * 2.0**n / s["ncols"], 3)}
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm (oracle port; the reference binary cannot be
-    built here: xtensor/xtensor-blas/OpenBLAS are not vendored) on the host cores."""
+    built here: xtensor/xtensor-blas/OpenBLAS are not vendored) on the host cores, same workload, same metric."""
     from qsyn_b200.workloads import WORKLOADS
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n, gen, g_total, seed, desc = WORKLOADS[args.workload]
-    if n > 14:
-        emit_result({"impl": "reference", "unavailable": f"the CPU tensordot path needs ~3x16x4^{n} B RAM and minutes per gate at n={n}"})
-        return
-    per_gate = 0.18 * 4.0 ** (n - 12)
-    g = min(g_total, max(2 if n > 13 else 4, int(8.0 / per_gate)))
-    for _ in range(max(args.warmup, 1) if args.warmup < 3 else 1):
-        cpu_reference_sample(args.workload, max(2, g // 8))
-    tot_s, tot_bytes, eq_s = 0.0, 0.0, 0.0
+    # each step a bounded sample; the whole run ends within a few minutes
+    per_step = max(2.0, min(8.0, 150.0 / max(args.steps + 1, 1)))
+    g = min(g_total, max(2, int(per_step / _per_gate_s(n))))
+    cpu_reference_sample(args.workload, 2)  # warm-up (imports, OpenBLAS threads, page faults)
+    tot_s, tot_bytes = 0.0, 0.0
     for _ in range(args.steps):
         s = cpu_reference_sample(args.workload, g)
         tot_s += s["construct_s"] + s["equiv_s"]
-        eq_s += s["equiv_s"]
         tot_bytes += s["gate_bytes"]
     value = tot_bytes / tot_s / 1e9
     out = {
@@ -466,10 +533,9 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(tot_s / args.steps * 1e3, 2),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "complex128 (f64)",
         "data": "synthetic (same seeded circuit as the GPU arm)",
-        "config": {"workload": desc, "n_qubits": n,
-                   "step": f"bounded sample: first {g} gates of circuit A via per-gate numpy.tensordot (OpenBLAS) + 8-pass equivalence vs identity"},
+        "config": {"workload": desc, "n_qubits": n, "step": "bounded sample: " + _sample_text(s, g_total)},
         "cpu_baseline": {"value": round(value, 3), "unit": "GB/s", "cores": s["threads"], "kind": "port",
-                         "sample": f"{g} of {g_total} gates per step; restatement of the reference algorithm, not the reference binary"},
+                         "sample": _sample_text(s, g_total)},
         "e2e": {"value": round(value, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit_result(out)
@@ -480,8 +546,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "tiny"])
+    ap.add_argument("--workload", default="c4", choices=["c2", "c3", "c4", "c5", "tiny"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--extras", default="auto", help="comma list of further workloads reported under `extra` (auto: c2, and c5 on 8 GPUs)")
+    ap.add_argument("--e2e-steps", type=int, default=10, help="timed end-to-end steps (at most --steps)")
     ap.add_argument("--cap", type=int, default=96, help="max ops per sweep")
     ap.add_argument("--tile", type=int, default=8)
     ap.add_argument("--reg", type=int, default=4)

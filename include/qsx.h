@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define QSX_ABI_VERSION 1
+#define QSX_ABI_VERSION 2
 #define QSX_MAX_GATE_QUBITS 16
 
 typedef enum qsx_status {
@@ -51,6 +51,12 @@ typedef struct qsx_plan    qsx_plan;    /* opaque: a scheduled gate stream      
 /* ---- runtime -------------------------------------------------------------- */
 int         qsx_abi_version(void);
 const char* qsx_last_error(void);
+/* Optional eager start-up: creates the per-device streams of devices 0..n_gpus-1 (n_gpus <= 0: all),
+ * enables peer access between them and, for n_gpus > 1, the NCCL communicators of that device set (ncclCommInitAll).
+ * Everything it does is otherwise done lazily on first use.  The reference has no counterpart: it is the start-up
+ * cost of keeping Tensor storage (tensor.hpp:144) on devices.  qsx_shutdown destroys the communicators. */
+int qsx_init(int n_gpus);
+int qsx_shutdown(void);
 /* number of usable CUDA devices (0 on a CPU-only host; never an error) */
 int qsx_device_count(int* count);
 /* the cudaStream_t (as void*) all work for `device` is enqueued on */
@@ -81,6 +87,14 @@ int qsx_unitary_get_info(const qsx_unitary* u, qsx_unitary_info* info);
  * Replaces element access / xt::adapt (tensor.hpp:156-175,380) for whole blocks. */
 int qsx_unitary_upload(qsx_unitary* u, uint64_t row0, uint64_t nrows, const double* host);
 int qsx_unitary_download(const qsx_unitary* u, uint64_t row0, uint64_t nrows, double* host);
+/* rows [row0,row0+nrows) x shard-local columns [c0,c0+nc) <-> a host block whose rows are host_ld complex128 apart
+ * (0: nc, i.e. a packed nrows x nc array; dim to address a column block of the full row-major matrix): one strided
+ * copy, no host-side transposition.  Element access `tensor(i, j)` for blocks (tensor.hpp:156-175; decomposer.hpp:64-69
+ * reads single elements this way) and the scatter / gather of a column-sharded tensor. */
+int qsx_unitary_download_block(const qsx_unitary* u, uint64_t row0, uint64_t nrows, uint64_t c0, uint64_t nc, double* host,
+                               uint64_t host_ld);
+int qsx_unitary_upload_block(qsx_unitary* u, uint64_t row0, uint64_t nrows, uint64_t c0, uint64_t nc, const double* host,
+                             uint64_t host_ld);
 
 /* ---- construction: replaces the per-gate tensordot loop (qcir_to_tensor.cpp:173-194 -> tensor.hpp:413-432) */
 typedef struct qsx_gate {
@@ -176,6 +190,23 @@ int qsx_apply_gates_async(qsx_unitary* u, const qsx_gate* gates, size_t n_gates,
  * (QSX_ERR_SHAPE otherwise).  Shards of one unitary are combined by adding the 8 doubles
  * (ncclAllReduce / torch.distributed.all_reduce, SUM). */
 int qsx_equiv_partial(const qsx_unitary* a, const qsx_unitary* b, double sums[8]);
+
+/* The whole check for a column-sharded pair in ONE call: the reduction is launched on every device concurrently, the
+ * per-device sums are combined by a single ncclAllReduce(8 x double, SUM) over NVLink, and 64 bytes are read back.
+ * Replaces the three reductions of tensor_cmd.cpp:152-154 (cosine_similarity, global_norm, global_phase).
+ *   - one process, several devices: a[k], b[k] = shard k of each operand (any device placement; communicators are
+ *     created with ncclCommInitAll on first use or by qsx_init);
+ *   - one process per GPU (torchrun): after qsx_comm_init_rank, n_shards = 1 and the all-reduce spans the ranks;
+ *   - one device, no communicator: the local sums (no NCCL call is made, libnccl is not even loaded). */
+int qsx_equiv_reduce(const qsx_unitary* const* a, const qsx_unitary* const* b, int n_shards, double sums[8]);
+
+/* One process per GPU: rank 0 creates an id (ncclGetUniqueId), the launcher hands its QSX_COMM_ID_BYTES bytes to every
+ * rank (torchrun's store, MPI, a file), every rank joins (ncclCommInitRank) with the device that holds its shards. */
+#define QSX_COMM_ID_BYTES 128
+int qsx_comm_get_unique_id(void* id, size_t id_size);
+int qsx_comm_init_rank(int device, int world, int rank, const void* id, size_t id_size);
+/* ranks the all-reduce of qsx_equiv_reduce spans beyond this process (1 without qsx_comm_init_rank); NCCL version code */
+int qsx_comm_info(int* world, int* nccl_version);
 
 typedef struct qsx_equiv_result {
     int32_t equivalent;      /* verdict incl. --strict rule (tensor_cmd.cpp:152-160)                      */

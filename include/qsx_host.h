@@ -22,6 +22,12 @@ typedef struct qsxh_tensor  qsxh_tensor;  /* a qsyn::tensor::QTensor<double> (de
 
 const char* qsxh_last_error(void);
 
+/* One process per GPU (torchrun / mpirun): every process runs the same commands; tensors of >= 64 x world columns are
+ * column-sharded over the processes (this one holds block `rank` on `device`), smaller ones are held in full by every
+ * process.  `tensor equiv` all-reduces over the ranks once qsx_comm_init_rank was called.  world = 1 restores the
+ * default (one process, QSX_NUM_GPUS devices). */
+int qsxh_set_process_shard(int rank, int world, int device);
+
 int qsxh_circuit_new(size_t n_qubits, qsxh_circuit** out);
 int qsxh_circuit_from_qasm_text(const char* text, qsxh_circuit** out);
 int qsxh_circuit_from_qasm_file(const char* path, qsxh_circuit** out);

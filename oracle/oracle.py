@@ -650,6 +650,37 @@ def to_tensor_literal(qc: QCir, trace: list | None = None) -> np.ndarray | None:
     return matrix_to_interleaved(mat)  # to_qtensor, qcir_to_tensor.cpp:208
 
 
+def to_tensor_literal_columns(qc: QCir, col0: int, ncols: int, max_gates: int | None = None) -> np.ndarray:
+    """The same per-gate tensordot loop (qcir_to_tensor.cpp:173-194) on a COLUMN BLOCK of the unitary: the n input
+    axes, which no gate ever contracts, are collapsed into one trailing axis of `ncols` columns.  Every gate is still
+    one np.tensordot(gate, main) over the gate's input pins and the main tensor's output pins (same transposed copy +
+    zgemm scheme), and its cost is linear in the number of columns -- this is the bounded sample the CPU baseline of
+    bench.py times at n >= 14, where the full tensor (3 x 16 x 4^n B) does not fit a host.  Returns U[:, col0:col0+ncols]."""
+    n = qc.n_qubits
+    dim = 2**n
+    tensor = np.zeros((dim, ncols), dtype=np.complex128)
+    for c in range(ncols):
+        tensor[col0 + c, c] = 1.0
+    tensor = tensor.reshape([2] * n + [ncols])
+    out_pin = {q: q for q in range(n)}  # qubit -> axis of its output index
+    gates = qc.topological_order()
+    for g in gates[:max_gates]:
+        gt = gate_tensor(g.op)
+        k = len(g.qubits)
+        gate_in = [2 * p + 1 for p in range(k)]
+        main_out = [out_pin[q] for q in g.qubits]
+        tensor = np.tensordot(gt, tensor, axes=(gate_in, main_out))
+        # result axes: the gate's k output pins, then the surviving main axes in order (tensor.hpp:419-430)
+        new_pin = {}
+        for q in range(n):
+            if q in g.qubits:
+                new_pin[q] = g.qubits.index(q)
+            else:
+                new_pin[q] = k + out_pin[q] - sum(1 for a in main_out if a < out_pin[q])
+        out_pin = new_pin
+    return np.ascontiguousarray(np.transpose(tensor, [out_pin[q] for q in range(n)] + [n])).reshape(dim, ncols)
+
+
 _LIBSTDCXX_PRIMES = [
     13, 29, 59, 127, 257, 541, 1109, 2357, 5087, 10273, 20753, 42043, 85229, 172933,
 ]

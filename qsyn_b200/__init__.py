@@ -15,6 +15,7 @@ from .abi import (  # noqa: F401
     adjoint_sharded,
     device_count,
     equiv_finish,
+    equiv_reduce,
     lib,
     lib_path,
 )

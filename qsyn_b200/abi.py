@@ -114,7 +114,15 @@ def _declare(L: C.CDLL) -> None:
         "qsx_apply_gates": [vp, C.POINTER(GateStruct), C.c_size_t, C.POINTER(PlanOptions), STOP_FN, vp,
                             C.POINTER(RunStats)],
         "qsx_apply_gates_async": [vp, C.POINTER(GateStruct), C.c_size_t, C.POINTER(PlanOptions), C.POINTER(RunStats)],
+        "qsx_init": [i32],
+        "qsx_shutdown": [],
+        "qsx_unitary_download_block": [vp, u64, u64, u64, u64, dp, u64],
+        "qsx_unitary_upload_block": [vp, u64, u64, u64, u64, dp, u64],
         "qsx_equiv_partial": [vp, vp, dp],
+        "qsx_equiv_reduce": [C.POINTER(vp), C.POINTER(vp), i32, dp],
+        "qsx_comm_get_unique_id": [vp, C.c_size_t],
+        "qsx_comm_init_rank": [i32, i32, i32, vp, C.c_size_t],
+        "qsx_comm_info": [C.POINTER(C.c_int), C.POINTER(C.c_int)],
         "qsx_equiv_finish": [dp, C.c_double, i32, C.POINTER(EquivResult)],
         "qsx_unitary_adjoint_inplace": [vp],
         "qsx_unitary_adjoint_sharded": [C.POINTER(vp), C.c_int],
@@ -233,6 +241,12 @@ class Unitary:
         _check(lib().qsx_unitary_download(self._h, row0, nrows, out.ctypes.data_as(C.POINTER(C.c_double))))
         return out
 
+    def download_block(self, row0: int, nrows: int, c0: int, nc: int) -> np.ndarray:
+        """rows [row0, row0+nrows) x shard-local columns [c0, c0+nc): qsx_unitary_download_block."""
+        out = np.empty((nrows, nc), dtype=np.complex128)
+        _check(lib().qsx_unitary_download_block(self._h, row0, nrows, c0, nc, out.ctypes.data_as(C.POINTER(C.c_double)), 0))
+        return out
+
     def upload(self, host: np.ndarray, row0: int = 0):
         i = self.info
         h = np.ascontiguousarray(host, dtype=np.complex128)
@@ -281,6 +295,45 @@ def adjoint_sharded(shards: Sequence["Unitary"]) -> None:
     """qsx_unitary_adjoint_sharded: shards[k] holds columns [k c, (k+1) c), possibly on different devices."""
     arr = (C.c_void_p * len(shards))(*[u._h for u in shards])
     _check(lib().qsx_unitary_adjoint_sharded(arr, len(shards)))
+
+
+def equiv_reduce(a: Sequence["Unitary"], b: Sequence["Unitary"]) -> np.ndarray:
+    """qsx_equiv_reduce: the fused reduction on every shard pair + ONE NCCL all-reduce of the 8 sums (over the
+    devices of this process, or over the ranks after comm_init_rank)."""
+    assert len(a) == len(b) and len(a) >= 1
+    aa = (C.c_void_p * len(a))(*[u._h for u in a])
+    bb = (C.c_void_p * len(b))(*[u._h for u in b])
+    out = np.zeros(8, dtype=np.float64)
+    _check(lib().qsx_equiv_reduce(aa, bb, len(a), out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
+
+
+QSX_COMM_ID_BYTES = 128
+
+
+def comm_get_unique_id() -> bytes:
+    buf = C.create_string_buffer(QSX_COMM_ID_BYTES)
+    _check(lib().qsx_comm_get_unique_id(buf, QSX_COMM_ID_BYTES))
+    return buf.raw
+
+
+def comm_init_rank(device: int, world: int, rank: int, uid: bytes) -> None:
+    buf = C.create_string_buffer(uid, QSX_COMM_ID_BYTES)
+    _check(lib().qsx_comm_init_rank(device, world, rank, buf, QSX_COMM_ID_BYTES))
+
+
+def comm_info() -> tuple[int, int]:
+    w, v = C.c_int(0), C.c_int(0)
+    _check(lib().qsx_comm_info(C.byref(w), C.byref(v)))
+    return w.value, v.value
+
+
+def init(n_gpus: int = 0) -> None:
+    _check(lib().qsx_init(n_gpus))
+
+
+def shutdown() -> None:
+    _check(lib().qsx_shutdown())
 
 
 def equiv_finish(sums: Sequence[float], eps: float = 1e-6, strict: bool = False) -> EquivResult:

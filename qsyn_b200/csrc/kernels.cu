@@ -571,16 +571,8 @@ __global__ void __launch_bounds__(1 << mode_threads_log2(R, MODE), mode_min_ctas
             int const ob = st->op_begin, oe = st->op_end;
             // (prefetching the next header was measured: the 8 extra live registers spill, -12 %)
             for (int o = ob; o < oe; ++o) {
-#if defined(QSX_EXP_DIRECT) && QSX_EXP_DIRECT == 1
-                run_handler<R, H_H>(e, scal, ops + o, 0u, 0, 0, grow, pool);  // timing experiment: no dispatch at all
-#elif defined(QSX_EXP_DIRECT) && QSX_EXP_DIRECT == 2
-                int4 const hdr2 = *(reinterpret_cast<const int4*>(ops + o) + 1);
-                if ((grow & (uint32_t)hdr2.x) != (uint32_t)hdr2.x || (grow & (uint32_t)hdr2.y) != 0u) continue;
-                run_handler<R, H_H>(e, scal, ops + o, 0u, 0, 0, grow, pool);  // timing experiment: control test, no switch
-#else
                 int4 const hdr = *reinterpret_cast<const int4*>(ops + o);
                 apply_op<R, MODE>(e, ops + o, hdr, grow, pool);
-#endif
             }
         }
 
@@ -967,16 +959,22 @@ __global__ void __launch_bounds__(kEqThreads) equiv_partial_kernel(const double2
     }
 }
 
-// deterministic finish: one block, fixed order
-__global__ void __launch_bounds__(32) equiv_finish_kernel(const double* __restrict__ partials, int n_blocks,
-                                                          double* __restrict__ out8) {
-    if (threadIdx.x < 8) {
-        int const q = threadIdx.x;
-        Kahan t;
-        for (int blk = 0; blk < n_blocks; ++blk)
-            kahan_merge(t, partials[(size_t)blk * 16 + 2 * q], partials[(size_t)blk * 16 + 2 * q + 1]);
-        out8[q] = t.value();
+// deterministic finish: one block, fixed order.  Warp q reduces quantity q: lane l merges the per-block partials
+// l, l + 32, ... in order, then the 32 lanes are merged by a shuffle tree (5 dependent merges instead of a chain
+// of n_blocks: 2 us instead of 9 us at 592 blocks, which is 10 % of the whole check at n = 12).
+__global__ void __launch_bounds__(256) equiv_finish_kernel(const double* __restrict__ partials, int n_blocks,
+                                                           double* __restrict__ out8) {
+    int const q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Kahan t;
+    for (int blk = lane; blk < n_blocks; blk += 32)
+        kahan_merge(t, partials[(size_t)blk * 16 + 2 * q], partials[(size_t)blk * 16 + 2 * q + 1]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double const s2 = __shfl_down_sync(0xffffffffu, t.s, off);
+        double const c2 = __shfl_down_sync(0xffffffffu, t.c, off);
+        kahan_merge(t, s2, c2);
     }
+    if (lane == 0) out8[q] = t.value();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1105,15 +1103,18 @@ bool sweep_can_start_from_identity(int R, const DevSweep& hs) {
 
 size_t equiv_partials_doubles() { return (size_t)kEqBlocks * 16; }
 
-cudaError_t launch_equiv(const double2* a, const double2* b, uint64_t n_elems, double* partials, double* out8,
-                         cudaStream_t s) {
+cudaError_t launch_equiv_partials(const double2* a, const double2* b, uint64_t n_elems, double* partials, int* n_blocks,
+                                  cudaStream_t s) {
     uint64_t blocks = (n_elems + kEqThreads - 1) / kEqThreads;
     if (blocks > (uint64_t)kEqBlocks) blocks = kEqBlocks;
     if (blocks == 0) blocks = 1;
     equiv_partial_kernel<<<(unsigned)blocks, kEqThreads, 0, s>>>(a, b, n_elems, partials);
-    cudaError_t rc = cudaGetLastError();
-    if (rc != cudaSuccess) return rc;
-    equiv_finish_kernel<<<1, 32, 0, s>>>(partials, (int)blocks, out8);
+    *n_blocks = (int)blocks;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_equiv_finish(const double* partials, int n_blocks, double* out8, cudaStream_t s) {
+    equiv_finish_kernel<<<1, 256, 0, s>>>(partials, n_blocks, out8);
     return cudaGetLastError();
 }
 

@@ -21,10 +21,12 @@ cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, uint64_t grid_ncols,
                          cudaStream_t s);
 
 // fused equivalence reduction (K4): 8 compensated sums of a shard pair.
-// `partials` must hold equiv_partials_doubles() doubles of device scratch; out8 is device memory.
+// `partials` receives 16 doubles per block used (*n_blocks <= equiv_partials_doubles() / 16); the finish kernel merges
+// the partials of any number of shard pairs (laid out back to back) into out8 (device memory) in a fixed order.
 size_t equiv_partials_doubles();
-cudaError_t launch_equiv(const double2* a, const double2* b, uint64_t n_elems, double* partials, double* out8,
-                         cudaStream_t s);
+cudaError_t launch_equiv_partials(const double2* a, const double2* b, uint64_t n_elems, double* partials, int* n_blocks,
+                                  cudaStream_t s);
+cudaError_t launch_equiv_finish(const double* partials, int n_blocks, double* out8, cudaStream_t s);
 
 // in-place conjugate transpose of a full 2^n x 2^n matrix (K5)
 // in-place conjugate transpose of a dim x dim row-major matrix

@@ -287,6 +287,13 @@ int build_plan(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gat
     cfg.m_cap       = std::min(cfg.m_cap, max_threads_log2(cfg.R) - cfg.log2w + cfg.R);  // CTA size limit
     cfg.m_cap       = std::max(std::min(cfg.m_cap, n_qubits), cfg.R);
     cfg.max_ops     = o.max_ops_per_sweep > 0 ? (int)o.max_ops_per_sweep : 96;
+    // a sweep's program is staged in shared memory next to the tile (200 KiB together, launch_sweep_r): cap the ops so
+    // that the serialised program always fits (<= 96 B header + a 16-entry table per micro-op, scalars 48 B each)
+    {
+        long const tile_bytes = 16L << (cfg.m_cap + cfg.log2w);
+        long const room       = 200L * 1024 - tile_bytes - 8192;
+        cfg.max_ops           = (int)std::max(4L, std::min((long)cfg.max_ops, room / 400));
+    }
     cfg.min_tail_ops = o.min_tail_ops > 0 ? (int)o.min_tail_ops : (o.min_tail_ops < 0 ? 0 : 8);
     cfg.lookahead   = o.lookahead > 0 ? (int)o.lookahead : 4096;
     // the search costs a few ms of host time: worth it once a sweep takes milliseconds (n >= 13)
@@ -330,6 +337,16 @@ int build_plan(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gat
     plan.stats.n_sweeps = plan.sweeps.size();
     choose_l2_blocking(plan, o.l2_block_mib);
     serialize(plan);
+    for (size_t k = 0; k < plan.sweeps.size(); ++k) {
+        PlannedSweep const& sw = plan.sweeps[k];
+        if (!sw.block_bits.empty()) continue;
+        size_t const tile = sw.stages.size() > 1 ? ((size_t)16 << (sw.tile_bits.size() + (size_t)cfg.log2w)) : 0;
+        if (plan.sweep_size[k] + tile > 200u * 1024u) {
+            msg = "sweep " + std::to_string(k) + " needs " + std::to_string(plan.sweep_size[k] + tile) +
+                  " B of shared memory (program + tile), more than the 200 KiB a CTA can have: lower max_ops_per_sweep or tile_qubits";
+            return QSX_ERR_BAD_ARG;
+        }
+    }
     plan.stats.plan_host_ms =
         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     return QSX_OK;

@@ -1,7 +1,8 @@
 // runtime.cu -- the C ABI of include/qsx.h: device contexts, shard storage, plan execution,
-// equivalence reduction.  CUDA lives only behind this file and kernels.cu.
+// equivalence reduction.  CUDA lives only behind this file, kernels.cu, comm.cpp and jit.cpp.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <complex>
@@ -18,19 +19,7 @@
 #include "../host/util/phase.hpp"
 #include "kernels.hpp"
 #include "planner.hpp"
-
-struct qsx_unitary {
-    int      device   = 0;
-    int      n        = 0;
-    uint64_t col0     = 0;
-    uint64_t ncols    = 0;
-    double2* data     = nullptr;
-    // set_identity is lazy: the first sweep of the next gate stream synthesises the identity instead of
-    // reading it (saves one write and one read pass); anything else that looks at the data writes it first
-    bool     lazy_identity = false;
-    uint64_t elems() const { return (1ull << n) * ncols; }
-    uint64_t bytes() const { return elems() * 16ull; }
-};
+#include "runtime_internal.hpp"
 
 struct qsx_plan {
     qsx::Plan plan;
@@ -38,9 +27,23 @@ struct qsx_plan {
     std::map<int, unsigned char*> device_blob;  // device id -> uploaded program
 };
 
-namespace {
+namespace qsx {
 
 thread_local std::string g_err;
+
+namespace {
+std::mutex g_mu;
+std::map<int, DeviceCtx> g_ctx;  // (node-based: the contexts never move)
+}  // namespace
+
+int device_count_nothrow() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
 
 int fail(int code, std::string msg) {
     g_err = std::move(msg);
@@ -52,40 +55,6 @@ int cuda_fail(cudaError_t e, char const* what) {
     std::string msg = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
     if (e == cudaErrorMemoryAllocation) return fail(QSX_ERR_OOM, msg);
     return fail(QSX_ERR_CUDA, msg);
-}
-
-#define QSX_CUDA(call)                                          \
-    do {                                                        \
-        cudaError_t const e__ = (call);                         \
-        if (e__ != cudaSuccess) return cuda_fail(e__, #call);   \
-    } while (0)
-
-struct DeviceCtx {
-    cudaStream_t stream   = nullptr;
-    double*      scratch  = nullptr;  // equiv partials + 8 outputs
-    double*      host8    = nullptr;  // pinned
-    cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
-    // one-shot programs of qsx_apply_gates*: a grow-only device buffer (reuse is ordered by the
-    // stream) fed from two pinned staging buffers (reuse is ordered by an event each)
-    unsigned char* prog_dev = nullptr;
-    size_t         prog_dev_cap = 0;
-    unsigned char* prog_pin[2] = {nullptr, nullptr};
-    size_t         prog_pin_cap[2] = {0, 0};
-    cudaEvent_t    prog_ev[2] = {nullptr, nullptr};
-    int            prog_slot = 0;
-};
-
-std::mutex g_mu;
-std::mutex g_prog_mu;  // guards the program staging state of every DeviceCtx (held for microseconds)
-std::map<int, DeviceCtx> g_ctx;
-
-int device_count_nothrow() {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-    }
-    return n;
 }
 
 int get_ctx(int device, DeviceCtx** out) {
@@ -100,36 +69,56 @@ int get_ctx(int device, DeviceCtx** out) {
     if (n == 0) return fail(QSX_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
     if (device < 0 || device >= n) return fail(QSX_ERR_BAD_ARG, "device index out of range");
     QSX_CUDA(cudaSetDevice(device));
-    DeviceCtx c;
-    QSX_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    QSX_CUDA(cudaMalloc(&c.scratch, (qsx::equiv_partials_doubles() + 8) * sizeof(double)));
-    QSX_CUDA(cudaMallocHost(&c.host8, 8 * sizeof(double)));
-    QSX_CUDA(cudaEventCreate(&c.ev0));
-    QSX_CUDA(cudaEventCreate(&c.ev1));
-    auto ins = g_ctx.emplace(device, c);
-    *out     = &ins.first->second;
+    // created piece by piece; whatever exists is released again when a later piece fails
+    cudaStream_t stream = nullptr;
+    double *scratch = nullptr, *host8 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaError_t e   = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&scratch, (equiv_partials_doubles() * kMaxLocalShards + 8) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMallocHost(&host8, 8 * sizeof(double));
+    if (e == cudaSuccess) e = cudaEventCreate(&ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ev1);
+    if (e != cudaSuccess) {
+        if (ev0 != nullptr) cudaEventDestroy(ev0);
+        if (host8 != nullptr) cudaFreeHost(host8);
+        if (scratch != nullptr) cudaFree(scratch);
+        if (stream != nullptr) cudaStreamDestroy(stream);
+        return cuda_fail(e, "creating the device context");
+    }
+    DeviceCtx& c = g_ctx[device];
+    c.device = device, c.stream = stream, c.scratch = scratch, c.host8 = host8, c.ev0 = ev0, c.ev1 = ev1;
+    *out = &c;
     return QSX_OK;
 }
 
 int materialize(qsx_unitary* u, DeviceCtx* c) {
     if (!u->lazy_identity) return QSX_OK;
-    QSX_CUDA(qsx::launch_set_identity(u->data, u->n, u->col0, u->ncols, c->stream));
+    QSX_CUDA(launch_set_identity(u->data, u->n, u->col0, u->ncols, c->stream));
     u->lazy_identity = false;
     return QSX_OK;
 }
-int materialize(const qsx_unitary* u, DeviceCtx* c) { return materialize(const_cast<qsx_unitary*>(u), c); }
 
+}  // namespace qsx
+
+namespace {
+using qsx::cuda_fail;
+using qsx::DeviceCtx;
+using qsx::fail;
+using qsx::get_ctx;
+int materialize_(qsx_unitary* u, DeviceCtx* c) { return qsx::materialize(u, c); }
+int materialize_(const qsx_unitary* u, DeviceCtx* c) { return qsx::materialize(const_cast<qsx_unitary*>(u), c); }
+std::mutex g_prog_mu;  // (kept for the staging state's own consistency; the device mutex is held around it)
 }  // namespace
 
 extern "C" {
 
 int qsx_abi_version(void) { return QSX_ABI_VERSION; }
 
-const char* qsx_last_error(void) { return g_err.c_str(); }
+const char* qsx_last_error(void) { return qsx::g_err.c_str(); }
 
 int qsx_device_count(int* count) {
     if (count == nullptr) return fail(QSX_ERR_BAD_ARG, "null count");
-    *count = device_count_nothrow();
+    *count = qsx::device_count_nothrow();
     return QSX_OK;
 }
 
@@ -182,12 +171,23 @@ int qsx_unitary_set_identity(qsx_unitary* u) {
 
 int qsx_unitary_clone(const qsx_unitary* u, qsx_unitary** out) {
     if (u == nullptr || out == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
-    if (int rc = qsx_unitary_create(u->device, u->n, u->col0, u->ncols, out)) return rc;
+    *out = nullptr;
+    qsx_unitary* copy = nullptr;
+    if (int rc = qsx_unitary_create(u->device, u->n, u->col0, u->ncols, &copy)) return rc;
     DeviceCtx* c = nullptr;
-    if (int rc = get_ctx(u->device, &c)) return rc;
-    if (int rc = materialize(u, c)) return rc;
-    QSX_CUDA(cudaMemcpyAsync((*out)->data, u->data, u->bytes(), cudaMemcpyDeviceToDevice, c->stream));
-    QSX_CUDA(cudaStreamSynchronize(c->stream));
+    int rc       = get_ctx(u->device, &c);
+    if (rc == QSX_OK) rc = materialize_(u, c);
+    if (rc == QSX_OK) {
+        cudaError_t e = cudaMemcpyAsync(copy->data, u->data, u->bytes(), cudaMemcpyDeviceToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync(clone)");
+    }
+    if (rc != QSX_OK) {
+        std::string const keep = qsx_last_error();
+        qsx_unitary_destroy(copy);
+        return fail(rc, keep);
+    }
+    *out = copy;
     return QSX_OK;
 }
 
@@ -209,7 +209,7 @@ int qsx_unitary_get_info(const qsx_unitary* u, qsx_unitary_info* info) {
     if (u->lazy_identity) {  // the raw pointer is handed out: the data must be there
         DeviceCtx* c = nullptr;
         if (int rc = get_ctx(u->device, &c)) return rc;
-        if (int rc = materialize(u, c)) return rc;
+        if (int rc = materialize_(u, c)) return rc;
     }
     info->n_qubits = u->n;
     info->device   = u->device;
@@ -223,11 +223,11 @@ int qsx_unitary_get_info(const qsx_unitary* u, qsx_unitary_info* info) {
 
 int qsx_unitary_upload(qsx_unitary* u, uint64_t row0, uint64_t nrows, const double* host) {
     if (u == nullptr || host == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
-    if (row0 + nrows > (1ull << u->n)) return fail(QSX_ERR_BAD_ARG, "row range out of bounds");
+    if (nrows > (1ull << u->n) || row0 > (1ull << u->n) - nrows) return fail(QSX_ERR_BAD_ARG, "row range out of bounds");
     DeviceCtx* c = nullptr;
     if (int rc = get_ctx(u->device, &c)) return rc;
     if (row0 == 0 && nrows == (1ull << u->n)) u->lazy_identity = false;  // everything is overwritten
-    if (int rc = materialize(u, c)) return rc;
+    if (int rc = materialize_(u, c)) return rc;
     QSX_CUDA(cudaMemcpyAsync(u->data + row0 * u->ncols, host, nrows * u->ncols * 16ull, cudaMemcpyHostToDevice, c->stream));
     QSX_CUDA(cudaStreamSynchronize(c->stream));
     return QSX_OK;
@@ -235,13 +235,49 @@ int qsx_unitary_upload(qsx_unitary* u, uint64_t row0, uint64_t nrows, const doub
 
 int qsx_unitary_download(const qsx_unitary* u, uint64_t row0, uint64_t nrows, double* host) {
     if (u == nullptr || host == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
-    if (row0 + nrows > (1ull << u->n)) return fail(QSX_ERR_BAD_ARG, "row range out of bounds");
+    if (nrows > (1ull << u->n) || row0 > (1ull << u->n) - nrows) return fail(QSX_ERR_BAD_ARG, "row range out of bounds");
     DeviceCtx* c = nullptr;
     if (int rc = get_ctx(u->device, &c)) return rc;
-    if (int rc = materialize(u, c)) return rc;
+    if (int rc = materialize_(u, c)) return rc;
     QSX_CUDA(cudaMemcpyAsync(host, u->data + row0 * u->ncols, nrows * u->ncols * 16ull, cudaMemcpyDeviceToHost, c->stream));
     QSX_CUDA(cudaStreamSynchronize(c->stream));
     return QSX_OK;
+}
+
+namespace {
+int copy_block(const qsx_unitary* u, uint64_t row0, uint64_t nrows, uint64_t c0, uint64_t nc, double* host, uint64_t host_ld,
+               bool to_host) {
+    if (u == nullptr || host == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    if (nrows > (1ull << u->n) || row0 > (1ull << u->n) - nrows) return fail(QSX_ERR_BAD_ARG, "row range out of bounds");
+    if (nc > u->ncols || c0 > u->ncols - nc) return fail(QSX_ERR_BAD_ARG, "column range out of bounds (columns are shard-local)");
+    if (host_ld == 0) host_ld = nc;
+    if (host_ld < nc) return fail(QSX_ERR_BAD_ARG, "host leading dimension smaller than the block width");
+    if (nrows == 0 || nc == 0) return QSX_OK;
+    DeviceCtx* c = nullptr;
+    if (int rc = get_ctx(u->device, &c)) return rc;
+    if (to_host || !(nrows == (1ull << u->n) && nc == u->ncols)) {
+        if (int rc = materialize_(u, c)) return rc;
+    } else {
+        const_cast<qsx_unitary*>(u)->lazy_identity = false;  // everything is overwritten
+    }
+    double2* const dev = u->data + row0 * u->ncols + c0;
+    if (to_host)
+        QSX_CUDA(cudaMemcpy2DAsync(host, host_ld * 16ull, dev, u->ncols * 16ull, nc * 16ull, nrows, cudaMemcpyDeviceToHost, c->stream));
+    else
+        QSX_CUDA(cudaMemcpy2DAsync(dev, u->ncols * 16ull, host, host_ld * 16ull, nc * 16ull, nrows, cudaMemcpyHostToDevice, c->stream));
+    QSX_CUDA(cudaStreamSynchronize(c->stream));
+    return QSX_OK;
+}
+}  // namespace
+
+int qsx_unitary_download_block(const qsx_unitary* u, uint64_t row0, uint64_t nrows, uint64_t c0, uint64_t nc, double* host,
+                               uint64_t host_ld) {
+    return copy_block(u, row0, nrows, c0, nc, host, host_ld, true);
+}
+
+int qsx_unitary_upload_block(qsx_unitary* u, uint64_t row0, uint64_t nrows, uint64_t c0, uint64_t nc, const double* host,
+                             uint64_t host_ld) {
+    return copy_block(u, row0, nrows, c0, nc, const_cast<double*>(host), host_ld, false);
 }
 
 // ---- construction -----------------------------------------------------------------------
@@ -314,7 +350,7 @@ int run_sweeps(qsx::Plan const& pl, qsx_unitary* u, DeviceCtx* c, unsigned char*
             identity_per_block = true;
             u->lazy_identity   = false;
         } else {
-            if (int rc = materialize(u, c)) return rc;
+            if (int rc = materialize_(u, c)) return rc;
             ++launches;  // (the identity kernel counts as one of this run's launches)
         }
     }
@@ -372,14 +408,19 @@ int qsx_plan_run(const qsx_plan* cplan, qsx_unitary* u, qsx_stop_fn should_stop,
     DeviceCtx* c = nullptr;
     if (int rc = get_ctx(u->device, &c)) return rc;
     if (pl.sweeps.empty()) return QSX_OK;
+    std::lock_guard<std::mutex> dev_lock(c->mu);
     unsigned char* dblob = nullptr;
     {
         std::lock_guard<std::mutex> lk(plan->mu);
         auto it = plan->device_blob.find(u->device);
         if (it == plan->device_blob.end()) {
             QSX_CUDA(cudaMalloc(&dblob, pl.blob.size()));
-            QSX_CUDA(cudaMemcpyAsync(dblob, pl.blob.data(), pl.blob.size(), cudaMemcpyHostToDevice, c->stream));
-            QSX_CUDA(cudaStreamSynchronize(c->stream));  // pl.blob is pageable
+            cudaError_t e = cudaMemcpyAsync(dblob, pl.blob.data(), pl.blob.size(), cudaMemcpyHostToDevice, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // pl.blob is pageable
+            if (e != cudaSuccess) {
+                cudaFree(dblob);
+                return cuda_fail(e, "uploading the plan");
+            }
             plan->device_blob.emplace(u->device, dblob);
         } else {
             dblob = it->second;
@@ -436,6 +477,8 @@ int apply_impl(qsx_unitary* u, const qsx_gate* gates, size_t n_gates, const qsx_
     DeviceCtx* c = nullptr;
     if (int e = get_ctx(u->device, &c)) return e;
     if (pl.sweeps.empty()) return QSX_OK;
+    // the program buffer, the event pair and the stream order are per device: one host thread at a time
+    std::lock_guard<std::mutex> dev_lock(c->mu);
     unsigned char* dblob = nullptr;
     if (int e = stage_programs(c, pl, &dblob)) return e;
     return run_sweeps(pl, u, c, dblob, should_stop, stop_arg, flags, stats);
@@ -454,21 +497,79 @@ int qsx_apply_gates_async(qsx_unitary* u, const qsx_gate* gates, size_t n_gates,
 
 // ---- verification -----------------------------------------------------------------------
 
+namespace {
+// Enqueues the fused reduction of every shard pair (concurrently on all devices involved), combines the per-device
+// results with ONE all-reduce of 8 doubles when `combine` is set, and reads 64 bytes back from the first device.
+int equiv_impl(const qsx_unitary* const* a, const qsx_unitary* const* b, int n_shards, bool combine, double out[8]) {
+    if (a == nullptr || b == nullptr || out == nullptr || n_shards < 1) return fail(QSX_ERR_BAD_ARG, "null argument");
+    for (int k = 0; k < n_shards; ++k) {
+        if (a[k] == nullptr || b[k] == nullptr) return fail(QSX_ERR_BAD_ARG, "null shard");
+        if (a[k]->n != b[k]->n || a[k]->ncols != b[k]->ncols || a[k]->col0 != b[k]->col0 || a[k]->n != a[0]->n)
+            return fail(QSX_ERR_SHAPE, "the two tensors should have the same shape");
+        if (a[k]->device != b[k]->device) return fail(QSX_ERR_SHAPE, "both shards of a pair must live on the same device");
+    }
+    // devices in order of first appearance
+    std::vector<DeviceCtx*> ctx;
+    std::vector<int> blocks_used;  // per device: partial blocks filled so far
+    std::vector<int> local_pairs;
+    std::vector<int> dev_of((size_t)n_shards, -1);
+    for (int k = 0; k < n_shards; ++k) {
+        size_t d = 0;
+        while (d < ctx.size() && ctx[d]->device != a[k]->device) ++d;
+        if (d == ctx.size()) {
+            DeviceCtx* c = nullptr;
+            if (int rc = get_ctx(a[k]->device, &c)) return rc;
+            ctx.push_back(c), blocks_used.push_back(0), local_pairs.push_back(0);
+        }
+        dev_of[(size_t)k] = (int)d;
+        if (++local_pairs[d] > qsx::kMaxLocalShards) return fail(QSX_ERR_BAD_ARG, "too many shard pairs on one device");
+    }
+    // lock the devices in ascending id order (no lock-order inversion between concurrent callers)
+    std::vector<DeviceCtx*> by_id = ctx;
+    std::sort(by_id.begin(), by_id.end(), [](DeviceCtx* x, DeviceCtx* y) { return x->device < y->device; });
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (DeviceCtx* c : by_id) locks.emplace_back(c->mu);
+    size_t const slot = qsx::equiv_partials_doubles();
+    for (int k = 0; k < n_shards; ++k) {
+        size_t const d = (size_t)dev_of[(size_t)k];
+        DeviceCtx* c   = ctx[d];
+        QSX_CUDA(cudaSetDevice(c->device));
+        if (int rc = materialize_(a[k], c)) return rc;
+        if (int rc = materialize_(b[k], c)) return rc;
+        int nb = 0;
+        QSX_CUDA(qsx::launch_equiv_partials(a[k]->data, b[k]->data, a[k]->elems(), c->scratch + (size_t)blocks_used[d] * 16, &nb, c->stream));
+        blocks_used[d] += nb;
+    }
+    std::vector<double*> out8(ctx.size(), nullptr);
+    for (size_t d = 0; d < ctx.size(); ++d) {
+        DeviceCtx* c = ctx[d];
+        out8[d]      = c->scratch + slot * qsx::kMaxLocalShards;
+        QSX_CUDA(cudaSetDevice(c->device));
+        QSX_CUDA(qsx::launch_equiv_finish(c->scratch, blocks_used[d], out8[d], c->stream));
+    }
+    if (combine)
+        if (int rc = qsx::comm_allreduce8(ctx.data(), out8.data(), (int)ctx.size())) return rc;
+    DeviceCtx* c0 = ctx[0];
+    QSX_CUDA(cudaSetDevice(c0->device));
+    if (!combine && ctx.size() > 1) return fail(QSX_ERR_BAD_ARG, "qsx_equiv_partial takes one shard pair");
+    QSX_CUDA(cudaMemcpyAsync(c0->host8, out8[0], 8 * sizeof(double), cudaMemcpyDeviceToHost, c0->stream));
+    // the other devices' streams carry their half of the collective: drain them too before the scratch is reused
+    for (size_t d = ctx.size(); d-- > 0;) {
+        QSX_CUDA(cudaSetDevice(ctx[d]->device));
+        QSX_CUDA(cudaStreamSynchronize(ctx[d]->stream));
+    }
+    std::memcpy(out, c0->host8, 8 * sizeof(double));
+    return QSX_OK;
+}
+}  // namespace
+
 int qsx_equiv_partial(const qsx_unitary* a, const qsx_unitary* b, double sums[8]) {
     if (a == nullptr || b == nullptr || sums == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
-    if (a->n != b->n || a->ncols != b->ncols || a->col0 != b->col0)
-        return fail(QSX_ERR_SHAPE, "the two tensors should have the same shape");
-    if (a->device != b->device) return fail(QSX_ERR_SHAPE, "both shards must live on the same device");
-    DeviceCtx* c = nullptr;
-    if (int rc = get_ctx(a->device, &c)) return rc;
-    if (int rc = materialize(a, c)) return rc;
-    if (int rc = materialize(b, c)) return rc;
-    double* const out8 = c->scratch + qsx::equiv_partials_doubles();
-    QSX_CUDA(qsx::launch_equiv(a->data, b->data, a->elems(), c->scratch, out8, c->stream));
-    QSX_CUDA(cudaMemcpyAsync(c->host8, out8, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    QSX_CUDA(cudaStreamSynchronize(c->stream));
-    std::memcpy(sums, c->host8, 8 * sizeof(double));
-    return QSX_OK;
+    return equiv_impl(&a, &b, 1, false, sums);
+}
+
+int qsx_equiv_reduce(const qsx_unitary* const* a, const qsx_unitary* const* b, int n_shards, double sums[8]) {
+    return equiv_impl(a, b, n_shards, true, sums);
 }
 
 int qsx_equiv_finish(const double sums[8], double eps, int strict, qsx_equiv_result* out) {
@@ -533,7 +634,7 @@ int qsx_unitary_adjoint_sharded(qsx_unitary* const* shards, int n_shards) {
     // everything queued on any shard must be done before a peer touches it
     for (int k = 0; k < n_shards; ++k) {
         QSX_CUDA(cudaSetDevice(shards[k]->device));
-        if (int rc = materialize(shards[k], ctx[(size_t)k])) return rc;
+        if (int rc = materialize_(shards[k], ctx[(size_t)k])) return rc;
         QSX_CUDA(cudaStreamSynchronize(ctx[(size_t)k]->stream));
     }
     for (int i = 0; i < n_shards; ++i) {

@@ -23,6 +23,7 @@ def lib() -> C.CDLL:
         vp, sz = C.c_void_p, C.c_size_t
         L.qsxh_last_error.restype = C.c_char_p
         sig = {
+            "qsxh_set_process_shard": [C.c_int, C.c_int, C.c_int],
             "qsxh_circuit_new": [sz, C.POINTER(vp)],
             "qsxh_circuit_from_qasm_text": [C.c_char_p, C.POINTER(vp)],
             "qsxh_circuit_from_qasm_file": [C.c_char_p, C.POINTER(vp)],

@@ -51,6 +51,12 @@ extern "C" {
 
 const char* qsxh_last_error(void) { return g_err.c_str(); }
 
+int qsxh_set_process_shard(int rank, int world, int device) {
+    if (world < 1 || rank < 0 || rank >= world || device < 0) return fail(QSX_ERR_BAD_ARG, "bad rank / world / device");
+    qsyn::tensor::process_shard() = qsyn::tensor::ProcessShard{rank, world, device};
+    return QSX_OK;
+}
+
 int qsxh_circuit_new(size_t n_qubits, qsxh_circuit** out) {
     if (out == nullptr) return fail(QSX_ERR_BAD_ARG, "null out-pointer");
     *out = new qsxh_circuit{qsyn::qcir::QCir(n_qubits), std::nullopt};

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     L = Q.lib()
     for nm in sorted(names):
         assert hasattr(L, nm), f"libqsx.so does not export {nm}"
-    assert L.qsx_abi_version() == 1
+    assert L.qsx_abi_version() == 2
 
 
 def test_no_cpu_fallback_when_no_device():

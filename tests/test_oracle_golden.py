@@ -202,3 +202,15 @@ def test_c_restatement_matches_numpy():
         if abs(np.sum(want)) > 1e-6:
             assert cos == pytest.approx(1.0, abs=1e-12)
             assert norm == pytest.approx(0.75, rel=1e-9) and ph == pytest.approx(0.3, abs=1e-9)
+
+
+def test_column_block_form_of_the_literal_algorithm():
+    """to_tensor_literal_columns (the bounded CPU-baseline sample of bench.py at n >= 14) is the same per-gate
+    tensordot loop with the input axes collapsed: bit-identical to the row form on any column block."""
+    from tests.test_abi_cpu import _rand_circuit
+    for n, g, seed, col0, ncols in [(3, 40, 1, 0, 8), (6, 120, 2, 16, 16), (7, 150, 3, 100, 28)]:
+        qc = _rand_circuit(n, g, seed)
+        want = O.to_matrix_rowform(qc)[:, col0:col0 + ncols]
+        got = O.to_tensor_literal_columns(qc, col0, ncols)
+        assert np.array_equal(got, want)
+        assert np.allclose(O.qc2ts(qc)[:, col0:col0 + ncols], got, rtol=0, atol=1e-14)
