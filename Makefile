@@ -15,7 +15,8 @@ OBJDIR    := build/obj
 
 LIBQSX    := $(LIBDIR)/libqsx.so
 OBJS      := $(OBJDIR)/kernels.o $(OBJDIR)/runtime.o $(OBJDIR)/planner.o $(OBJDIR)/planner_lower.o \
-             $(OBJDIR)/planner_schedule.o $(OBJDIR)/planner_emit.o $(OBJDIR)/comm.o
+             $(OBJDIR)/planner_schedule.o $(OBJDIR)/planner_emit.o $(OBJDIR)/comm.o \
+             $(OBJDIR)/jit.o $(OBJDIR)/jit_codegen.o
 CUDAINC   := -I/usr/local/cuda/include
 
 HOST      := qsyn_b200/host

@@ -176,13 +176,20 @@ def measure(c, args, workload, steps, warmup, e2e_steps, main_line):
     dim = 2**n
     col0, ncols = sharding.shard_columns(n, c.rank, c.world)
     opt = Q.PlanOptions(max_ops_per_sweep=args.cap, tile_qubits=args.tile, reg_qubits=args.reg, log2_tile_cols=args.log2w,
-                        dense_block=args.dense, l2_block_mib=args.l2_block)
+                        dense_block=args.dense, l2_block_mib=args.l2_block, jit=args.jit)
     ua = Q.Unitary(n, c.local, col0, ncols)
     ub = Q.Unitary(n, c.local, col0, ncols)
     plan_a = Q.Plan(n, ncols, gs_a, opt)
     plan_b = Q.Plan(n, ncols, gs_b, opt)
     st_a, st_b = plan_a.stats(), plan_b.stats()
-    launches = {"n": 0}
+    launches = {"n": 0, "jit": 0}
+    # "inputs resident" includes the specialised kernels of the schedules (qsx_plan_options.jit): compiled before the
+    # timed region, like the schedules themselves; the cold compile time is reported under `jit`
+    jit0, t0 = abi.jit_stats(), time.perf_counter()
+    if args.jit >= 0:
+        plan_a.compile(True)
+        plan_b.compile(True)
+    jit_cold_s = time.perf_counter() - t0
 
     def step_resident():
         """inputs resident: prebuilt schedules, device-side identity, async sweeps, ONE reduce call."""
@@ -192,6 +199,7 @@ def measure(c, args, workload, steps, warmup, e2e_steps, main_line):
         rb = plan_b.run(ub, flags=abi.QSX_RUN_ASYNC)
         sums = Q.equiv_reduce([ua], [ub])  # partial + finish kernels, ncclAllReduce(8 doubles) when world > 1, 64 B read-back
         launches["n"] += ra.launches + rb.launches + 2  # (the identity is synthesised by the first sweep of each operand)
+        launches["jit"] += ra.jit_launches + rb.jit_launches
         return Q.equiv_finish(sums, 1e-6, False)
 
     def step_e2e():
@@ -228,7 +236,7 @@ def measure(c, args, workload, steps, warmup, e2e_steps, main_line):
     barrier(c)
     ms_step = max_over_ranks(c, ev0.elapsed_time(ev1)) / steps
     clocks = sampler.stop() if (c.rank == 0 and main_line) else None
-    gpu_launches = launches["n"]
+    gpu_launches, jit_launches = launches["n"], launches["jit"]
 
     # ---- dominant kernel, timed live with CUDA events around the sweep launches only ----
     ua.set_identity()
@@ -308,12 +316,19 @@ def measure(c, args, workload, steps, warmup, e2e_steps, main_line):
             "equiv_ms": round(equiv_ms, 4),
             "equiv_GBps": round(2 * 16 * dim * dim / (equiv_ms * 1e-3) / 1e9, 1),
             "gpu_launches": gpu_launches,
-            "roofline": {"bound": "hbm", "kernel": ("dense_kernel<%d>" % args.dense) if args.dense else ("sweep_kernel<%d, *>" % args.reg),
+            "roofline": {"bound": "hbm", "kernel": ("dense_kernel<%d>" % args.dense) if args.dense else (("specialised sweep (NVRTC, jit_codegen.cpp), R=%d" if jit_launches else "sweep_kernel<%d, *>") % args.reg),
                          "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": st_a.alg_bytes_per_run / max(n_launch, 1),
                          "launches": n_launch, "avg_launch_us": round(sweep_ms * 1e3 / max(n_launch, 1), 2)},
         }
+        js = abi.jit_stats()
+        out["jit"] = {"option": args.jit, "available": bool(js.available), "specialised_launches_in_timed_region": jit_launches,
+                      "kernels_compiled": int(js.compiled - jit0.compiled), "cold_compile_wall_s": round(jit_cold_s, 3),
+                      "compiler_threads": js.workers, "compile_cpu_s": round(js.compile_seconds - jit0.compile_seconds, 2),
+                      "failed": int(js.failed),
+                      "note": "sweep programs are compiled once (NVRTC, all host cores) and cached by content; a program whose kernel is not "
+                              "ready yet runs in the interpreter, so nothing ever waits for the compiler outside this set-up step"}
         if clocks is not None:
             out["clocks"] = clocks
         if e2e_s is not None:
@@ -351,7 +366,7 @@ def run_ours(args):
         r = measure(c, args, w, 3 if few else 20, 3, 2 if few else 10, False)
         if r is not None:
             extra[w] = {k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "config", "construct_ms_A", "equiv_ms",
-                                          "gpu_launches", "roofline", "roofline_fp64", "e2e") if k in r}
+                                          "gpu_launches", "roofline", "roofline_fp64", "e2e", "jit") if k in r}
     if c.rank == 0:
         if extra:
             out["extra"] = extra
@@ -556,6 +571,7 @@ def main():
     ap.add_argument("--log2w", type=int, default=3)
     ap.add_argument("--dense", type=int, default=0, help="fold the gate stream into dense k-qubit blocks on the FP64 tensor pipe (3..5)")
     ap.add_argument("--l2-block", type=int, default=0, help="column blocking through the L2 in MiB (0: cost model decides, -1: off)")
+    ap.add_argument("--jit", type=int, default=0, help="specialised sweeps: 0 library default (n >= 13), 1 always, -1 never (interpreter only)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

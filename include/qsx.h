@@ -62,6 +62,9 @@ int qsx_device_count(int* count);
 /* the cudaStream_t (as void*) all work for `device` is enqueued on */
 int qsx_device_stream(int device, void** stream);
 int qsx_device_synchronize(int device);
+/* Shard buffers of destroyed unitaries are parked per device for reuse (up to QSX_POOL_FRACTION, default 0.45, of the
+ * device memory; an allocation that fails releases them and retries).  This returns them to the driver now. */
+int qsx_device_trim(int device);
 
 /* ---- storage: replaces xt::xarray<complex<double>> inside Tensor<DT> (tensor.hpp:38,144) -------- */
 typedef struct qsx_unitary_info {
@@ -134,7 +137,11 @@ typedef struct qsx_plan_options {
                               block from HBM and only the last write has to reach it.  0 (default): 64 MiB when the
                               cost model says the plan is memory-bound (a few micro-ops per sweep at most);
                               < 0: never; > 0: always, with this block size                                    */
-    int32_t reserved[1];
+    int32_t jit;           /* specialised sweeps: the program of a sweep is compiled at run time (NVRTC, all host cores, cached
+                              by content) into straight-line code and replaces the interpreter once it is ready.
+                              0 (default): on for n >= 13, where a sweep runs for milliseconds (never blocks: a sweep whose
+                              kernel is still compiling is interpreted); 1: on for any n; 2: on and WAIT for the compiler
+                              (first use of a program costs ~0.1 s per sweep / host cores); < 0: always interpret      */
 } qsx_plan_options;
 
 typedef struct qsx_plan_stats {
@@ -160,6 +167,23 @@ int qsx_plan_get_stats(const qsx_plan* plan, qsx_plan_stats* stats);
  * *needed receives the size required including the NUL. */
 int qsx_plan_dump(const qsx_plan* plan, char* buf, size_t buf_size, size_t* needed);
 
+/* Requests the specialised kernels of every sweep of the plan (see qsx_plan_options.jit); wait != 0 blocks until the
+ * compiler threads are done with them.  Returns QSX_OK also when run-time compilation is unavailable on this host
+ * (no libnvrtc): the plan then simply keeps running in the interpreter. */
+int qsx_plan_compile(const qsx_plan* plan, int wait);
+
+typedef struct qsx_jit_stats {
+    uint64_t requested;       /* sweep programs looked up                          */
+    uint64_t cache_hits;      /* ... found in the cache (compiled or in flight)    */
+    uint64_t compiled;        /* kernels compiled so far                           */
+    uint64_t failed;          /* programs that could not be compiled or loaded     */
+    uint64_t launches;        /* launches of specialised kernels                   */
+    double   compile_seconds; /* compiler time summed over the worker threads      */
+    int32_t  workers;         /* compiler threads                                  */
+    int32_t  available;       /* 0: libnvrtc / driver entry points missing         */
+} qsx_jit_stats;
+int qsx_jit_get_stats(qsx_jit_stats* stats);
+
 typedef int (*qsx_stop_fn)(void* arg); /* mirrors `extern bool stop_requested()` (qcir_to_tensor.cpp:20) */
 
 #define QSX_RUN_ASYNC 1u /* do not synchronise at the end (for event timing on qsx_device_stream) */
@@ -167,14 +191,19 @@ typedef int (*qsx_stop_fn)(void* arg); /* mirrors `extern bool stop_requested()`
 typedef struct qsx_run_stats {
     uint64_t launches;   /* kernels launched by this call        */
     double   device_ms;  /* CUDA-event time of the launches (0 when QSX_RUN_ASYNC) */
+    uint64_t jit_launches; /* ... of which specialised (run-time compiled) sweeps */
+    int32_t  plan_cache_hit; /* qsx_apply_gates*: the schedule of this exact gate stream was reused */
+    int32_t  reserved;
 } qsx_run_stats;
 
 /* U <- plan(U) in place.  should_stop (nullable) is polled between sweeps; when it
  * returns non-zero the call drains the stream and returns QSX_ERR_INTERRUPTED. */
 int qsx_plan_run(const qsx_plan* plan, qsx_unitary* u, qsx_stop_fn should_stop, void* stop_arg,
                  uint32_t flags, qsx_run_stats* stats);
-/* One-shot: schedule the stream, stage its programs (pinned staging, no stream synchronisation) and
- * run it.  This is what to_tensor(QCir) calls (qcir_to_tensor.cpp:143-214). */
+/* One-shot: schedule the stream, upload its programs and run it.  This is what to_tensor(QCir) calls
+ * (qcir_to_tensor.cpp:143-214).  The last few schedules are kept (keyed by geometry, options and every gate incl. its
+ * matrix; QSX_PLAN_CACHE entries, default 8): converting the same circuit again skips the scheduler and finds its
+ * programs on the device and its specialised kernels compiled. */
 int qsx_apply_gates(qsx_unitary* u, const qsx_gate* gates, size_t n_gates, const qsx_plan_options* opt,
                     qsx_stop_fn should_stop, void* stop_arg, qsx_run_stats* stats);
 /* Same, but returns as soon as the sweeps are enqueued on the device's stream: the host can schedule

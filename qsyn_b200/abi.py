@@ -56,7 +56,7 @@ class PlanOptions(C.Structure):
                 ("lookahead", C.c_int32), ("dense_block", C.c_int32), ("no_perm_folding", C.c_int32), ("min_tail_ops", C.c_int32),
                 ("search", C.c_int32), ("no_diag_conjugation", C.c_int32),
                 ("no_1q_fusion", C.c_int32), ("stage_search", C.c_int32),
-                ("l2_block_mib", C.c_int32), ("reserved", C.c_int32 * 1)]
+                ("l2_block_mib", C.c_int32), ("jit", C.c_int32)]
 
     def __init__(self, fuse: int = 1, **kw):
         super().__init__()
@@ -74,8 +74,14 @@ class PlanStats(C.Structure):
                 ("plan_host_ms", C.c_double)]
 
 
+class JitStats(C.Structure):
+    _fields_ = [("requested", C.c_uint64), ("cache_hits", C.c_uint64), ("compiled", C.c_uint64), ("failed", C.c_uint64),
+                ("launches", C.c_uint64), ("compile_seconds", C.c_double), ("workers", C.c_int32), ("available", C.c_int32)]
+
+
 class RunStats(C.Structure):
-    _fields_ = [("launches", C.c_uint64), ("device_ms", C.c_double)]
+    _fields_ = [("launches", C.c_uint64), ("device_ms", C.c_double), ("jit_launches", C.c_uint64), ("plan_cache_hit", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class UnitaryInfo(C.Structure):
@@ -99,6 +105,7 @@ def _declare(L: C.CDLL) -> None:
         "qsx_device_count": [C.POINTER(C.c_int)],
         "qsx_device_stream": [i32, C.POINTER(vp)],
         "qsx_device_synchronize": [i32],
+        "qsx_device_trim": [i32],
         "qsx_unitary_create": [i32, i32, u64, u64, C.POINTER(vp)],
         "qsx_unitary_set_identity": [vp],
         "qsx_unitary_clone": [vp, C.POINTER(vp)],
@@ -114,6 +121,8 @@ def _declare(L: C.CDLL) -> None:
         "qsx_apply_gates": [vp, C.POINTER(GateStruct), C.c_size_t, C.POINTER(PlanOptions), STOP_FN, vp,
                             C.POINTER(RunStats)],
         "qsx_apply_gates_async": [vp, C.POINTER(GateStruct), C.c_size_t, C.POINTER(PlanOptions), C.POINTER(RunStats)],
+        "qsx_plan_compile": [vp, i32],
+        "qsx_jit_get_stats": [C.POINTER(JitStats)],
         "qsx_init": [i32],
         "qsx_shutdown": [],
         "qsx_unitary_download_block": [vp, u64, u64, u64, u64, dp, u64],
@@ -193,6 +202,10 @@ class Plan:
         cb = STOP_FN(lambda _arg: int(bool(should_stop()))) if should_stop is not None else C.cast(None, STOP_FN)
         _check(lib().qsx_plan_run(self._h, u._h, cb, None, flags, C.byref(st)))
         return st
+
+    def compile(self, wait: bool = True) -> None:
+        """qsx_plan_compile: request (and optionally wait for) the specialised kernels of every sweep."""
+        _check(lib().qsx_plan_compile(self._h, int(wait)))
 
     def close(self):
         if self._h:
@@ -328,6 +341,12 @@ def comm_info() -> tuple[int, int]:
     return w.value, v.value
 
 
+def jit_stats() -> JitStats:
+    s = JitStats()
+    _check(lib().qsx_jit_get_stats(C.byref(s)))
+    return s
+
+
 def init(n_gpus: int = 0) -> None:
     _check(lib().qsx_init(n_gpus))
 
@@ -347,6 +366,10 @@ def device_stream(device: int = 0) -> int:
     p = C.c_void_p()
     _check(lib().qsx_device_stream(device, C.byref(p)))
     return p.value
+
+
+def device_trim(device: int = 0) -> None:
+    _check(lib().qsx_device_trim(device))
 
 
 def device_synchronize(device: int = 0) -> None:

@@ -1,0 +1,401 @@
+// jit.cpp -- run-time compilation and cache of specialised sweep kernels.
+//
+// request(): hash the sweep program, look it up, on a miss generate CUDA C++ (jit_codegen.cpp) and queue it for a
+// pool of compiler threads (NVRTC -> sm_100a cubin; ~0.1 s per sweep, all host cores).  The caller never waits:
+// a sweep whose kernel is not ready yet runs in the interpreter (kernels.cu), the next run of the same program
+// (operand B of the job, the next column block, the next check of the same circuit) finds it compiled.
+// Compiled code is loaded with cuLibraryLoadData (context independent: one load serves every GPU of the process)
+// and launched with cuLaunchKernel; both come from the driver through cudaGetDriverEntryPoint, NVRTC through dlopen,
+// so libqsx.so links against neither and a host without them simply keeps interpreting.
+#include "jit.hpp"
+
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace qsx::jit {
+
+namespace {
+
+// ---- NVRTC (dlopen) ------------------------------------------------------------------------
+struct Nvrtc {
+    void* handle = nullptr;
+    nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*)                                               = nullptr;
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*)                                                                 = nullptr;
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char*)                                                                       = nullptr;
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*)                                                            = nullptr;
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char*)                                                                  = nullptr;
+    nvrtcResult (*DestroyProgram)(nvrtcProgram*)                                                                       = nullptr;
+    const char* (*GetErrorString)(nvrtcResult)                                                                         = nullptr;
+};
+
+// ---- driver entry points (cudaGetDriverEntryPoint) -------------------------------------------
+struct Driver {
+    CUresult (*LibraryLoadData)(CUlibrary*, const void*, CUjit_option*, void**, unsigned, CUlibraryOption*, void**, unsigned) = nullptr;
+    CUresult (*LibraryGetKernel)(CUkernel*, CUlibrary, const char*)                                                           = nullptr;
+    CUresult (*KernelSetAttribute)(CUfunction_attribute, int, CUkernel, CUdevice)                                             = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char**)                                                                        = nullptr;
+    CUresult (*CtxGetDevice)(CUdevice*)                                                                                       = nullptr;
+};
+
+enum State : int { kQueued = 0, kCompiling = 1, kReady = 2, kFailed = 3 };
+
+}  // namespace
+
+struct Kernel {
+    uint64_t h0 = 0, h1 = 0;
+    int R = 0, threads = 0;
+    std::string name, source;
+    std::atomic<int> state{kQueued};
+    std::vector<char> cubin;
+    // loading (first launch)
+    std::mutex load_mu;
+    CUlibrary lib  = nullptr;
+    CUkernel kern  = nullptr;
+    bool load_failed = false;
+    bool attr_set[64] = {};
+};
+
+namespace {
+
+// The synchronisation objects and containers the (detached, never-ending) compiler threads touch are allocated once
+// and never destroyed: a static destructor running at process exit while a worker waits on the condition variable
+// would block forever in pthread_cond_destroy.
+std::mutex& g_mu                   = *new std::mutex;  // cache, queue, stats
+std::condition_variable& g_cv_work = *new std::condition_variable;
+std::condition_variable& g_cv_done = *new std::condition_variable;
+auto& g_cache                      = *new std::map<std::pair<uint64_t, uint64_t>, std::unique_ptr<Kernel>>;
+std::deque<Kernel*>& g_queue       = *new std::deque<Kernel*>;
+bool g_pool_started = false;
+Stats g_stats;
+std::string& g_last_error = *new std::string;
+
+Nvrtc g_nvrtc;
+Driver g_drv;
+int g_avail = -1;  // -1 unknown, 0 no, 1 yes
+std::string& g_why = *new std::string;
+
+bool load_nvrtc(std::string& why) {
+    char const* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"};
+    for (char const* nm : names) {
+        g_nvrtc.handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+        if (g_nvrtc.handle != nullptr) break;
+    }
+    if (g_nvrtc.handle == nullptr) {
+        why = std::string("libnvrtc is not loadable: ") + dlerror();
+        return false;
+    }
+    bool ok  = true;
+    auto sym = [&](char const* n) {
+        void* p = dlsym(g_nvrtc.handle, n);
+        if (p == nullptr) ok = false;
+        return p;
+    };
+    g_nvrtc.CreateProgram     = reinterpret_cast<decltype(g_nvrtc.CreateProgram)>(sym("nvrtcCreateProgram"));
+    g_nvrtc.CompileProgram    = reinterpret_cast<decltype(g_nvrtc.CompileProgram)>(sym("nvrtcCompileProgram"));
+    g_nvrtc.GetCUBINSize      = reinterpret_cast<decltype(g_nvrtc.GetCUBINSize)>(sym("nvrtcGetCUBINSize"));
+    g_nvrtc.GetCUBIN          = reinterpret_cast<decltype(g_nvrtc.GetCUBIN)>(sym("nvrtcGetCUBIN"));
+    g_nvrtc.GetProgramLogSize = reinterpret_cast<decltype(g_nvrtc.GetProgramLogSize)>(sym("nvrtcGetProgramLogSize"));
+    g_nvrtc.GetProgramLog     = reinterpret_cast<decltype(g_nvrtc.GetProgramLog)>(sym("nvrtcGetProgramLog"));
+    g_nvrtc.DestroyProgram    = reinterpret_cast<decltype(g_nvrtc.DestroyProgram)>(sym("nvrtcDestroyProgram"));
+    g_nvrtc.GetErrorString    = reinterpret_cast<decltype(g_nvrtc.GetErrorString)>(sym("nvrtcGetErrorString"));
+    if (!ok) why = "libnvrtc lacks a required entry point";
+    return ok;
+}
+
+bool load_driver(std::string& why) {
+    bool ok  = true;
+    auto get = [&](char const* n) -> void* {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        cudaError_t const e = cudaGetDriverEntryPoint(n, &fn, cudaEnableDefault, &qr);
+        if (e != cudaSuccess || qr != cudaDriverEntryPointSuccess || fn == nullptr) {
+            cudaGetLastError();
+            ok = false;
+            if (why.empty()) why = std::string("the CUDA driver does not provide ") + n;
+            return nullptr;
+        }
+        return fn;
+    };
+    g_drv.LibraryLoadData    = reinterpret_cast<decltype(g_drv.LibraryLoadData)>(get("cuLibraryLoadData"));
+    g_drv.LibraryGetKernel   = reinterpret_cast<decltype(g_drv.LibraryGetKernel)>(get("cuLibraryGetKernel"));
+    g_drv.KernelSetAttribute = reinterpret_cast<decltype(g_drv.KernelSetAttribute)>(get("cuKernelSetAttribute"));
+    g_drv.LaunchKernel       = reinterpret_cast<decltype(g_drv.LaunchKernel)>(get("cuLaunchKernel"));
+    g_drv.GetErrorString     = reinterpret_cast<decltype(g_drv.GetErrorString)>(get("cuGetErrorString"));
+    g_drv.CtxGetDevice       = reinterpret_cast<decltype(g_drv.CtxGetDevice)>(get("cuCtxGetDevice"));
+    return ok;
+}
+
+// called with g_mu held
+bool available_locked(bool need_driver) {
+    if (g_avail < 0) {
+        char const* env = std::getenv("QSX_JIT");
+        if (env != nullptr && std::strcmp(env, "0") == 0) {
+            g_avail = 0, g_why = "disabled by QSX_JIT=0";
+        } else if (!load_nvrtc(g_why)) {
+            g_avail = 0;
+        } else {
+            g_avail = 1;
+        }
+    }
+    if (g_avail == 1 && need_driver && g_drv.LaunchKernel == nullptr) {
+        std::string why;
+        if (!load_driver(why)) {
+            g_avail = 0, g_why = why;
+        }
+    }
+    return g_avail == 1;
+}
+
+void hash_program(const unsigned char* p, size_t n, int R, int threads, uint64_t& h0, uint64_t& h1) {
+    // two independent 64-bit multiplicative hashes over 8-byte words (blobs are 16-byte multiples)
+    uint64_t a = 0x9e3779b97f4a7c15ull ^ (uint64_t)R, b = 0xc2b2ae3d27d4eb4full ^ ((uint64_t)threads << 8);
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t w;
+        std::memcpy(&w, p + i, 8);
+        a = (a ^ w) * 0x100000001b3ull;
+        a ^= a >> 29;
+        b = (b + w) * 0xff51afd7ed558ccdull;
+        b ^= b >> 32;
+    }
+    for (; i < n; ++i) {
+        a = (a ^ p[i]) * 0x100000001b3ull;
+        b = (b + p[i]) * 0xff51afd7ed558ccdull;
+    }
+    h0 = a ^ (uint64_t)n, h1 = b;
+}
+
+int min_ctas_for(int threads) {
+    if (char const* e = std::getenv("QSX_JIT_MINCTAS")) {
+        int const v = std::atoi(e);
+        if (v >= 1 && v <= 16) return v;
+    }
+    // 2^R elements of 2 doubles = 64 registers at R = 4; ~96 registers per thread leave room for temporaries
+    int const v = 65536 / (threads * 96);
+    return v < 1 ? 1 : (v > 8 ? 8 : v);
+}
+
+void compile_one(Kernel* k) {
+    auto const t0 = std::chrono::steady_clock::now();
+    nvrtcProgram prog = nullptr;
+    std::string err;
+    bool ok = false;
+    do {
+        nvrtcResult r = g_nvrtc.CreateProgram(&prog, k->source.c_str(), (k->name + ".cu").c_str(), 0, nullptr, nullptr);
+        if (r != NVRTC_SUCCESS) {
+            err = std::string("nvrtcCreateProgram: ") + g_nvrtc.GetErrorString(r);
+            break;
+        }
+        // --fmad=false: the generated source spells every fma and every product out like the interpreter's handlers do
+        char const* opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "--std=c++17", "-lineinfo"};
+        r = g_nvrtc.CompileProgram(prog, 4, opts);
+        if (r != NVRTC_SUCCESS) {
+            size_t n = 0;
+            g_nvrtc.GetProgramLogSize(prog, &n);
+            std::string log(n, '\0');
+            if (n > 0) g_nvrtc.GetProgramLog(prog, log.data());
+            err = std::string("nvrtcCompileProgram: ") + g_nvrtc.GetErrorString(r) + "\n" + log.substr(0, 2000);
+            break;
+        }
+        size_t n = 0;
+        r = g_nvrtc.GetCUBINSize(prog, &n);
+        if (r != NVRTC_SUCCESS || n == 0) {
+            err = "nvrtcGetCUBINSize failed";
+            break;
+        }
+        k->cubin.resize(n);
+        r = g_nvrtc.GetCUBIN(prog, k->cubin.data());
+        if (r != NVRTC_SUCCESS) {
+            err = "nvrtcGetCUBIN failed";
+            break;
+        }
+        ok = true;
+    } while (false);
+    if (prog != nullptr) g_nvrtc.DestroyProgram(&prog);
+    if (char const* dir = std::getenv("QSX_JIT_DUMP")) {  // development aid: keep the generated source and the cubin
+        std::string const base = std::string(dir) + "/" + k->name;
+        if (FILE* f = std::fopen((base + ".cu").c_str(), "w")) {
+            std::fwrite(k->source.data(), 1, k->source.size(), f);
+            std::fclose(f);
+        }
+        if (ok)
+            if (FILE* f = std::fopen((base + ".cubin").c_str(), "wb")) {
+                std::fwrite(k->cubin.data(), 1, k->cubin.size(), f);
+                std::fclose(f);
+            }
+    }
+    double const dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_stats.compile_seconds += dt;
+        if (ok) {
+            ++g_stats.compiled;
+        } else {
+            ++g_stats.failed;
+            g_last_error = err;
+            if (std::getenv("QSX_JIT_VERBOSE") != nullptr) std::fprintf(stderr, "[qsx jit] %s: %s\n", k->name.c_str(), err.c_str());
+        }
+        std::string().swap(k->source);  // not needed any more
+        k->state.store(ok ? kReady : kFailed, std::memory_order_release);
+    }
+    g_cv_done.notify_all();
+}
+
+void worker_main() {
+    for (;;) {
+        Kernel* k = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(g_mu);
+            g_cv_work.wait(lk, [] { return !g_queue.empty(); });
+            k = g_queue.front();
+            g_queue.pop_front();
+            k->state.store(kCompiling, std::memory_order_relaxed);
+        }
+        compile_one(k);
+    }
+}
+
+// called with g_mu held
+void start_pool_locked() {
+    if (g_pool_started) return;
+    g_pool_started = true;
+    int n = (int)std::thread::hardware_concurrency();
+    if (char const* e = std::getenv("QSX_JIT_THREADS")) n = std::atoi(e);
+    if (n < 1) n = 1;
+    if (n > 64) n = 64;
+    g_stats.workers = n;
+    for (int i = 0; i < n; ++i) std::thread(worker_main).detach();  // daemon threads: they only ever wait on the queue
+}
+
+std::string cu_error(CUresult r) {
+    const char* s = nullptr;
+    if (g_drv.GetErrorString != nullptr && g_drv.GetErrorString(r, &s) == CUDA_SUCCESS && s != nullptr) return s;
+    return "CUDA driver error " + std::to_string((int)r);
+}
+
+}  // namespace
+
+bool available(std::string* why) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    bool const ok = available_locked(false);
+    if (!ok && why != nullptr) *why = g_why;
+    return ok;
+}
+
+Kernel* request(const unsigned char* blob, size_t size, int R, int threads) {
+    uint64_t h0, h1;
+    hash_program(blob, size, R, threads, h0, h1);
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!available_locked(false)) return nullptr;
+    ++g_stats.requested;
+    auto it = g_cache.find({h0, h1});
+    if (it != g_cache.end()) {
+        ++g_stats.hits;
+        return it->second.get();
+    }
+    auto k     = std::make_unique<Kernel>();
+    k->h0 = h0, k->h1 = h1, k->R = R, k->threads = threads;
+    char nm[64];
+    std::snprintf(nm, sizeof(nm), "qsx_sweep_%016llx%016llx", (unsigned long long)h0, (unsigned long long)h1);
+    k->name = nm;
+    std::string err;
+    if (!generate_sweep_source(blob, size, R, k->name, threads, min_ctas_for(threads), k->source, err)) {
+        k->state.store(kFailed);
+        g_last_error = err;
+    } else {
+        start_pool_locked();
+        g_queue.push_back(k.get());
+        g_cv_work.notify_one();
+    }
+    Kernel* const raw = k.get();
+    g_cache.emplace(std::make_pair(h0, h1), std::move(k));
+    return raw;
+}
+
+bool ready(Kernel* k) { return k != nullptr && k->state.load(std::memory_order_acquire) == kReady && !k->load_failed; }
+bool failed(Kernel* k) { return k == nullptr || k->state.load(std::memory_order_acquire) == kFailed || k->load_failed; }
+
+bool wait(Kernel* k) {
+    if (k == nullptr) return false;
+    std::unique_lock<std::mutex> lk(g_mu);
+    g_cv_done.wait(lk, [&] {
+        int const s = k->state.load(std::memory_order_acquire);
+        return s == kReady || s == kFailed;
+    });
+    return k->state.load() == kReady && !k->load_failed;
+}
+
+cudaError_t launch(Kernel* k, double2* u, int log2_ncols, int log2_ncb, uint32_t flags, uint32_t col0, unsigned grid, unsigned threads,
+                   size_t smem, cudaStream_t stream) {
+    if (!ready(k)) return cudaErrorNotReady;
+    int dev = 0;
+    if (cudaError_t const e = cudaGetDevice(&dev); e != cudaSuccess) return e;
+    {
+        std::lock_guard<std::mutex> lk(k->load_mu);
+        if (k->kern == nullptr && !k->load_failed) {
+            bool drv_ok;
+            {
+                std::lock_guard<std::mutex> g(g_mu);
+                drv_ok = available_locked(true);
+            }
+            CUresult r = drv_ok ? g_drv.LibraryLoadData(&k->lib, k->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) : CUDA_ERROR_NOT_SUPPORTED;
+            if (r == CUDA_SUCCESS) r = g_drv.LibraryGetKernel(&k->kern, k->lib, k->name.c_str());
+            if (r != CUDA_SUCCESS) {
+                k->load_failed = true;
+                std::lock_guard<std::mutex> g(g_mu);
+                g_last_error = "loading " + k->name + ": " + cu_error(r);
+                ++g_stats.failed;
+            } else {
+                std::vector<char>().swap(k->cubin);  // the driver keeps its own copy
+            }
+        }
+        if (k->load_failed) return cudaErrorNotReady;
+        if (dev >= 0 && dev < 64 && !k->attr_set[dev] && smem > 48 * 1024) {
+            CUdevice cudev = 0;
+            CUresult r     = g_drv.CtxGetDevice(&cudev);
+            if (r == CUDA_SUCCESS) r = g_drv.KernelSetAttribute(CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, 200 * 1024, k->kern, cudev);
+            if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+            k->attr_set[dev] = true;
+        }
+    }
+    void* args[] = {&u, &log2_ncols, &log2_ncb, &flags, &col0};
+    CUresult const r = g_drv.LaunchKernel(reinterpret_cast<CUfunction>(k->kern), grid, 1, 1, threads, 1, 1, (unsigned)smem, stream, args, nullptr);
+    if (r != CUDA_SUCCESS) {
+        std::lock_guard<std::mutex> g(g_mu);
+        g_last_error = "launching " + k->name + ": " + cu_error(r);
+        return cudaErrorLaunchFailure;
+    }
+    {
+        std::lock_guard<std::mutex> g(g_mu);
+        ++g_stats.launches;
+    }
+    return cudaSuccess;
+}
+
+Stats stats() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_stats;
+}
+
+std::string last_compile_error() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_last_error;
+}
+
+}  // namespace qsx::jit

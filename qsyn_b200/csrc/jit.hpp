@@ -1,0 +1,44 @@
+// jit.hpp -- specialised sweep kernels: code generation (jit_codegen.cpp), run-time compilation with NVRTC and the
+// kernel cache (jit.cpp).  Internal.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+
+namespace qsx::jit {
+
+// CUDA C++ source of one sweep program (serialized DevSweep blob) as a kernel
+//   extern "C" __global__ void <kernel_name>(double2* u, int log2_ncols, int log2_ncb, u32 flags, u32 col0)
+// with the launch geometry of sweep_kernel<R> (same grid, same CTA size, same dynamic shared memory for the tile).
+bool generate_sweep_source(const unsigned char* blob, size_t size, int R, std::string const& kernel_name, int threads, int min_ctas,
+                           std::string& source, std::string& error);
+
+struct Kernel;  // one compiled sweep (cache entry)
+
+// Is run-time compilation usable on this host (libnvrtc + libcuda loadable)?  `why` receives the reason when not.
+bool available(std::string* why);
+
+// Looks the program up in the cache (key: content hash + R); on a miss, generates the source and queues the
+// compilation on the worker pool.  Never blocks.  Returns nullptr when JIT is unavailable or the program cannot be
+// specialised.
+Kernel* request(const unsigned char* blob, size_t size, int R, int threads);
+// compiled and loadable?  (false while the compilation is in flight, and forever after a failed one)
+bool ready(Kernel* k);
+bool failed(Kernel* k);
+// blocks until the compilation of k has finished; returns ready(k)
+bool wait(Kernel* k);
+// launch on the CURRENT device (the runtime has made the shard's device current)
+cudaError_t launch(Kernel* k, double2* u, int log2_ncols, int log2_ncb, uint32_t flags, uint32_t col0, unsigned grid, unsigned threads,
+                   size_t smem, cudaStream_t stream);
+
+struct Stats {
+    uint64_t requested = 0, compiled = 0, failed = 0, hits = 0, launches = 0;
+    double compile_seconds = 0;  // summed over the worker threads
+    int workers            = 0;
+};
+Stats stats();
+std::string last_compile_error();
+
+}  // namespace qsx::jit

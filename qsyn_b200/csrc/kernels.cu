@@ -1092,6 +1092,23 @@ cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, uint64_t grid_ncols,
     }
 }
 
+bool sweep_geometry(uint64_t ncols, uint64_t grid_ncols, int R, const DevSweep& hs, SweepGeometry& g) {
+    if (grid_ncols == 0 || grid_ncols > ncols || (grid_ncols & (grid_ncols - 1)) != 0 || grid_ncols < (1ull << hs.log2w)) return false;
+    int const m = hs.m;
+    if (m - R + hs.log2w < 0 || m - R + hs.log2w > 10) return false;
+    g.threads    = 1u << (m - R + hs.log2w);
+    g.tile_bytes = hs.n_stages > 1 ? ((size_t)16 << (m + hs.log2w)) : 0;
+    g.log2_ncols = 0;
+    while ((1ull << g.log2_ncols) < ncols) ++g.log2_ncols;
+    int log2_gcols = 0;
+    while ((1ull << log2_gcols) < grid_ncols) ++log2_gcols;
+    g.log2_ncb             = log2_gcols - hs.log2w;
+    uint64_t const nblocks = 1ull << (g.log2_ncb + hs.n_outer);
+    if (nblocks > 0x7fffffffull || g.tile_bytes > 200 * 1024) return false;
+    g.grid = (unsigned)nblocks;
+    return true;
+}
+
 bool sweep_can_start_from_identity(int R, const DevSweep& hs) {
     if (R != 4 || hs.dense_k != 0 || hs.fixed_one != 0) return false;
     const unsigned char* const host = reinterpret_cast<const unsigned char*>(&hs);

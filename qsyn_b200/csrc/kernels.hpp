@@ -20,6 +20,14 @@ cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, uint64_t grid_ncols,
                          const unsigned char* prog, size_t prog_bytes, bool reverse, bool from_identity, uint64_t col0,
                          cudaStream_t s);
 
+// launch geometry of an interpreted OR specialised sweep (same grid, same CTA, the tile in dynamic shared memory)
+struct SweepGeometry {
+    unsigned grid = 0, threads = 0;
+    size_t tile_bytes = 0;
+    int log2_ncols = 0, log2_ncb = 0;
+};
+bool sweep_geometry(uint64_t ncols, uint64_t grid_ncols, int R, const DevSweep& hs, SweepGeometry& g);
+
 // fused equivalence reduction (K4): 8 compensated sums of a shard pair.
 // `partials` receives 16 doubles per block used (*n_blocks <= equiv_partials_doubles() / 16); the finish kernel merges
 // the partials of any number of shard pairs (laid out back to back) into out8 (device memory) in a fixed order.

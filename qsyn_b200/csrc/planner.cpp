@@ -301,6 +301,7 @@ int build_plan(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gat
     cfg.conjugate_diagonals = o.no_diag_conjugation == 0;
     cfg.fuse_1q             = o.no_1q_fusion == 0;
     cfg.stage_search        = o.stage_search > 0 || (o.stage_search == 0 && n_qubits >= 13);
+    cfg.jit                 = o.jit < 0 ? 0 : (o.jit == 0 ? (n_qubits >= 13 ? 1 : 0) : std::min((int)o.jit, 2));
 
     plan.stats          = qsx_plan_stats{};
     plan.stats.n_gates  = n_gates;

@@ -79,6 +79,7 @@ struct PlanConfig {
     double snap_tol = 1e-15;
     int  l2_block_mib = 0;        // option as given: 0 auto, < 0 off, > 0 forced
     uint64_t block_cols = 0;      // columns per L2 block (0: the sweeps run over the whole shard)
+    int  jit = 0;                 // specialised sweeps: 0 never, 1 when ready (never blocks), 2 wait for the compiler
 };
 
 struct Plan {
@@ -90,6 +91,8 @@ struct Plan {
     std::vector<unsigned char> blob;
     std::vector<size_t> sweep_offset;
     std::vector<size_t> sweep_size;
+    // specialised kernels of the sweeps (jit.hpp), requested on first use; nullptr = interpret
+    std::vector<void*> jit_kernels;
 };
 
 // returns QSX_OK or an error code; msg receives the reason

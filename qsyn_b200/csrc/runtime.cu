@@ -9,7 +9,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <list>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -17,6 +19,7 @@
 
 #include "../../include/qsx.h"
 #include "../host/util/phase.hpp"
+#include "jit.hpp"
 #include "kernels.hpp"
 #include "planner.hpp"
 #include "runtime_internal.hpp"
@@ -91,6 +94,62 @@ int get_ctx(int device, DeviceCtx** out) {
     return QSX_OK;
 }
 
+// Shard buffers are recycled: `tensor` commands create and delete 2^n x 2^n operands all the time (every qc2ts, every
+// TensorMgr copy), and a cudaMalloc / cudaFree pair of 16 GiB costs milliseconds and a device-wide synchronisation.
+// A freed buffer is parked (exact size match on reuse; all work on a device is ordered by its one stream, so the next
+// owner's kernels run after the previous owner's) up to QSX_POOL_FRACTION (default 0.45) of the device memory.
+cudaError_t pool_alloc(DeviceCtx* c, void** out, size_t bytes) {
+    {
+        std::lock_guard<std::mutex> lk(c->pool_mu);
+        auto it = c->pool.find(bytes);
+        if (it != c->pool.end()) {
+            *out = it->second;
+            c->pool.erase(it);
+            c->pool_bytes -= bytes;
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        pool_trim(c);
+        e = cudaMalloc(out, bytes);
+    }
+    return e;
+}
+
+void pool_free(DeviceCtx* c, void* p, size_t bytes) {
+    {
+        std::lock_guard<std::mutex> lk(c->pool_mu);
+        if (c->pool_cap == 0) {
+            size_t free_b = 0, total_b = 0;
+            double frac   = 0.45;
+            if (char const* e = std::getenv("QSX_POOL_FRACTION")) frac = std::atof(e);
+            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) total_b = 0, cudaGetLastError();
+            c->pool_cap = frac <= 0 ? 1 : (size_t)(frac * (double)total_b) + 1;
+        }
+        if (c->pool_bytes + bytes <= c->pool_cap) {
+            c->pool.emplace(bytes, p);
+            c->pool_bytes += bytes;
+            return;
+        }
+    }
+    cudaStreamSynchronize(c->stream);
+    cudaFree(p);
+}
+
+void pool_trim(DeviceCtx* c) {
+    std::multimap<size_t, void*> victims;
+    {
+        std::lock_guard<std::mutex> lk(c->pool_mu);
+        victims.swap(c->pool);
+        c->pool_bytes = 0;
+    }
+    if (victims.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (auto& kv : victims) cudaFree(kv.second);
+}
+
 int materialize(qsx_unitary* u, DeviceCtx* c) {
     if (!u->lazy_identity) return QSX_OK;
     QSX_CUDA(launch_set_identity(u->data, u->n, u->col0, u->ncols, c->stream));
@@ -108,6 +167,20 @@ using qsx::get_ctx;
 int materialize_(qsx_unitary* u, DeviceCtx* c) { return qsx::materialize(u, c); }
 int materialize_(const qsx_unitary* u, DeviceCtx* c) { return qsx::materialize(const_cast<qsx_unitary*>(u), c); }
 std::mutex g_prog_mu;  // (kept for the staging state's own consistency; the device mutex is held around it)
+// Looks up / queues the specialised kernel of every interpreted sweep of the plan (never blocks).
+void request_jit_kernels(qsx::Plan& pl) {
+    if (pl.cfg.jit == 0 || !pl.jit_kernels.empty() || pl.sweeps.empty()) return;
+    pl.jit_kernels.assign(pl.sweeps.size(), nullptr);
+    if (!qsx::jit::available(nullptr)) return;
+    for (size_t s = 0; s < pl.sweeps.size(); ++s) {
+        qsx::DevSweep const& hs = *reinterpret_cast<qsx::DevSweep const*>(pl.blob.data() + pl.sweep_offset[s]);
+        if (hs.dense_k != 0) continue;
+        int const log2_threads = hs.m - pl.cfg.R + hs.log2w;
+        if (log2_threads < 0 || log2_threads > 10) continue;
+        pl.jit_kernels[s] = qsx::jit::request(pl.blob.data() + pl.sweep_offset[s], pl.sweep_size[s], pl.cfg.R, 1 << log2_threads);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -137,6 +210,13 @@ int qsx_device_synchronize(int device) {
     return QSX_OK;
 }
 
+int qsx_device_trim(int device) {
+    DeviceCtx* c = nullptr;
+    if (int rc = get_ctx(device, &c)) return rc;
+    qsx::pool_trim(c);
+    return QSX_OK;
+}
+
 // ---- storage ----------------------------------------------------------------------------
 
 int qsx_unitary_create(int device, int n_qubits, uint64_t col0, uint64_t ncols, qsx_unitary** out) {
@@ -151,7 +231,7 @@ int qsx_unitary_create(int device, int n_qubits, uint64_t col0, uint64_t ncols, 
     auto* u = new (std::nothrow) qsx_unitary;
     if (u == nullptr) return fail(QSX_ERR_OOM, "host allocation failed");
     u->device = device, u->n = n_qubits, u->col0 = col0, u->ncols = ncols;
-    cudaError_t const e = cudaMalloc(&u->data, u->bytes());
+    cudaError_t const e = qsx::pool_alloc(c, reinterpret_cast<void**>(&u->data), u->bytes());
     if (e != cudaSuccess) {
         delete u;
         return cuda_fail(e, "cudaMalloc(unitary shard)");
@@ -195,10 +275,7 @@ int qsx_unitary_destroy(qsx_unitary* u) {
     if (u == nullptr) return QSX_OK;
     if (u->data != nullptr) {
         DeviceCtx* c = nullptr;
-        if (get_ctx(u->device, &c) == QSX_OK) {
-            cudaStreamSynchronize(c->stream);
-            cudaFree(u->data);
-        }
+        if (get_ctx(u->device, &c) == QSX_OK) qsx::pool_free(c, u->data, u->bytes());
     }
     delete u;
     return QSX_OK;
@@ -313,6 +390,29 @@ int qsx_plan_destroy(qsx_plan* plan) {
     return QSX_OK;
 }
 
+int qsx_plan_compile(const qsx_plan* cplan, int wait) {
+    if (cplan == nullptr) return fail(QSX_ERR_BAD_ARG, "null plan");
+    auto* plan = const_cast<qsx_plan*>(cplan);
+    {
+        std::lock_guard<std::mutex> lk(plan->mu);
+        if (plan->plan.cfg.jit == 0) plan->plan.cfg.jit = 1;  // an explicit request overrides the size heuristic
+        request_jit_kernels(plan->plan);
+    }
+    if (wait)
+        for (void* k : plan->plan.jit_kernels)
+            if (k != nullptr) qsx::jit::wait(static_cast<qsx::jit::Kernel*>(k));
+    return QSX_OK;
+}
+
+int qsx_jit_get_stats(qsx_jit_stats* out) {
+    if (out == nullptr) return fail(QSX_ERR_BAD_ARG, "null stats");
+    qsx::jit::Stats const st = qsx::jit::stats();
+    out->requested = st.requested, out->cache_hits = st.hits, out->compiled = st.compiled, out->failed = st.failed;
+    out->launches = st.launches, out->compile_seconds = st.compile_seconds, out->workers = st.workers;
+    out->available = qsx::jit::available(nullptr) ? 1 : 0;
+    return QSX_OK;
+}
+
 int qsx_plan_get_stats(const qsx_plan* plan, qsx_plan_stats* stats) {
     if (plan == nullptr || stats == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
     *stats = plan->plan.stats;
@@ -333,11 +433,12 @@ int qsx_plan_dump(const qsx_plan* plan, char* buf, size_t buf_size, size_t* need
 
 namespace {
 // enqueues the sweeps of a plan whose programs are at dblob (device); synchronises unless QSX_RUN_ASYNC
-int run_sweeps(qsx::Plan const& pl, qsx_unitary* u, DeviceCtx* c, unsigned char* dblob, qsx_stop_fn should_stop,
+int run_sweeps(qsx::Plan& pl, qsx_unitary* u, DeviceCtx* c, unsigned char* dblob, qsx_stop_fn should_stop,
                void* stop_arg, uint32_t flags, qsx_run_stats* stats) {
+    request_jit_kernels(pl);
     bool const async = (flags & QSX_RUN_ASYNC) != 0;
     if (!async) QSX_CUDA(cudaEventRecord(c->ev0, c->stream));
-    uint64_t launches = 0;
+    uint64_t launches = 0, jit_launches = 0;
     // Column blocking through the L2 (plan option l2_block_mib): all sweeps run on one block of columns before
     // the next block is touched.  Columns are independent, so any order of (block, sweep) pairs that keeps the
     // sweep order within a block is the same computation.
@@ -346,7 +447,11 @@ int run_sweeps(qsx::Plan const& pl, qsx_unitary* u, DeviceCtx* c, unsigned char*
     if (u->lazy_identity && !pl.sweeps.empty()) {
         // an interpreted sweep that touches every tile can start from the synthesised identity
         qsx::DevSweep const& first = *reinterpret_cast<qsx::DevSweep const*>(pl.blob.data() + pl.sweep_offset[0]);
-        if (qsx::sweep_can_start_from_identity(pl.cfg.R, first)) {
+        // (a specialised kernel synthesises the identity for any register count and handler set)
+        auto* const k0 = pl.jit_kernels.empty() ? nullptr : static_cast<qsx::jit::Kernel*>(pl.jit_kernels[0]);
+        bool const jit_first = k0 != nullptr && first.dense_k == 0 && first.fixed_one == 0 &&
+                               (pl.cfg.jit == 2 ? qsx::jit::wait(k0) : qsx::jit::ready(k0));
+        if (jit_first || qsx::sweep_can_start_from_identity(pl.cfg.R, first)) {
             identity_per_block = true;
             u->lazy_identity   = false;
         } else {
@@ -376,16 +481,36 @@ int run_sweeps(qsx::Plan const& pl, qsx_unitary* u, DeviceCtx* c, unsigned char*
                 }
             }
             qsx::DevSweep const& hs = *reinterpret_cast<qsx::DevSweep const*>(pl.blob.data() + pl.sweep_offset[s]);
-            // serpentine: every other sweep walks the tiles backwards, so it starts with what the previous
-            // sweep wrote last and is still in the 126 MB L2 (n = 12, memory-bound sweeps: 77.7 -> 71.6 us)
-            QSX_CUDA(qsx::launch_sweep(u->data + cb0, u->n, u->ncols, block_cols, pl.cfg.R, hs, dblob + pl.sweep_offset[s],
-                                       pl.sweep_size[s], (s & 1) != 0, identity_per_block && s == 0, u->col0 + cb0,
-                                       c->stream));
+            bool const from_identity = identity_per_block && s == 0;
+            bool launched            = false;
+            auto* const k = pl.jit_kernels.empty() ? nullptr : static_cast<qsx::jit::Kernel*>(pl.jit_kernels[s]);
+            if (k != nullptr && (pl.cfg.jit == 2 ? qsx::jit::wait(k) : qsx::jit::ready(k))) {
+                qsx::SweepGeometry g;
+                if (qsx::sweep_geometry(u->ncols, block_cols, pl.cfg.R, hs, g)) {
+                    uint32_t const fl   = ((s & 1) != 0 ? 1u : 0u) | (from_identity ? 2u : 0u);
+                    cudaError_t const e = qsx::jit::launch(k, u->data + cb0, g.log2_ncols, g.log2_ncb, fl, (uint32_t)(u->col0 + cb0), g.grid,
+                                                           g.threads, g.tile_bytes, c->stream);
+                    if (e == cudaSuccess) {
+                        launched = true;
+                        ++jit_launches;
+                    } else if (e != cudaErrorNotReady) {
+                        return fail(QSX_ERR_CUDA, "specialised sweep: " + qsx::jit::last_compile_error());
+                    }
+                }
+            }
+            if (!launched) {
+                if (from_identity && !qsx::sweep_can_start_from_identity(pl.cfg.R, hs))
+                    return fail(QSX_ERR_CUDA, "the specialised first sweep became unavailable after the identity was skipped");
+                // serpentine: every other sweep walks the tiles backwards, so it starts with what the previous
+                // sweep wrote last and is still in the 126 MB L2 (n = 12, memory-bound sweeps: 77.7 -> 71.6 us)
+                QSX_CUDA(qsx::launch_sweep(u->data + cb0, u->n, u->ncols, block_cols, pl.cfg.R, hs, dblob + pl.sweep_offset[s],
+                                           pl.sweep_size[s], (s & 1) != 0, from_identity, u->col0 + cb0, c->stream));
+            }
             pending_bytes += pl.sweeps[s].alg_bytes * share;
             ++launches;
         }
     }
-    if (stats != nullptr) stats->launches = launches;
+    if (stats != nullptr) stats->launches = launches, stats->jit_launches = jit_launches;
     if (!async) {
         QSX_CUDA(cudaEventRecord(c->ev1, c->stream));
         QSX_CUDA(cudaStreamSynchronize(c->stream));
@@ -397,17 +522,15 @@ int run_sweeps(qsx::Plan const& pl, qsx_unitary* u, DeviceCtx* c, unsigned char*
 }
 }  // namespace
 
-int qsx_plan_run(const qsx_plan* cplan, qsx_unitary* u, qsx_stop_fn should_stop, void* stop_arg, uint32_t flags,
-                 qsx_run_stats* stats) {
-    if (cplan == nullptr || u == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
-    auto* plan           = const_cast<qsx_plan*>(cplan);
-    qsx::Plan const& pl  = plan->plan;
-    if (pl.cfg.n != u->n || pl.cfg.ncols != u->ncols)
-        return fail(QSX_ERR_SHAPE, "plan was built for a different shard geometry");
+namespace {
+int run_plan(qsx_plan* plan, qsx_unitary* u, qsx_stop_fn should_stop, void* stop_arg, uint32_t flags, qsx_run_stats* stats) {
+    qsx::Plan& pl = plan->plan;
+    if (pl.cfg.n != u->n || pl.cfg.ncols != u->ncols) return fail(QSX_ERR_SHAPE, "plan was built for a different shard geometry");
     if (stats != nullptr) *stats = qsx_run_stats{};
     DeviceCtx* c = nullptr;
     if (int rc = get_ctx(u->device, &c)) return rc;
     if (pl.sweeps.empty()) return QSX_OK;
+    // the stream order and the event pair are per device: one host thread at a time
     std::lock_guard<std::mutex> dev_lock(c->mu);
     unsigned char* dblob = nullptr;
     {
@@ -429,59 +552,111 @@ int qsx_plan_run(const qsx_plan* cplan, qsx_unitary* u, qsx_stop_fn should_stop,
     return run_sweeps(pl, u, c, dblob, should_stop, stop_arg, flags, stats);
 }
 
+void free_plan(qsx_plan* plan) {
+    for (auto& kv : plan->device_blob)
+        if (cudaSetDevice(kv.first) == cudaSuccess) cudaFree(kv.second);  // (cudaFree waits for the sweeps that read it)
+    delete plan;
+}
+}  // namespace
+
+int qsx_plan_run(const qsx_plan* cplan, qsx_unitary* u, qsx_stop_fn should_stop, void* stop_arg, uint32_t flags,
+                 qsx_run_stats* stats) {
+    if (cplan == nullptr || u == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    return run_plan(const_cast<qsx_plan*>(cplan), u, should_stop, stop_arg, flags, stats);
+}
+
 namespace {
-// stages a one-shot plan's programs on the device without synchronising the stream
-int stage_programs(DeviceCtx* c, qsx::Plan const& pl, unsigned char** dblob) {
-    std::lock_guard<std::mutex> lk(g_prog_mu);
-    size_t const bytes = pl.blob.size();
-    if (bytes > c->prog_dev_cap) {
-        if (c->prog_dev != nullptr) QSX_CUDA(cudaFree(c->prog_dev));  // (waits for the sweeps that read it)
-        c->prog_dev     = nullptr;
-        c->prog_dev_cap = 0;
-        size_t const cap = std::max(bytes * 2, size_t{1} << 20);
-        QSX_CUDA(cudaMalloc(&c->prog_dev, cap));
-        c->prog_dev_cap = cap;
+// ---- plan cache: `qc2ts` on a circuit that was converted before (the same operand again, a TensorMgr round trip, a
+//      repeated check) finds its schedule, the uploaded programs and the specialised kernels instead of re-planning.
+//      Key: geometry + options + every gate (controls, targets, qubits, matrix bytes). ----
+struct PlanKey {
+    uint64_t h0, h1;
+    bool operator==(PlanKey const& o) const { return h0 == o.h0 && h1 == o.h1; }
+};
+std::mutex g_plan_cache_mu;
+std::list<std::pair<PlanKey, std::shared_ptr<qsx_plan>>> g_plan_cache;  // most recently used first
+
+PlanKey plan_key(int n, uint64_t ncols, const qsx_gate* gates, size_t n_gates, const qsx_plan_options* opt) {
+    uint64_t a = 0x9e3779b97f4a7c15ull ^ (uint64_t)n, b = 0xc2b2ae3d27d4eb4full ^ ncols;
+    auto mix   = [&](const void* p, size_t bytes) {
+        const unsigned char* c = static_cast<const unsigned char*>(p);
+        size_t i               = 0;
+        for (; i + 8 <= bytes; i += 8) {
+            uint64_t w;
+            std::memcpy(&w, c + i, 8);
+            a = (a ^ w) * 0x100000001b3ull, a ^= a >> 29;
+            b = (b + w) * 0xff51afd7ed558ccdull, b ^= b >> 32;
+        }
+        for (; i < bytes; ++i) a = (a ^ c[i]) * 0x100000001b3ull, b = (b + c[i]) * 0xff51afd7ed558ccdull;
+    };
+    qsx_plan_options o{};
+    if (opt != nullptr) o = *opt;
+    int32_t const has_opt = opt != nullptr;
+    mix(&has_opt, sizeof(has_opt));
+    mix(&o, sizeof(o));
+    for (size_t g = 0; g < n_gates; ++g) {
+        int32_t hdr[2 + QSX_MAX_GATE_QUBITS] = {};
+        hdr[0] = gates[g].n_ctrls, hdr[1] = gates[g].n_targets;
+        int const k = gates[g].n_ctrls + gates[g].n_targets;
+        for (int q = 0; q < k && q < QSX_MAX_GATE_QUBITS; ++q) hdr[2 + q] = gates[g].qubits[q];
+        mix(hdr, sizeof(hdr));
+        if (gates[g].matrix != nullptr && gates[g].n_targets >= 0 && gates[g].n_targets <= 8)
+            mix(gates[g].matrix, (size_t)16 << (2 * gates[g].n_targets));
     }
-    int const slot = c->prog_slot ^= 1;
-    if (c->prog_ev[slot] == nullptr) QSX_CUDA(cudaEventCreateWithFlags(&c->prog_ev[slot], cudaEventDisableTiming));
-    QSX_CUDA(cudaEventSynchronize(c->prog_ev[slot]));  // the copy that last read this staging buffer is done
-    if (bytes > c->prog_pin_cap[slot]) {
-        if (c->prog_pin[slot] != nullptr) QSX_CUDA(cudaFreeHost(c->prog_pin[slot]));
-        c->prog_pin[slot]     = nullptr;
-        c->prog_pin_cap[slot] = 0;
-        size_t const cap = std::max(bytes * 2, size_t{1} << 20);
-        QSX_CUDA(cudaMallocHost(&c->prog_pin[slot], cap));
-        c->prog_pin_cap[slot] = cap;
-    }
-    std::memcpy(c->prog_pin[slot], pl.blob.data(), bytes);
-    QSX_CUDA(cudaMemcpyAsync(c->prog_dev, c->prog_pin[slot], bytes, cudaMemcpyHostToDevice, c->stream));
-    QSX_CUDA(cudaEventRecord(c->prog_ev[slot], c->stream));
-    *dblob = c->prog_dev;
-    return QSX_OK;
+    return PlanKey{a ^ (uint64_t)n_gates, b};
+}
+
+size_t plan_cache_capacity() {
+    static size_t const cap = [] {
+        if (char const* e = std::getenv("QSX_PLAN_CACHE")) return (size_t)std::max(0, std::atoi(e));
+        return (size_t)8;
+    }();
+    return cap;
 }
 
 int apply_impl(qsx_unitary* u, const qsx_gate* gates, size_t n_gates, const qsx_plan_options* opt, qsx_stop_fn should_stop,
                void* stop_arg, uint32_t flags, qsx_run_stats* stats) {
     if (u == nullptr) return fail(QSX_ERR_BAD_ARG, "null unitary");
+    if (n_gates > 0 && gates == nullptr) return fail(QSX_ERR_BAD_ARG, "null gate array");
     if (stats != nullptr) *stats = qsx_run_stats{};
-    qsx::Plan pl;
-    std::string msg;
-    int rc;
-    try {
-        rc = qsx::build_plan(u->n, u->ncols, gates, n_gates, opt, pl, msg);
-    } catch (std::bad_alloc const&) {
-        rc  = QSX_ERR_OOM;
-        msg = "host allocation failed while planning";
+    std::shared_ptr<qsx_plan> plan;
+    PlanKey const key = plan_key(u->n, u->ncols, gates, n_gates, opt);
+    size_t const cap  = plan_cache_capacity();
+    if (cap > 0) {
+        std::lock_guard<std::mutex> lk(g_plan_cache_mu);
+        for (auto it = g_plan_cache.begin(); it != g_plan_cache.end(); ++it)
+            if (it->first == key) {
+                plan = it->second;
+                g_plan_cache.splice(g_plan_cache.begin(), g_plan_cache, it);
+                break;
+            }
     }
-    if (rc != QSX_OK) return fail(rc, msg);
-    DeviceCtx* c = nullptr;
-    if (int e = get_ctx(u->device, &c)) return e;
-    if (pl.sweeps.empty()) return QSX_OK;
-    // the program buffer, the event pair and the stream order are per device: one host thread at a time
-    std::lock_guard<std::mutex> dev_lock(c->mu);
-    unsigned char* dblob = nullptr;
-    if (int e = stage_programs(c, pl, &dblob)) return e;
-    return run_sweeps(pl, u, c, dblob, should_stop, stop_arg, flags, stats);
+    bool const hit = plan != nullptr;
+    if (!hit) {
+        plan = std::shared_ptr<qsx_plan>(new qsx_plan, free_plan);
+        std::string msg;
+        int rc;
+        try {
+            rc = qsx::build_plan(u->n, u->ncols, gates, n_gates, opt, plan->plan, msg);
+        } catch (std::bad_alloc const&) {
+            rc  = QSX_ERR_OOM;
+            msg = "host allocation failed while planning";
+        }
+        if (rc != QSX_OK) return fail(rc, msg);
+        if (cap > 0) {
+            std::lock_guard<std::mutex> lk(g_plan_cache_mu);
+            g_plan_cache.emplace_front(key, plan);
+            while (g_plan_cache.size() > cap) g_plan_cache.pop_back();  // (a plan still running is kept alive by `plan`)
+        }
+    }
+    int const rc = run_plan(plan.get(), u, should_stop, stop_arg, flags, stats);
+    if (stats != nullptr) stats->plan_cache_hit = hit ? 1 : 0;
+    if ((flags & QSX_RUN_ASYNC) != 0 && cap == 0) {
+        // nobody else owns the plan: its programs must outlive the enqueued sweeps
+        DeviceCtx* c = nullptr;
+        if (get_ctx(u->device, &c) == QSX_OK) cudaStreamSynchronize(c->stream);
+    }
+    return rc;
 }
 }  // namespace
 

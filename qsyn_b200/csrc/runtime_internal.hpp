@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <map>
 #include <mutex>
 #include <string>
 
@@ -25,8 +26,8 @@ struct qsx_unitary {
 namespace qsx {
 
 // Everything the library owns on one device.  `mu` serialises the host threads that use the device:
-// the stream, the event pair, the equivalence scratch and the one-shot program buffer are shared by
-// every call on the device, so a call holds `mu` from its first use of them to its last launch.
+// the stream, the event pair and the equivalence scratch are shared by every call on the device, so a call holds
+// `mu` from its first use of them to its last launch.
 struct DeviceCtx {
     std::mutex   mu;
     int          device   = -1;
@@ -34,15 +35,14 @@ struct DeviceCtx {
     double*      scratch  = nullptr;  // equiv partials of up to kMaxLocalShards shard pairs + 8 outputs
     double*      host8    = nullptr;  // pinned
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
-    // one-shot programs of qsx_apply_gates*: a grow-only device buffer (reuse is ordered by the
-    // stream) fed from two pinned staging buffers (reuse is ordered by an event each)
-    unsigned char* prog_dev = nullptr;
-    size_t         prog_dev_cap = 0;
-    unsigned char* prog_pin[2] = {nullptr, nullptr};
-    size_t         prog_pin_cap[2] = {0, 0};
-    cudaEvent_t    prog_ev[2] = {nullptr, nullptr};
-    int            prog_slot = 0;
+    // parked shard buffers (pool_alloc / pool_free): size -> pointer
+    std::mutex                   pool_mu;
+    std::multimap<size_t, void*> pool;
+    size_t                       pool_bytes = 0, pool_cap = 0;
 };
+cudaError_t pool_alloc(DeviceCtx* c, void** out, size_t bytes);
+void pool_free(DeviceCtx* c, void* p, size_t bytes);
+void pool_trim(DeviceCtx* c);
 constexpr int kMaxLocalShards = 64;  // shard pairs of one equivalence check that may share a device
 
 int device_count_nothrow();

@@ -109,10 +109,21 @@ def _check_geometry(key, n, gs_a, gs_tail, oracle, opt, shards):
             ea, eb = _frob(got_a, want_a), _frob(got_b, want_b)
             assert ea <= FROB_TOL and eb <= FROB_TOL, (key, shards, w0, ea, eb)
             worst_a, worst_b = max(worst_a, ea), max(worst_b, eb)
-        # the whole-shard reduction: B = e^{i pi/4} A exactly, whatever the columns
-        r = Q.equiv_finish(Q.equiv_reduce([ua], [ub]))
-        assert r.equivalent == 1 and (r.phase_num, r.phase_den) == (1, 4), (key, shards, k)
-        assert abs(r.norm - 1) <= EQUIV_TOL and abs(r.phase_rad - math.pi / 4) <= EQUIV_TOL, (r.norm, r.phase_rad)
+        # the whole-shard reduction: B = e^{i pi/4} A exactly, whatever the columns.  <A,B> = e^{i pi/4} <A,A> and
+        # sum(B) = e^{i pi/4} sum(A) are checked on the sums themselves; the RATIO sum(B)/sum(A) (norm, phase) only where
+        # sum(A) is not a cancellation residue (a column block of a QFT sums to ~0: SURVEY Appendix C trap 2)
+        sums = Q.equiv_reduce([ua], [ub])
+        w = complex(math.cos(math.pi / 4), math.sin(math.pi / 4))
+        ip, sa, sb = complex(sums[0], sums[1]), complex(sums[4], sums[5]), complex(sums[6], sums[7])
+        full = float(dim) * ncols / dim  # sum |a|^2 over a block of `ncols` unit columns
+        assert abs(sums[2] - full) <= EQUIV_TOL * full and abs(sums[3] - full) <= EQUIV_TOL * full, (key, sums[2], sums[3], full)
+        assert abs(ip - w * sums[2]) <= EQUIV_TOL * full, (key, shards, k, ip)
+        assert abs(sb - w * sa) <= EQUIV_TOL * max(1.0, abs(sa)), (key, shards, k, sa, sb)
+        r = Q.equiv_finish(sums)
+        assert r.equivalent == 1 and abs(r.cosine - 1) <= EQUIV_TOL
+        if abs(sa) > 1e-3 * math.sqrt(full):
+            assert (r.phase_num, r.phase_den) == (1, 4), (key, shards, k)
+            assert abs(r.norm - 1) <= EQUIV_TOL and abs(r.phase_rad - math.pi / 4) <= EQUIV_TOL, (r.norm, r.phase_rad)
         ua.close()
         ub.close()
     return worst_a, worst_b
@@ -132,12 +143,11 @@ def _check_equiv_on_windows(key, n, gs_a, gs_tail, oracle, opt):
     sums = Q.equiv_reduce(uas, ubs)
     want = O.equiv_sums(np.concatenate(wa, axis=1), np.concatenate(wb, axis=1))
     got, ref = Q.equiv_finish(sums), O.finish_equiv(want)
-    assert bool(got.equivalent) == ref.equivalent is True
-    assert (got.phase_num, got.phase_den) == (ref.phase.numerator(), ref.phase.denominator()) == (1, 4)
+    assert got.equivalent == 1 and ref.equivalent is True
+    assert (got.phase_num, got.phase_den) == (ref.phase.numerator, ref.phase.denominator) == (1, 4)
     s = complex(want[6], want[7]) / complex(want[4], want[5])
     d_norm, d_phase, d_cos = abs(got.norm - abs(s)), abs(got.phase_rad - math.atan2(s.imag, s.real)), abs(got.cosine - ref.cosine)
     assert d_norm <= EQUIV_TOL and d_phase <= EQUIV_TOL and d_cos <= EQUIV_TOL, (key, d_norm, d_phase, d_cos)
-    # the eps ladder on the negative side: A vs A.rz(0.001) fails at 1e-8 like tests/tensor/not_equiv/ref/error.log
     for u in uas + ubs:
         u.close()
     return d_norm, d_phase, d_cos
