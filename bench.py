@@ -182,11 +182,12 @@ def measure(c, args, workload, steps, warmup, e2e_steps, main_line):
     plan_a = Q.Plan(n, ncols, gs_a, opt)
     plan_b = Q.Plan(n, ncols, gs_b, opt)
     st_a, st_b = plan_a.stats(), plan_b.stats()
+    dump_a = plan_a.dump()
     launches = {"n": 0, "jit": 0}
     # "inputs resident" includes the specialised kernels of the schedules (qsx_plan_options.jit): compiled before the
     # timed region, like the schedules themselves; the cold compile time is reported under `jit`
     jit0, t0 = abi.jit_stats(), time.perf_counter()
-    if args.jit >= 0:
+    if args.jit >= 0 and dump_a.get("jit", 0):
         plan_a.compile(True)
         plan_b.compile(True)
     jit_cold_s = time.perf_counter() - t0
@@ -307,16 +308,17 @@ def measure(c, args, workload, steps, warmup, e2e_steps, main_line):
                 "l2": "unitary shard per GPU is %.0f MiB; L2 is 126 MB: %s" % (
                     shard_mib, "inputs larger than L2" if 16 * dim * ncols > 126e6 else "shard fits in L2 (strong scaling), no flush"),
                 "schedule": {"sweeps_A": st_a.n_sweeps, "stages_A": st_a.n_stages, "micro_ops_A": st_a.n_micro_ops,
-                             "max_ops_per_sweep": args.cap, "tile_qubits": args.tile, "reg_qubits": args.reg,
+                             "max_ops_per_sweep": args.cap or 96, "tile_qubits": dump_a["m_cap"], "reg_qubits": dump_a["R"],
+                             "log2_tile_cols": dump_a["log2w"],
                              "dense_block": args.dense, "dense_blocks_A": st_a.n_dense_blocks,
-                             "l2_block_mib": args.l2_block, "l2_block_columns": plan_a.dump()["block_cols"],
+                             "l2_block_mib": args.l2_block, "l2_block_columns": dump_a["block_cols"],
                              "plan_host_ms_A": round(st_a.plan_host_ms, 3), "plan_host_ms_B": round(st_b.plan_host_ms, 3)},
             },
             "construct_ms_A": round(sweep_ms, 4),
             "equiv_ms": round(equiv_ms, 4),
             "equiv_GBps": round(2 * 16 * dim * dim / (equiv_ms * 1e-3) / 1e9, 1),
             "gpu_launches": gpu_launches,
-            "roofline": {"bound": "hbm", "kernel": ("dense_kernel<%d>" % args.dense) if args.dense else (("specialised sweep (NVRTC, jit_codegen.cpp), R=%d" if jit_launches else "sweep_kernel<%d, *>") % args.reg),
+            "roofline": {"bound": "hbm", "kernel": ("dense_kernel<%d>" % args.dense) if args.dense else (("specialised sweep (NVRTC, jit_codegen.cpp), R=%d" if jit_launches else "sweep_kernel<%d, *>") % dump_a["R"]),
                          "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": st_a.alg_bytes_per_run / max(n_launch, 1),
@@ -344,7 +346,7 @@ def measure(c, args, workload, steps, warmup, e2e_steps, main_line):
             fp64_peak_tflops, fp64_src = _fp64_peak()
             instr = _fp64_instructions_per_run(plan_a, float(dim) * ncols)
             ach = 2.0 * instr / (sweep_ms * 1e-3) / 1e12  # an FP64 pipe slot is worth 2 flop at the DFMA peak
-            out["roofline_fp64"] = {"bound": "fp64_pipe", "kernel": "sweep_kernel<%d, *>" % args.reg, "achieved": round(ach, 2),
+            out["roofline_fp64"] = {"bound": "fp64_pipe", "kernel": "the same launches", "achieved": round(ach, 2),
                                     "peak": fp64_peak_tflops, "peak_source": fp64_src, "unit": "TFLOP/s (FP64 pipe slots x 2)",
                                     "frac": round(ach / fp64_peak_tflops, 4),
                                     "fp64_instructions_per_element_per_launch": round(instr / (float(dim) * ncols) / max(st_a.n_sweeps, 1), 2)}
@@ -565,13 +567,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--extras", default="auto", help="comma list of further workloads reported under `extra` (auto: c2, and c5 on 8 GPUs)")
     ap.add_argument("--e2e-steps", type=int, default=10, help="timed end-to-end steps (at most --steps)")
-    ap.add_argument("--cap", type=int, default=96, help="max ops per sweep")
-    ap.add_argument("--tile", type=int, default=8)
-    ap.add_argument("--reg", type=int, default=4)
-    ap.add_argument("--log2w", type=int, default=3)
+    ap.add_argument("--cap", type=int, default=0, help="max ops per sweep (0: library default)")
+    ap.add_argument("--tile", type=int, default=0, help="tile row bits (0: library default: 9 with specialised sweeps, else 8)")
+    ap.add_argument("--reg", type=int, default=0, help="register row bits (0: library default 4)")
+    ap.add_argument("--log2w", type=int, default=0, help="log2 tile columns (0: library default 3)")
     ap.add_argument("--dense", type=int, default=0, help="fold the gate stream into dense k-qubit blocks on the FP64 tensor pipe (3..5)")
     ap.add_argument("--l2-block", type=int, default=0, help="column blocking through the L2 in MiB (0: cost model decides, -1: off)")
-    ap.add_argument("--jit", type=int, default=0, help="specialised sweeps: 0 library default (n >= 13), 1 always, -1 never (interpreter only)")
+    ap.add_argument("--jit", type=int, default=0, help="specialised sweeps: 0 library default (n >= 12), 1 always, -1 never (interpreter only)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

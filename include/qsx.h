@@ -113,7 +113,7 @@ typedef struct qsx_plan_options {
     double  snap_tol;      /* matrix entries within snap_tol of 0 / +-1 / +-i are snapped (default 1e-15);
                               < 0 disables snapping: the host-built matrices are applied as given               */
     int32_t reg_qubits;    /* qubits held in registers per thread (1..5, default 4; 5 was measured slower)      */
-    int32_t tile_qubits;   /* max row bits staged per shared-memory tile (default 8)                            */
+    int32_t tile_qubits;   /* max row bits staged per shared-memory tile (default 9 with specialised sweeps, else 8) */
     int32_t log2_tile_cols;/* log2 of tile width in columns (default 3 -> 128 B contiguous per row)             */
     int32_t max_ops_per_sweep; /* cap on ops per sweep (default 96)                                             */
     int32_t lookahead;     /* scheduler scan window in gates (default 4096)                                     */
@@ -139,8 +139,8 @@ typedef struct qsx_plan_options {
                               < 0: never; > 0: always, with this block size                                    */
     int32_t jit;           /* specialised sweeps: the program of a sweep is compiled at run time (NVRTC, all host cores, cached
                               by content) into straight-line code and replaces the interpreter once it is ready.
-                              0 (default): on for n >= 13, where a sweep runs for milliseconds (never blocks: a sweep whose
-                              kernel is still compiling is interpreted); 1: on for any n; 2: on and WAIT for the compiler
+                              0 (default): on for n >= 12 (never blocks: a sweep whose kernel is still compiling is
+                              interpreted); 1: on for any n; 2: on and WAIT for the compiler
                               (first use of a program costs ~0.1 s per sweep / host cores); < 0: always interpret      */
 } qsx_plan_options;
 

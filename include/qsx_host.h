@@ -39,6 +39,11 @@ int qsxh_circuit_gate_repr(qsxh_circuit* c, size_t i, char* buf, size_t buf_size
 /* the ordered gate stream in the layout qsx_plan_create / qsx_apply_gates take; owned by the circuit,
  * valid until the circuit is modified or destroyed */
 int qsxh_circuit_gate_stream(qsxh_circuit* c, const qsx_gate** gates, size_t* n_gates);
+/* `qcir adjoint`: every gate replaced by its adjoint, order reversed (qcir_action.cpp:136-153) */
+int qsxh_circuit_adjoint_inplace(qsxh_circuit* c);
+/* `qcir equiv` (qcir_cmd.cpp:603-650 -> qcir_equiv.cpp:19-66): *equivalent = 1 iff c1^-1 . c2 is the identity up to a
+ * global phase.  The reference's tableau pre-check is not part of this path; the tensor half runs on the device. */
+int qsxh_circuit_equiv(const qsxh_circuit* c1, const qsxh_circuit* c2, int* equivalent);
 int qsxh_circuit_destroy(qsxh_circuit* c);
 
 /* convert qcir tensor: nullopt cases of the reference return QSX_ERR_BAD_ARG (empty circuit),
@@ -57,6 +62,13 @@ int qsxh_zxgraph_destroy(qsxh_zxgraph* g);
 int qsxh_tensor_shape(const qsxh_tensor* t, size_t* dims, size_t max_dims, size_t* n_dims);
 /* host copy of the matrix, row-major complex128; n_doubles = 2 * rows * cols */
 int qsxh_tensor_download(const qsxh_tensor* t, double* out, size_t n_doubles);
+/* one element of a matrix-shaped tensor: `tensor(i, j)` (tensor.hpp:156-175); a device-resident tensor reads 16 bytes */
+int qsxh_tensor_element(const qsxh_tensor* t, size_t i, size_t j, double re_im[2]);
+/* `tensor write` / `tensor read` (tensor.hpp:326-384): CSV of "re+imj" cells, one matrix row per line */
+int qsxh_tensor_write(const qsxh_tensor* t, const char* path);
+int qsxh_tensor_read(const char* path, qsxh_tensor** out);
+/* `tensor print`: the text qsyn prints (xtensor's format, sk.log:19-20); buf may be NULL to query *needed */
+int qsxh_tensor_print(const qsxh_tensor* t, char* buf, size_t buf_size, size_t* needed);
 int qsxh_tensor_adjoint_inplace(qsxh_tensor* t);
 /* tensor equiv: result numbers + the exact text qsyn prints ("Equivalent\n- Global Norm : 1\n...") */
 int qsxh_tensor_equiv(const qsxh_tensor* t1, const qsxh_tensor* t2, double eps, int strict, qsx_equiv_result* result,

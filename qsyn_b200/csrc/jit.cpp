@@ -13,6 +13,7 @@
 #include <dlfcn.h>
 #include <nvrtc.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -186,8 +187,10 @@ int min_ctas_for(int threads) {
         int const v = std::atoi(e);
         if (v >= 1 && v <= 16) return v;
     }
-    // 2^R elements of 2 doubles = 64 registers at R = 4; ~96 registers per thread leave room for temporaries
-    int const v = 65536 / (threads * 96);
+    // 2^R elements of 2 doubles = 64 registers at R = 4; 128 registers per thread (16 warps per SM) measured best on
+    // C4: 96 (20 warps) spills into the op stream, +13 % time; 170 (12 warps) hides the barriers worse
+    // (profiles/r2_tile_sweep_c4.jsonl)
+    int const v = 65536 / (threads * 128);
     return v < 1 ? 1 : (v > 8 ? 8 : v);
 }
 
@@ -374,7 +377,19 @@ cudaError_t launch(Kernel* k, double2* u, int log2_ncols, int log2_ncb, uint32_t
             k->attr_set[dev] = true;
         }
     }
-    void* args[] = {&u, &log2_ncols, &log2_ncb, &flags, &col0};
+    // L2 prefetch distance in CTAs (0 = off): about twice the CTAs resident on the device (measured)
+    static uint32_t const pf_env = [] {
+        char const* e = std::getenv("QSX_JIT_PREFETCH");
+        return e != nullptr ? (uint32_t)std::max(0, std::atoi(e)) : 0xffffffffu;
+    }();
+    uint32_t pf = pf_env;
+    if (pf == 0xffffffffu) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int const resident = std::max(1, std::min(65536 / (int)(threads * 128), smem > 0 ? (int)((220 * 1024) / smem) : 8));
+        pf                 = (uint32_t)(2 * sms * resident);
+    }
+    void* args[] = {&u, &log2_ncols, &log2_ncb, &flags, &col0, &pf};
     CUresult const r = g_drv.LaunchKernel(reinterpret_cast<CUfunction>(k->kern), grid, 1, 1, threads, 1, 1, (unsigned)smem, stream, args, nullptr);
     if (r != CUDA_SUCCESS) {
         std::lock_guard<std::mutex> g(g_mu);

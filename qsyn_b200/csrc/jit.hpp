@@ -10,7 +10,7 @@
 namespace qsx::jit {
 
 // CUDA C++ source of one sweep program (serialized DevSweep blob) as a kernel
-//   extern "C" __global__ void <kernel_name>(double2* u, int log2_ncols, int log2_ncb, u32 flags, u32 col0)
+//   extern "C" __global__ void <kernel_name>(double2* u, int log2_ncols, int log2_ncb, u32 flags, u32 col0, u32 prefetch_distance)
 // with the launch geometry of sweep_kernel<R> (same grid, same CTA size, same dynamic shared memory for the tile).
 bool generate_sweep_source(const unsigned char* blob, size_t size, int R, std::string const& kernel_name, int threads, int min_ctas,
                            std::string& source, std::string& error);

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <sstream>
 
+#include "jit.hpp"
 #include "planner_internal.hpp"
 
 namespace qsx {
@@ -281,7 +282,13 @@ int build_plan(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gat
     cfg.R           = std::min(n_qubits, o.reg_qubits > 0 ? std::min((int)o.reg_qubits, kMaxRegBits) : 4);
     cfg.log2w       = std::min(lc, o.log2_tile_cols > 0 ? std::min((int)o.log2_tile_cols, 5) : 3);
     if (o.log2_tile_cols < 0) cfg.log2w = 0;
-    cfg.m_cap       = o.tile_qubits > 0 ? (int)o.tile_qubits : 8;
+    // specialised sweeps (qsx_plan_options.jit): on by default from n = 12 (a sweep runs for >= 0.1 ms and a job repeats
+    // its programs; below that the compiler would only burn host time)
+    cfg.jit         = o.jit < 0 ? 0 : (o.jit == 0 ? (n_qubits >= 12 ? 1 : 0) : std::min((int)o.jit, 2));
+    if (cfg.jit != 0 && !jit::available(nullptr)) cfg.jit = 0;  // no libnvrtc on this host: the interpreter runs everything
+    // tile: 2^8 rows x 8 columns (32 KiB, 4-5 CTAs per SM) is the interpreter's optimum; compiled sweeps are cheap enough
+    // per op that one more tile bit pays: C4 174 -> 142 sweeps at 5.9 -> 6.5 ms each (profiles/r2_tile_sweep_c4.jsonl)
+    cfg.m_cap       = o.tile_qubits > 0 ? (int)o.tile_qubits : (cfg.jit != 0 ? 9 : 8);
     cfg.m_cap       = std::min(cfg.m_cap, kMaxTileBits);
     cfg.m_cap       = std::min(cfg.m_cap, 13 - cfg.log2w);            // 2^m * W * 16 B <= 128 KiB
     cfg.m_cap       = std::min(cfg.m_cap, max_threads_log2(cfg.R) - cfg.log2w + cfg.R);  // CTA size limit
@@ -301,7 +308,6 @@ int build_plan(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gat
     cfg.conjugate_diagonals = o.no_diag_conjugation == 0;
     cfg.fuse_1q             = o.no_1q_fusion == 0;
     cfg.stage_search        = o.stage_search > 0 || (o.stage_search == 0 && n_qubits >= 13);
-    cfg.jit                 = o.jit < 0 ? 0 : (o.jit == 0 ? (n_qubits >= 13 ? 1 : 0) : std::min((int)o.jit, 2));
 
     plan.stats          = qsx_plan_stats{};
     plan.stats.n_gates  = n_gates;
@@ -358,7 +364,7 @@ std::string dump_plan_json(const Plan& plan) {
     std::ostringstream os;
     os.precision(17);
     os << "{\"n\":" << plan.cfg.n << ",\"ncols\":" << plan.cfg.ncols << ",\"R\":" << plan.cfg.R
-       << ",\"log2w\":" << plan.cfg.log2w << ",\"m_cap\":" << plan.cfg.m_cap << ",\"block_cols\":" << plan.cfg.block_cols << ",\"sweeps\":[";
+       << ",\"log2w\":" << plan.cfg.log2w << ",\"m_cap\":" << plan.cfg.m_cap << ",\"jit\":" << plan.cfg.jit << ",\"block_cols\":" << plan.cfg.block_cols << ",\"sweeps\":[";
     for (size_t s = 0; s < plan.sweeps.size(); ++s) {
         PlannedSweep const& sw = plan.sweeps[s];
         os << (s ? "," : "") << "{\"tile_bits\":[";

@@ -31,6 +31,8 @@ def lib() -> C.CDLL:
             "qsxh_circuit_info": [vp, C.POINTER(sz), C.POINTER(sz)],
             "qsxh_circuit_gate_repr": [vp, sz, C.c_char_p, sz, C.POINTER(sz)],
             "qsxh_circuit_gate_stream": [vp, C.POINTER(C.POINTER(abi.GateStruct)), C.POINTER(sz)],
+            "qsxh_circuit_adjoint_inplace": [vp],
+            "qsxh_circuit_equiv": [vp, vp, C.POINTER(C.c_int)],
             "qsxh_circuit_destroy": [vp],
             "qsxh_qc2ts": [vp, C.POINTER(vp)],
             "qsxh_zxgraph_from_zx_text": [C.c_char_p, C.c_int, C.POINTER(vp)],
@@ -40,6 +42,10 @@ def lib() -> C.CDLL:
             "qsxh_zxgraph_destroy": [vp],
             "qsxh_tensor_shape": [vp, C.POINTER(sz), sz, C.POINTER(sz)],
             "qsxh_tensor_download": [vp, C.POINTER(C.c_double), sz],
+            "qsxh_tensor_element": [vp, sz, sz, C.POINTER(C.c_double)],
+            "qsxh_tensor_write": [vp, C.c_char_p],
+            "qsxh_tensor_read": [C.c_char_p, C.POINTER(vp)],
+            "qsxh_tensor_print": [vp, C.c_char_p, sz, C.POINTER(sz)],
             "qsxh_tensor_adjoint_inplace": [vp],
             "qsxh_tensor_equiv": [vp, vp, C.c_double, C.c_int, C.POINTER(abi.EquivResult), C.c_char_p, sz],
             "qsxh_tensor_destroy": [vp],
@@ -120,6 +126,16 @@ class Circuit:
         _check(lib().qsxh_qc2ts(self._h, C.byref(h)))
         return Tensor(h)
 
+    def adjoint_inplace(self) -> "Circuit":
+        _check(lib().qsxh_circuit_adjoint_inplace(self._h))
+        return self
+
+    def equiv(self, other: "Circuit") -> bool:
+        """`qcir equiv`: the tensor half of qcir::is_equivalent on the device."""
+        out = C.c_int(0)
+        _check(lib().qsxh_circuit_equiv(self._h, other._h, C.byref(out)))
+        return bool(out.value)
+
     def close(self):
         if getattr(self, "_h", None):
             lib().qsxh_circuit_destroy(self._h)
@@ -186,6 +202,27 @@ class Tensor:
 
     def adjoint_inplace(self):
         _check(lib().qsxh_tensor_adjoint_inplace(self._h))
+
+    def element(self, i: int, j: int) -> complex:
+        v = (C.c_double * 2)()
+        _check(lib().qsxh_tensor_element(self._h, i, j, v))
+        return complex(v[0], v[1])
+
+    def write(self, path: str) -> None:
+        _check(lib().qsxh_tensor_write(self._h, str(path).encode()))
+
+    @staticmethod
+    def read(path: str) -> "Tensor":
+        h = C.c_void_p()
+        _check(lib().qsxh_tensor_read(str(path).encode(), C.byref(h)))
+        return Tensor(h)
+
+    def print_string(self) -> str:
+        need = C.c_size_t(0)
+        _check(lib().qsxh_tensor_print(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        _check(lib().qsxh_tensor_print(self._h, buf, need.value, None))
+        return buf.value.decode()
 
     def equiv(self, other: "Tensor", eps: float = 1e-6, strict: bool = False):
         """`tensor equiv`: (qsx_equiv_result, the text qsyn prints)."""

@@ -6,10 +6,12 @@
 #include <filesystem>
 #include <sstream>
 #include <string>
+#include <utility>
 
 #include "../convert/qcir_to_tensor.hpp"
 #include "../convert/zxgraph_to_tensor.hpp"
 #include "../qcir/qcir.hpp"
+#include "../qcir/qcir_equiv.hpp"
 #include "../tensor/qtensor.hpp"
 
 // the embedding application owns cancellation (qsyn: SIGINT -> jthread stop token); a library user
@@ -140,6 +142,21 @@ int qsxh_circuit_gate_stream(qsxh_circuit* c, const qsx_gate** gates, size_t* n_
     });
 }
 
+int qsxh_circuit_adjoint_inplace(qsxh_circuit* c) {
+    if (c == nullptr) return fail(QSX_ERR_BAD_ARG, "null circuit");
+    c->qcir.adjoint_inplace();
+    c->stream.reset();
+    return QSX_OK;
+}
+
+int qsxh_circuit_equiv(const qsxh_circuit* c1, const qsxh_circuit* c2, int* equivalent) {
+    if (c1 == nullptr || c2 == nullptr || equivalent == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    return guarded([&] {
+        *equivalent = qsyn::qcir::is_equivalent(c1->qcir, c2->qcir) ? 1 : 0;
+        return (int)QSX_OK;
+    });
+}
+
 int qsxh_circuit_destroy(qsxh_circuit* c) {
     delete c;
     return QSX_OK;
@@ -223,6 +240,51 @@ int qsxh_tensor_download(const qsxh_tensor* t, double* out, size_t n_doubles) {
         auto const v = t->tensor.host_elements();
         if (n_doubles != 2 * v.size()) return fail(QSX_ERR_BAD_ARG, "buffer size mismatch");
         std::memcpy(out, v.data(), sizeof(double) * n_doubles);
+        return (int)QSX_OK;
+    });
+}
+
+int qsxh_tensor_element(const qsxh_tensor* t, size_t i, size_t j, double re_im[2]) {
+    if (t == nullptr || re_im == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    return guarded([&] {
+        auto const sh = t->tensor.shape();
+        if (sh.size() != 2 || i >= sh[0] || j >= sh[1]) return fail(QSX_ERR_BAD_ARG, "element index out of range (the tensor must be a matrix)");
+        std::complex<double> const v = std::as_const(t->tensor)(i, j);
+        re_im[0] = v.real(), re_im[1] = v.imag();
+        return (int)QSX_OK;
+    });
+}
+
+int qsxh_tensor_write(const qsxh_tensor* t, const char* path) {
+    if (t == nullptr || path == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    return guarded([&] {
+        if (!const_cast<qsxh_tensor*>(t)->tensor.tensor_write(path)) return fail(QSX_ERR_BAD_ARG, "Failed to open file");
+        return (int)QSX_OK;
+    });
+}
+
+int qsxh_tensor_read(const char* path, qsxh_tensor** out) {
+    if (path == nullptr || out == nullptr) return fail(QSX_ERR_BAD_ARG, "null argument");
+    return guarded([&] {
+        auto t = std::make_unique<qsxh_tensor>();
+        if (!t->tensor.tensor_read(path)) return fail(QSX_ERR_BAD_ARG, "the tensor file cannot be read (see the log)");
+        *out = t.release();
+        return (int)QSX_OK;
+    });
+}
+
+int qsxh_tensor_print(const qsxh_tensor* t, char* buf, size_t buf_size, size_t* needed) {
+    if (t == nullptr) return fail(QSX_ERR_BAD_ARG, "null tensor");
+    return guarded([&] {
+        std::ostringstream os;
+        os << t->tensor;
+        std::string const s = os.str();
+        if (needed != nullptr) *needed = s.size() + 1;
+        if (buf != nullptr && buf_size > 0) {
+            size_t const k = std::min(buf_size - 1, s.size());
+            std::memcpy(buf, s.data(), k);
+            buf[k] = '\0';
+        }
         return (int)QSX_OK;
     });
 }

@@ -23,6 +23,7 @@
 #include "../convert/qcir_to_tensor.hpp"
 #include "../convert/zxgraph_to_tensor.hpp"
 #include "../qcir/qcir.hpp"
+#include "../qcir/qcir_equiv.hpp"
 #include "../tensor/qtensor.hpp"
 #include "../util/logger.hpp"
 
@@ -200,6 +201,26 @@ struct Shell {
             } else {
                 std::cout << std::format("QCir ({} qubits, {} gates)\n", qcir_mgr.get()->get_num_qubits(), qcir_mgr.get()->get_num_gates());
             }
+        } else if (is_prefix(sub, "equiv")) {
+            // qcir_cmd.cpp:603-650: one id = compare the focused circuit with it
+            if (!need_qcir() || a.empty()) return;
+            std::vector<size_t> ids;
+            for (auto const& t : a) ids.push_back(std::stoul(t));
+            for (size_t id : ids)
+                if (qcir_mgr.find_by_id(id) == nullptr) {
+                    std::fprintf(stderr, "Error: QCir %zu does not exist!!\n", id);
+                    return;
+                }
+            if ((ids.size() == 2 && ids[0] == ids[1]) || (ids.size() == 1 && qcir_mgr.focused_id() == ids[0]))
+                spdlog::info("Note: comparing the same circuit...");
+            bool const eq = ids.size() == 1 ? qsyn::qcir::is_equivalent(*qcir_mgr.get(), *qcir_mgr.find_by_id(ids[0]))
+                                            : qsyn::qcir::is_equivalent(*qcir_mgr.find_by_id(ids[0]), *qcir_mgr.find_by_id(ids[1]));
+            std::cout << (eq ? "The two circuits are equivalent!!" : "The two circuits are not equivalent!!") << "\n";
+        } else if (is_prefix(sub, "adjoint")) {
+            if (!need_qcir()) return;
+            qcir_mgr.get()->adjoint_inplace();
+        } else if (is_prefix(sub, "checkout")) {
+            if (!a.empty()) qcir_mgr.checkout(std::stoul(a[0]));
         } else if (is_prefix(sub, "qubit")) {
             if (a.empty() || !is_prefix(a[0], "add")) return;
             size_t const n = a.size() > 1 ? std::stoul(a[1]) : 1;

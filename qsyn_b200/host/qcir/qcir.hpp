@@ -323,6 +323,26 @@ public:
         return id;
     }
 
+    // Append `other` to this circuit, gate by gate in other's topological order (qcir_action.cpp:28-36)
+    QCir& compose(QCir const& other) {
+        if (get_num_qubits() < other.get_num_qubits()) add_qubits(other.get_num_qubits() - get_num_qubits());
+        for (QCirGate* g : other.get_gates()) append(g->get_operation(), g->get_qubits());
+        return *this;
+    }
+
+    // Every gate becomes its adjoint and the wiring is reversed: predecessors <-> successors, first <-> last gate of
+    // every qubit; gate ids are kept (qcir_action.cpp:136-153)
+    void adjoint_inplace() {
+        for (auto& g : _gates_by_id) g->set_operation(adjoint(g->get_operation()));
+        std::swap(_predecessors, _successors);
+        for (auto& q : _qubits) {
+            QCirGate* const first = q.get_first_gate();
+            q.set_first_gate(q.get_last_gate());
+            q.set_last_gate(first);
+        }
+        _dirty = true;
+    }
+
     void reset() {
         _qubits.clear();
         _gates_by_id.clear();

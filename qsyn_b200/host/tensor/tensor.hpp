@@ -136,16 +136,23 @@ public:
 
     bool is_device_resident() const { return _dev.resident(); }
 
+    // Element access (tensor.hpp:156-175).  On a device-resident tensor a const access reads ONE element from the
+    // device (decomposer.hpp:64-69 walks a matrix this way); asking for a writable reference brings the tensor
+    // to the host first (the device copy is dropped: the caller is about to change the data).
     template <typename... Args>
     DT& operator()(Args const&... args) {
+        _pull_to_host();
         return _data[_offset({static_cast<size_t>(args)...})];
     }
     template <typename... Args>
     DT const& operator()(Args const&... args) const {
-        return _data[_offset({static_cast<size_t>(args)...})];
+        return _const_element({static_cast<size_t>(args)...});
     }
-    DT& operator[](TensorIndex const& i) { return _data[_offset(i)]; }
-    DT const& operator[](TensorIndex const& i) const { return _data[_offset(i)]; }
+    DT& operator[](TensorIndex const& i) {
+        _pull_to_host();
+        return _data[_offset(i)];
+    }
+    DT const& operator[](TensorIndex const& i) const { return _const_element(i); }
 
     virtual bool operator==(Tensor<DT> const& rhs) const { return shape() == rhs.shape() && _host_view() == rhs._host_view(); }
     virtual bool operator!=(Tensor<DT> const& rhs) const { return !(*this == rhs); }
@@ -260,6 +267,7 @@ public:
 protected:
     TensorShape _shape;
     InternalType _data;
+    mutable DT _element_cache{};  // last element read from a device-resident tensor
     DeviceSlot<DT> _dev;
     std::unordered_map<size_t, size_t> _axis_history;
 
@@ -276,6 +284,39 @@ protected:
     void _require_host(char const* what) const {
         if (_dev.resident())
             throw std::logic_error(std::string(what) + " is not available on a device-resident tensor; use host_elements()");
+    }
+    void _pull_to_host() {
+        if constexpr (std::is_same_v<DT, std::complex<double>>) {
+            if (_dev.resident()) {
+                auto shp  = shape();
+                auto data = _host_view();
+                _dev      = DeviceSlot<DT>{};
+                _shape    = std::move(shp);
+                _data     = std::move(data);
+            }
+        }
+    }
+    DT const& _const_element(TensorIndex const& idx) const {
+        if constexpr (std::is_same_v<DT, std::complex<double>>) {
+            if (_dev.resident()) {
+                size_t r = 0, c = 0;
+                if (_dev.as_matrix) {
+                    if (idx.size() != 2) throw std::invalid_argument("element access: a matrix takes two indices");
+                    r = idx[0], c = idx[1];
+                } else {  // interleaved [o0, i0, o1, i1, ...], qubit 0 = most significant bit
+                    size_t const n = (size_t)_dev.unitary.n_qubits();
+                    if (idx.size() != 2 * n) throw std::invalid_argument("element access: index rank mismatch");
+                    for (size_t q = 0; q < n; ++q) {
+                        r = (r << 1) | (idx[2 * q] & 1);
+                        c = (c << 1) | (idx[2 * q + 1] & 1);
+                    }
+                }
+                if (r >= _dev.unitary.dim() || c >= _dev.unitary.dim()) throw std::out_of_range("element access: index out of range");
+                _element_cache = _dev.unitary.element(r, c);
+                return _element_cache;
+            }
+        }
+        return _data[_offset(idx)];
     }
     template <typename IL>
     void _from_il(IL const& il) {
@@ -460,12 +501,25 @@ bool Tensor<DT>::tensor_write(std::string const& filepath) {
         return false;
     }
     auto const s = shape();
-    auto const v = _host_view();
     if (s.size() != 2) return false;
+    // a device-resident matrix is streamed in blocks of rows (no second full copy on the host)
+    bool streamed = false;
+    if constexpr (std::is_same_v<DT, std::complex<double>>) streamed = _dev.resident() && _dev.as_matrix;
+    size_t const block = streamed ? std::max<size_t>(1, (size_t{1} << 22) / std::max<size_t>(s[1], 1)) : s[0];
+    std::vector<DT> v;
+    if (!streamed) v = _host_view();
     for (size_t row = 0; row < s[0]; row++) {
+        if constexpr (std::is_same_v<DT, std::complex<double>>) {
+            if (streamed && row % block == 0) {
+                size_t const nrows = std::min(block, s[0] - row);
+                v.resize(nrows * s[1]);
+                _dev.unitary.download_rows(row, nrows, v.data());
+            }
+        }
+        size_t const base = streamed ? (row % block) * s[1] : row * s[1];
         for (size_t col = 0; col < s[1]; col++) {
             if constexpr (detail::is_complex<DT>::value) {
-                auto const re = v[row * s[1] + col].real(), im = v[row * s[1] + col].imag();
+                auto const re = v[base + col].real(), im = v[base + col].imag();
                 // "{space if re >= 0}{re}+{|im|}j" / "{re}{im}j"  (tensor.hpp:335-339)
                 out_file << (re >= 0 ? " " : "") << std::format("{}", re);
                 if (im >= 0)
@@ -473,7 +527,7 @@ bool Tensor<DT>::tensor_write(std::string const& filepath) {
                 else
                     out_file << std::format("{}", im) << "j";
             } else {
-                out_file << std::format("{}", v[row * s[1] + col]);
+                out_file << std::format("{}", v[base + col]);
             }
             if (col != s[1] - 1) out_file << ", ";
         }
