@@ -377,18 +377,15 @@ cudaError_t launch(Kernel* k, double2* u, int log2_ncols, int log2_ncb, uint32_t
             k->attr_set[dev] = true;
         }
     }
-    // L2 prefetch distance in CTAs (0 = off): about twice the CTAs resident on the device (measured)
+    // L2 prefetch distance in CTAs.  OFF by default: measured on C4 (profiles/r2_prefetch_sweep_c4.jsonl) every distance
+    // from 1x to 8x the resident CTAs made the sweeps 14-40 % SLOWER -- the sweeps already run at the bandwidth this access
+    // pattern (128-byte rows, 2^n x 16 B apart) gets from HBM, and the prefetches only add requests.  QSX_JIT_PREFETCH=<CTAs>
+    // keeps the experiment reproducible.
     static uint32_t const pf_env = [] {
         char const* e = std::getenv("QSX_JIT_PREFETCH");
-        return e != nullptr ? (uint32_t)std::max(0, std::atoi(e)) : 0xffffffffu;
+        return e != nullptr ? (uint32_t)std::max(0, std::atoi(e)) : 0u;
     }();
     uint32_t pf = pf_env;
-    if (pf == 0xffffffffu) {
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        int const resident = std::max(1, std::min(65536 / (int)(threads * 128), smem > 0 ? (int)((220 * 1024) / smem) : 8));
-        pf                 = (uint32_t)(2 * sms * resident);
-    }
     void* args[] = {&u, &log2_ncols, &log2_ncb, &flags, &col0, &pf};
     CUresult const r = g_drv.LaunchKernel(reinterpret_cast<CUfunction>(k->kern), grid, 1, 1, threads, 1, 1, (unsigned)smem, stream, args, nullptr);
     if (r != CUDA_SUCCESS) {

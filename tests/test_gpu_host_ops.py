@@ -93,8 +93,17 @@ def test_tensor_write_read_roundtrip(tmp_path, goldens):
     lines = path.read_text().split("\n")
     assert len(lines) == 257 and lines[-1] == ""
     first = lines[0].split(", ")
-    assert len(first) == 256 and first[0] == " 0.0625+0j"  # {space if re >= 0}{re}+{|im|}j, fmt's shortest repr
     m = t.to_numpy()
+
+    def shortest(x):  # fmt's "{}" of a double: shortest round-trip digits, no trailing ".0"
+        s = repr(float(x))
+        return s[:-2] if s.endswith(".0") else s
+
+    def cell(z):  # tensor.hpp:335-339: "{space if re >= 0}{re}+{|im|}j" / "{re}{im}j"
+        return (" " if z.real >= 0 else "") + shortest(z.real) + ("+" + shortest(abs(z.imag)) if z.imag >= 0 else shortest(z.imag)) + "j"
+
+    assert len(first) == 256 and first[0] == cell(m[0, 0]) == " 0.06250000000000001+0j"
+    assert lines[1].split(", ")[1] == cell(m[1, 1]) and lines[200].split(", ")[77] == cell(m[200, 77])
     parsed = np.array([[complex(c.strip().replace("j", "j")) for c in ln.split(", ")] for ln in lines[:-1]])
     assert np.array_equal(parsed, m)  # shortest round-trip formatting loses nothing
     back = host.Tensor.read(path)
