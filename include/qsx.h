@@ -181,6 +181,7 @@ typedef struct qsx_jit_stats {
     double   compile_seconds; /* compiler time summed over the worker threads      */
     int32_t  workers;         /* compiler threads                                  */
     int32_t  available;       /* 0: libnvrtc / driver entry points missing         */
+    uint64_t disk_hits;       /* kernels loaded from the on-disk cache (QSX_JIT_CACHE) instead of being compiled */
 } qsx_jit_stats;
 int qsx_jit_get_stats(qsx_jit_stats* stats);
 

@@ -33,6 +33,9 @@ int qsxh_circuit_from_qasm_text(const char* text, qsxh_circuit** out);
 int qsxh_circuit_from_qasm_file(const char* path, qsxh_circuit** out);
 /* `qcir gate add <gate> [-ph <phase>] <qubits...>`: gate name as in gate_type.cpp, phase string as in phase.hpp (nullable) */
 int qsxh_circuit_append(qsxh_circuit* c, const char* gate, const char* phase, const size_t* qubits, size_t n_qubits);
+/* appends circuit `sub` as ONE gate on `qubits` (the first n_ctrls of them are controls): a nested QCir is an Operation
+ * in the reference (qcir.hpp:181-183); its to_tensor is the circuit's unitary (qcir_to_tensor.cpp:147) */
+int qsxh_circuit_append_circuit(qsxh_circuit* c, const qsxh_circuit* sub, size_t n_ctrls, const size_t* qubits, size_t n_qubits);
 int qsxh_circuit_info(const qsxh_circuit* c, size_t* n_qubits, size_t* n_gates);
 /* repr of the i-th gate in topological order, e.g. "rz(277π/376)" (UTF-8) */
 int qsxh_circuit_gate_repr(qsxh_circuit* c, size_t i, char* buf, size_t buf_size, size_t* gate_id);

@@ -76,7 +76,8 @@ class PlanStats(C.Structure):
 
 class JitStats(C.Structure):
     _fields_ = [("requested", C.c_uint64), ("cache_hits", C.c_uint64), ("compiled", C.c_uint64), ("failed", C.c_uint64),
-                ("launches", C.c_uint64), ("compile_seconds", C.c_double), ("workers", C.c_int32), ("available", C.c_int32)]
+                ("launches", C.c_uint64), ("compile_seconds", C.c_double), ("workers", C.c_int32), ("available", C.c_int32),
+                ("disk_hits", C.c_uint64)]
 
 
 class RunStats(C.Structure):

@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -92,10 +93,21 @@ int nccl_fail(ncclResult_t r, char const* what) {
         if (r__ != ncclSuccess) return ::qsx::nccl_fail(r__, #call); \
     } while (0)
 
+// Communicators must be destroyed while the CUDA runtime is still alive: a process that simply returns from main with
+// live communicators crashes in NCCL's teardown (seen as SIGSEGV after `quit -f` with QSX_NUM_GPUS=2).  atexit handlers
+// run in reverse order of registration, and this one is registered after the runtime's own (the first CUDA call is
+// long past when a communicator is created), so it runs before the runtime shuts down.
+void destroy_comms_at_exit() { qsx_shutdown(); }
+void register_exit_hook() {
+    static bool const once = (std::atexit(destroy_comms_at_exit), true);
+    (void)once;
+}
+
 int clique_for(std::vector<int> const& devices, std::vector<ncclComm_t>** out) {
     auto it = g_cliques.find(devices);
     if (it == g_cliques.end()) {
         if (int rc = load_nccl()) return rc;
+        register_exit_hook();
         std::vector<ncclComm_t> comms(devices.size(), nullptr);
         QSX_NCCL(g_nccl.CommInitAll(comms.data(), (int)devices.size(), devices.data()));
         it = g_cliques.emplace(devices, std::move(comms)).first;
@@ -208,6 +220,7 @@ int qsx_comm_init_rank(int device, int world, int rank, const void* id, size_t i
     std::lock_guard<std::mutex> lk(qsx::g_comm_mu);
     if (qsx::g_rank_comm != nullptr) return qsx::fail(QSX_ERR_BAD_ARG, "qsx_comm_init_rank was already called (qsx_shutdown first)");
     if (int rc = qsx::load_nccl()) return rc;
+    qsx::register_exit_hook();
     ncclUniqueId uid;
     std::memcpy(&uid, id, sizeof(uid));
     QSX_NCCL(qsx::g_nccl.CommInitRank(&qsx::g_rank_comm, world, uid, rank));

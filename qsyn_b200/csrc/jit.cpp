@@ -12,6 +12,9 @@
 #include <cuda.h>
 #include <dlfcn.h>
 #include <nvrtc.h>
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -42,6 +45,7 @@ struct Nvrtc {
     nvrtcResult (*GetProgramLog)(nvrtcProgram, char*)                                                                  = nullptr;
     nvrtcResult (*DestroyProgram)(nvrtcProgram*)                                                                       = nullptr;
     const char* (*GetErrorString)(nvrtcResult)                                                                         = nullptr;
+    nvrtcResult (*Version)(int*, int*)                                                                                 = nullptr;
 };
 
 // ---- driver entry points (cudaGetDriverEntryPoint) -------------------------------------------
@@ -115,6 +119,7 @@ bool load_nvrtc(std::string& why) {
     g_nvrtc.GetProgramLog     = reinterpret_cast<decltype(g_nvrtc.GetProgramLog)>(sym("nvrtcGetProgramLog"));
     g_nvrtc.DestroyProgram    = reinterpret_cast<decltype(g_nvrtc.DestroyProgram)>(sym("nvrtcDestroyProgram"));
     g_nvrtc.GetErrorString    = reinterpret_cast<decltype(g_nvrtc.GetErrorString)>(sym("nvrtcGetErrorString"));
+    g_nvrtc.Version           = reinterpret_cast<decltype(g_nvrtc.Version)>(sym("nvrtcVersion"));
     if (!ok) why = "libnvrtc lacks a required entry point";
     return ok;
 }
@@ -194,12 +199,77 @@ int min_ctas_for(int threads) {
     return v < 1 ? 1 : (v > 8 ? 8 : v);
 }
 
+// ---- on-disk cache of compiled kernels ------------------------------------------------------------------
+// One file per (generated source, compiler): a second process on the same host -- the other ranks of a torchrun job, the
+// next invocation of the CLI on the same circuit -- loads the cubin instead of compiling it again.  The key is a hash of
+// the SOURCE TEXT (so any change of the code generator or of the launch bounds is a different file) plus the NVRTC
+// version.  QSX_JIT_CACHE=<dir> moves it, QSX_JIT_CACHE=off disables it.  Files are written to a temporary name and
+// renamed, so a reader never sees a partial file.
+std::string const& cache_dir() {
+    static std::string const dir = [] {
+        std::string d;
+        if (char const* e = std::getenv("QSX_JIT_CACHE")) {
+            d = e;
+            if (d == "off" || d == "0") return std::string();
+        } else if (char const* x = std::getenv("XDG_CACHE_HOME")) {
+            d = std::string(x) + "/qsx-jit";
+        } else {
+            d = "/tmp/qsx-jit-" + std::to_string((unsigned)getuid());
+        }
+        ::mkdir(d.c_str(), 0700);
+        struct stat st {};
+        if (::stat(d.c_str(), &st) != 0 || !S_ISDIR(st.st_mode)) return std::string();
+        return d;
+    }();
+    return dir;
+}
+
+std::string cache_path(Kernel const* k) {
+    if (cache_dir().empty()) return {};
+    uint64_t h0, h1;
+    hash_program(reinterpret_cast<const unsigned char*>(k->source.data()), k->source.size(), 0, 0, h0, h1);
+    int major = 0, minor = 0;
+    if (g_nvrtc.Version != nullptr) g_nvrtc.Version(&major, &minor);
+    char nm[160];
+    std::snprintf(nm, sizeof(nm), "/%016llx%016llx-sm100a-nvrtc%d.%d.cubin", (unsigned long long)h0, (unsigned long long)h1, major, minor);
+    return cache_dir() + nm;
+}
+
+bool read_cached(std::string const& path, std::vector<char>& out) {
+    if (path.empty()) return false;
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (f == nullptr) return false;
+    std::fseek(f, 0, SEEK_END);
+    long const n = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    bool ok = n > 64;
+    if (ok) {
+        out.resize((size_t)n);
+        ok = std::fread(out.data(), 1, (size_t)n, f) == (size_t)n && std::memcmp(out.data(), "\x7f" "ELF", 4) == 0;
+    }
+    std::fclose(f);
+    if (!ok) out.clear();
+    return ok;
+}
+
+void write_cached(std::string const& path, std::vector<char> const& data) {
+    if (path.empty()) return;
+    std::string const tmp = path + ".tmp." + std::to_string((long)getpid()) + "." + std::to_string((unsigned long)(uintptr_t)&data);
+    FILE* f = std::fopen(tmp.c_str(), "wb");
+    if (f == nullptr) return;
+    bool const ok = std::fwrite(data.data(), 1, data.size(), f) == data.size();
+    std::fclose(f);
+    if (!ok || std::rename(tmp.c_str(), path.c_str()) != 0) std::remove(tmp.c_str());
+}
+
 void compile_one(Kernel* k) {
     auto const t0 = std::chrono::steady_clock::now();
     nvrtcProgram prog = nullptr;
     std::string err;
-    bool ok = false;
-    do {
+    bool ok = false, from_disk = false;
+    std::string const cpath = cache_path(k);
+    if (read_cached(cpath, k->cubin)) ok = from_disk = true;
+    if (!ok) do {
         nvrtcResult r = g_nvrtc.CreateProgram(&prog, k->source.c_str(), (k->name + ".cu").c_str(), 0, nullptr, nullptr);
         if (r != NVRTC_SUCCESS) {
             err = std::string("nvrtcCreateProgram: ") + g_nvrtc.GetErrorString(r);
@@ -231,6 +301,7 @@ void compile_one(Kernel* k) {
         ok = true;
     } while (false);
     if (prog != nullptr) g_nvrtc.DestroyProgram(&prog);
+    if (ok && !from_disk) write_cached(cpath, k->cubin);
     if (char const* dir = std::getenv("QSX_JIT_DUMP")) {  // development aid: keep the generated source and the cubin
         std::string const base = std::string(dir) + "/" + k->name;
         if (FILE* f = std::fopen((base + ".cu").c_str(), "w")) {
@@ -248,7 +319,10 @@ void compile_one(Kernel* k) {
         std::lock_guard<std::mutex> lk(g_mu);
         g_stats.compile_seconds += dt;
         if (ok) {
-            ++g_stats.compiled;
+            if (from_disk)
+                ++g_stats.disk_hits;
+            else
+                ++g_stats.compiled;
         } else {
             ++g_stats.failed;
             g_last_error = err;

@@ -34,7 +34,7 @@ cudaError_t launch(Kernel* k, double2* u, int log2_ncols, int log2_ncb, uint32_t
                    size_t smem, cudaStream_t stream);
 
 struct Stats {
-    uint64_t requested = 0, compiled = 0, failed = 0, hits = 0, launches = 0;
+    uint64_t requested = 0, compiled = 0, failed = 0, hits = 0, launches = 0, disk_hits = 0;
     double compile_seconds = 0;  // summed over the worker threads
     int workers            = 0;
 };

@@ -711,7 +711,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) 
 }
 
 template <int K>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, K >= 6 ? 1 : 2)
     dense_kernel(double2* __restrict__ u, const unsigned char* __restrict__ gprog, int log2_ncols, int log2_ncb,
                  uint32_t n_tiles) {
     constexpr int D   = 1 << K;        // complex components per vector
@@ -756,17 +756,28 @@ __global__ void __launch_bounds__(256, 2)
     int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     int const g = lane >> 2, t = lane & 3;
     double* const tile_d = reinterpret_cast<double*>(tile);
+    // Column swizzle: a tile row is 8 columns x 16 B = all 32 banks, so the same column of different rows is the same
+    // bank.  The C fragments of one store instruction cover 4 rows (components 4rb .. 4rb+3) x columns {0,2,4,6}: a
+    // 4-way conflict on 16 banks (ncu, round 1: 46 % of the shared-memory wavefronts were conflicts).  XOR-ing the
+    // column with block bit 0 of the row puts components 4rb+{1,3} on the odd columns: every bank is hit exactly twice,
+    // the minimum for 256 bytes.  Loads (16 consecutive doubles of one row per quarter warp) are unaffected.
+    int const swz_bit = block_local[0];
+    auto swz = [&](uint32_t row) { return (row >> swz_bit) & 1u; };
     // per-lane fragment offsets (in doubles, relative to the j base row), fixed for the whole launch
-    uint32_t boff[KB], ooff[RB];
+    // (the j base row has block bit 0 clear, so the swizzle of a component row is the component's bit 0)
+    uint32_t boff[KB], ooff[RB], ooff2[RB];
 #pragma unroll
     for (int kb = 0; kb < KB; ++kb) {
         int const kidx = 4 * kb + t;  // real component index = 2*c + part
-        boff[kb]       = (((comp_row[kidx >> 1] << 3) + g) << 1) + (kidx & 1);
+        int const c    = kidx >> 1;
+        boff[kb]       = (((comp_row[c] << 3) + ((uint32_t)g ^ (uint32_t)(c & 1))) << 1) + (kidx & 1);
     }
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) {
         int const ridx = rb * 8 + g;  // output real component = 2*c' + part'
-        ooff[rb]       = (((comp_row[ridx >> 1] << 3) + 2 * t) << 1) + (ridx & 1);
+        int const c    = ridx >> 1;
+        ooff[rb]       = (((comp_row[c] << 3) + ((uint32_t)(2 * t) ^ (uint32_t)(c & 1))) << 1) + (ridx & 1);
+        ooff2[rb]      = (((comp_row[c] << 3) + ((uint32_t)(2 * t + 1) ^ (uint32_t)(c & 1))) << 1) + (ridx & 1);
     }
 
     for (uint32_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
@@ -780,7 +791,7 @@ __global__ void __launch_bounds__(256, 2)
         //      thread in flight at once without staging registers ----
         for (int l = threadIdx.x >> 3; l < rows; l += blockDim.x >> 3) {
             const double2* const src = u + ((size_t)(row_outer | growl[l]) << log2_ncols) + col;
-            uint32_t const dst       = (uint32_t)__cvta_generic_to_shared(tile + (l << 3) + cw);
+            uint32_t const dst       = (uint32_t)__cvta_generic_to_shared(tile + (l << 3) + (cw ^ swz((uint32_t)l)));
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
         }
         asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
@@ -814,15 +825,15 @@ __global__ void __launch_bounds__(256, 2)
             __syncwarp();  // every lane has read its B fragments of this j
 #pragma unroll
             for (int rb = 0; rb < RB; ++rb) {
-                jbase[ooff[rb]]     = out[rb][0];  // column 2t
-                jbase[ooff[rb] + 2] = out[rb][1];  // column 2t + 1
+                jbase[ooff[rb]]  = out[rb][0];  // column 2t
+                jbase[ooff2[rb]] = out[rb][1];  // column 2t + 1
             }
         }
         __syncthreads();
 
 #pragma unroll 8
         for (int l = threadIdx.x >> 3; l < rows; l += blockDim.x >> 3)
-            __stcg(u + ((size_t)(row_outer | growl[l]) << log2_ncols) + col, tile[(l << 3) + cw]);
+            __stcg(u + ((size_t)(row_outer | growl[l]) << log2_ncols) + col, tile[(l << 3) + (cw ^ swz((uint32_t)l))]);
         __syncthreads();  // the tile buffer is reused by the next iteration
     }
 }
@@ -1058,6 +1069,7 @@ cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, uint64_t grid_ncols,
             case 3: return launch_dense_k<3>(u, ncols, hs, prog, s);
             case 4: return launch_dense_k<4>(u, ncols, hs, prog, s);
             case 5: return launch_dense_k<5>(u, ncols, hs, prog, s);
+            case 6: return launch_dense_k<6>(u, ncols, hs, prog, s);
             default: return cudaErrorInvalidValue;
         }
     }

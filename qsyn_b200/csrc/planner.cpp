@@ -325,6 +325,11 @@ int build_plan(int n_qubits, uint64_t ncols, const qsx_gate* gates, size_t n_gat
             cfg.R     = 2;
             cfg.m_cap = std::max(cfg.m_cap, 2);
         }
+    for (LoweredOp const& op : plan.ops)
+        if (op.kind == OP_DENSE && cfg.log2w != 3) {
+            msg = "gate " + std::to_string(op.src_gate) + ": dense gates with >= 3 targets need tiles of 8 columns (>= 8 columns per shard, default log2_tile_cols)";
+            return QSX_ERR_UNSUPPORTED;
+        }
     cfg.dense_k = 0;
     if (o.dense_block != 0) {
         if (o.dense_block < 3 || o.dense_block > kMaxDenseK) {

@@ -17,11 +17,16 @@ struct LoweredOp {
     int      dbit  = -1;  // OP_DIAG: row bit selecting d0/d1 (needs no locality)
     uint32_t req   = 0;   // required-one mask over global row bits (controls; phase-type: incl. the phase bit)
     double   c[8]  = {0, 0, 0, 0, 0, 0, 0, 0};
-    std::vector<double> mat;  // OP_U2: 4x4 complex, row-major
+    std::vector<double> mat;  // OP_U2: 4x4 complex, row-major; OP_DENSE: 2^k x 2^k complex, row-major
+    std::vector<int> dbits;   // OP_DENSE: global row bit of matrix-index bit i (i = 0 is the least significant)
     int      src_gate = -1;
     double   frac     = 1.0;  // touched fraction f of SURVEY 8(d)
 
-    uint32_t tmask() const { return (t0 >= 0 ? 1u << t0 : 0u) | (t1 >= 0 ? 1u << t1 : 0u); }
+    uint32_t tmask() const {
+        uint32_t m = (t0 >= 0 ? 1u << t0 : 0u) | (t1 >= 0 ? 1u << t1 : 0u);
+        for (int b : dbits) m |= 1u << b;
+        return m;
+    }
     uint32_t dmask() const { return req | (dbit >= 0 ? 1u << dbit : 0u); }
 };
 

@@ -124,9 +124,42 @@ int lower_gate(int n, const qsx_gate& g, int gate_index, double tol, std::vector
         out.push_back(std::move(op));
         return QSX_OK;
     }
-    msg = "gate " + std::to_string(gate_index) + ": " + std::to_string(nt) +
-          "-target dense gates are not supported (flatten nested circuits on the host)";
-    return QSX_ERR_UNSUPPORTED;
+    // >= 3 targets (a nested circuit handed over as one matrix, a user-defined k-qubit unitary): ONE dense block on the
+    // FP64 tensor pipe.  Controls become further block bits: the block matrix is the identity except where every control
+    // bit is 1 (qtensor.hpp:346-372: direct_sum(I, target) with the controls as most significant bits).
+    int const k = nt + nc;
+    if (k > kMaxDenseK) {
+        msg = "gate " + std::to_string(gate_index) + ": a dense gate on " + std::to_string(k) + " qubits (targets + controls) exceeds the " +
+              std::to_string(kMaxDenseK) + "-qubit dense block; decompose it on the host";
+        return QSX_ERR_UNSUPPORTED;
+    }
+    if (n < 3) {
+        msg = "gate " + std::to_string(gate_index) + ": dense blocks need at least 3 qubits";
+        return QSX_ERR_UNSUPPORTED;
+    }
+    LoweredOp op;
+    op.kind     = OP_DENSE;
+    op.src_gate = gate_index;
+    op.frac     = 1.0;
+    // matrix-index bit i: targets first (the LAST target is the least significant bit of the gate matrix), then controls
+    for (int i = 0; i < nt; ++i) op.dbits.push_back(n - 1 - g.qubits[nc + nt - 1 - i]);
+    for (int i = 0; i < nc; ++i) op.dbits.push_back(n - 1 - g.qubits[i]);
+    size_t const D = size_t{1} << k, Dt = size_t{1} << nt;
+    op.mat.assign(2 * D * D, 0.0);
+    bool identity = true;
+    for (size_t r = 0; r < D; ++r)
+        for (size_t c = 0; c < D; ++c) {
+            double re = r == c ? 1.0 : 0.0, im = 0.0;
+            if ((r >> nt) == (D >> nt) - 1 && (c >> nt) == (D >> nt) - 1) {  // every control bit set in both indices
+                size_t const e = ((r & (Dt - 1)) * Dt + (c & (Dt - 1)));
+                re = snap1(g.matrix[2 * e], tol), im = snap1(g.matrix[2 * e + 1], tol);
+            }
+            op.mat[2 * (r * D + c)] = re, op.mat[2 * (r * D + c) + 1] = im;
+            if (re != (r == c ? 1.0 : 0.0) || im != 0.0) identity = false;
+        }
+    if (identity) return QSX_OK;
+    out.push_back(std::move(op));
+    return QSX_OK;
 }
 
 }  // namespace qsx::detail

@@ -288,15 +288,50 @@ void finish_sweep(Plan& plan, std::vector<int> chosen, uint32_t S, std::vector<i
 
 }  // namespace
 
-void schedule(Plan& plan) {
+// One dense sweep for a single OP_DENSE op (a user gate with >= 3 targets): dense_kernel<k>
+void dense_op_sweep(Plan& plan, int idx) {
     PlanConfig const& cfg = plan.cfg;
-    size_t const N        = plan.ops.size();
+    LoweredOp const& op   = plan.ops[idx];
+    int const k           = (int)op.dbits.size();
+    PlannedSweep sw;
+    sw.block_bits   = op.dbits;
+    sw.block_matrix = op.mat;
+    sw.block_ops    = {idx};
+    uint32_t T      = op.tmask();
+    // tile: the block bits plus other row bits for a full CTA (k = 6 keeps 2^8 rows: its matrix alone takes 130 KiB)
+    int const m_want = std::min(cfg.n, std::max(k, k >= 6 ? 8 : 9));
+    for (int b = 0; b < cfg.n && popc(T) < m_want; ++b) T |= 1u << b;
+    for (int b = 0; b < cfg.n; ++b)
+        if ((T >> b) & 1u) sw.tile_bits.push_back(b);
+    sw.alg_bytes = 32.0 * std::ldexp(1.0, cfg.n) * (double)cfg.ncols;
+    plan.stats.alg_bytes_per_run += sw.alg_bytes;
+    ++plan.stats.n_dense_blocks;
+    plan.sweeps.push_back(std::move(sw));
+}
+
+void schedule_range(Plan& plan, size_t begin, size_t N);
+
+void schedule(Plan& plan) {
+    // a dense user gate is a sweep of its own: the ops before it and after it are scheduled separately
+    size_t begin = 0;
+    for (size_t i = 0; i < plan.ops.size(); ++i)
+        if (plan.ops[i].kind == OP_DENSE) {
+            schedule_range(plan, begin, i);
+            dense_op_sweep(plan, (int)i);
+            begin = i + 1;
+        }
+    schedule_range(plan, begin, plan.ops.size());
+}
+
+void schedule_range(Plan& plan, size_t begin, size_t N) {
+    PlanConfig const& cfg = plan.cfg;
+    if (begin >= N) return;
     if (!cfg.fuse) {
-        for (size_t i = 0; i < N; ++i) finish_sweep(plan, {(int)i}, plan.ops[i].tmask());
+        for (size_t i = begin; i < N; ++i) finish_sweep(plan, {(int)i}, plan.ops[i].tmask());
         return;
     }
     std::vector<char> done(N, 0);
-    size_t first = 0;
+    size_t first = begin;
     // One scan of the pending ops: an op joins the sweep if it commutes past everything skipped
     // so far and its non-diagonal targets fit the tile.  `allowed` restricts the tile bits
     // (search); without it the tile grows first come, first served up to m_cap bits.
@@ -457,6 +492,11 @@ void schedule_dense(Plan& plan) {
     while (true) {
         while (first < N && done[first]) ++first;
         if (first >= N) break;
+        if (plan.ops[first].kind == OP_DENSE) {  // a user gate that already is a dense block
+            done[first] = 1;
+            dense_op_sweep(plan, (int)first);
+            continue;
+        }
         if (popc(plan.ops[first].tmask() | plan.ops[first].dmask()) > k) {
             // touches more than k bits (e.g. cccx for k = 3): no dense block can hold it ->
             // an interpreted sweep of its own
@@ -473,7 +513,7 @@ void schedule_dense(Plan& plan) {
             ++scanned;
             LoweredOp const& op = plan.ops[i];
             uint32_t const bits = op.tmask() | op.dmask();  // a dense matrix needs every touched bit inside
-            if (pk.passes(op) && popc(S | bits) <= k) {
+            if (op.kind != OP_DENSE && pk.passes(op) && popc(S | bits) <= k) {
                 S |= bits;
                 chosen.push_back((int)i);
                 done[i] = 1;

@@ -45,6 +45,8 @@ enum OpKind : int32_t {
     OP_U2    = 7,  // dense 4x4 on (t0,t1) (t0 = MSB)
     OP_NEG   = 8,  // PHASE with w = -1  (snapped Z / CZ)
     OP_MULI  = 9,  // PHASE with w = +-i (snapped S / Sdg), c[0] = +-1
+    OP_DENSE = 10, // dense 2^k x 2^k matrix on k = 3..kMaxDenseK row bits (user gates with >= 3 targets, controls folded
+                   // in): never interpreted -- always a dense sweep of its own (dense_kernel<k>, FP64 tensor pipe)
 };
 
 // kinds the kernel interprets
@@ -154,7 +156,7 @@ struct alignas(16) DevSweep {
     //                    component index); then the REAL form of the block matrix,
     //                    A[(2c'+p')][(2c+p)] with p = 0 re / 1 im, 2^(k+1) rows of dense_lda(k) doubles
 };
-constexpr int kMaxDenseK = 5;
+constexpr int kMaxDenseK = 6;
 QSX_HD constexpr int dense_lda(int k) { return (2 << k) + 2; }  // +2 doubles: conflict-free A fragments
 static_assert(sizeof(DevSweep) % 16 == 0, "DevSweep layout");
 

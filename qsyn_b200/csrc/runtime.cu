@@ -1,6 +1,7 @@
 // runtime.cu -- the C ABI of include/qsx.h: device contexts, shard storage, plan execution,
 // equivalence reduction.  CUDA lives only behind this file, kernels.cu, comm.cpp and jit.cpp.
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -172,7 +173,11 @@ void request_jit_kernels(qsx::Plan& pl) {
     if (pl.cfg.jit == 0 || !pl.jit_kernels.empty() || pl.sweeps.empty()) return;
     pl.jit_kernels.assign(pl.sweeps.size(), nullptr);
     if (!qsx::jit::available(nullptr)) return;
-    for (size_t s = 0; s < pl.sweeps.size(); ++s) {
+    // every process of a job requests the same kernels: each starts at its own offset, so that together with the
+    // on-disk cache (jit.cpp) the ranks compile different kernels first and pick up each other's results
+    size_t const n_sw = pl.sweeps.size(), start = ((size_t)getpid() * 2654435761u >> 7) % n_sw;
+    for (size_t i = 0; i < n_sw; ++i) {
+        size_t const s          = (start + i) % n_sw;
         qsx::DevSweep const& hs = *reinterpret_cast<qsx::DevSweep const*>(pl.blob.data() + pl.sweep_offset[s]);
         if (hs.dense_k != 0) continue;
         int const log2_threads = hs.m - pl.cfg.R + hs.log2w;
@@ -410,6 +415,7 @@ int qsx_jit_get_stats(qsx_jit_stats* out) {
     out->requested = st.requested, out->cache_hits = st.hits, out->compiled = st.compiled, out->failed = st.failed;
     out->launches = st.launches, out->compile_seconds = st.compile_seconds, out->workers = st.workers;
     out->available = qsx::jit::available(nullptr) ? 1 : 0;
+    out->disk_hits = st.disk_hits;
     return QSX_OK;
 }
 

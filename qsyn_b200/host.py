@@ -28,6 +28,7 @@ def lib() -> C.CDLL:
             "qsxh_circuit_from_qasm_text": [C.c_char_p, C.POINTER(vp)],
             "qsxh_circuit_from_qasm_file": [C.c_char_p, C.POINTER(vp)],
             "qsxh_circuit_append": [vp, C.c_char_p, C.c_char_p, C.POINTER(sz), sz],
+            "qsxh_circuit_append_circuit": [vp, vp, sz, C.POINTER(sz), sz],
             "qsxh_circuit_info": [vp, C.POINTER(sz), C.POINTER(sz)],
             "qsxh_circuit_gate_repr": [vp, sz, C.c_char_p, sz, C.POINTER(sz)],
             "qsxh_circuit_gate_stream": [vp, C.POINTER(C.POINTER(abi.GateStruct)), C.POINTER(sz)],
@@ -78,6 +79,12 @@ class Circuit:
     def append(self, gate: str, qubits, phase: str | None = None) -> "Circuit":
         q = (C.c_size_t * len(qubits))(*[int(x) for x in qubits])
         _check(lib().qsxh_circuit_append(self._h, gate.encode(), phase.encode() if phase is not None else None, q, len(qubits)))
+        return self
+
+    def append_circuit(self, sub: "Circuit", qubits, n_ctrls: int = 0) -> "Circuit":
+        """`sub` as ONE gate on `qubits` (controls first): a nested QCir used as an Operation."""
+        q = (C.c_size_t * len(qubits))(*[int(x) for x in qubits])
+        _check(lib().qsxh_circuit_append_circuit(self._h, sub._h, n_ctrls, q, len(qubits)))
         return self
 
     @property

@@ -108,6 +108,22 @@ int qsxh_circuit_append(qsxh_circuit* c, const char* gate, const char* phase, co
     });
 }
 
+int qsxh_circuit_append_circuit(qsxh_circuit* c, const qsxh_circuit* sub, size_t n_ctrls, const size_t* qubits, size_t n_qubits) {
+    if (c == nullptr || sub == nullptr || (n_qubits > 0 && qubits == nullptr)) return fail(QSX_ERR_BAD_ARG, "null argument");
+    return guarded([&] {
+        if (sub->qcir.get_num_qubits() + n_ctrls != n_qubits) return fail(QSX_ERR_BAD_ARG, "the sub-circuit's qubits plus the controls must match the qubit list");
+        qsyn::QubitIdList ids(qubits, qubits + n_qubits);
+        if (!qsyn::qcir::QCirGate::qubit_id_is_unique(ids)) return fail(QSX_ERR_BAD_ARG, "duplicate qubit ids");
+        for (auto q : ids)
+            if (q >= c->qcir.get_num_qubits()) return fail(QSX_ERR_BAD_ARG, std::format("Qubit ID {} does not exist!!", q));
+        qsyn::qcir::Operation op = sub->qcir;
+        if (n_ctrls > 0) op = qsyn::qcir::ControlGate(op, n_ctrls);
+        c->qcir.append(op, ids);
+        c->stream.reset();
+        return (int)QSX_OK;
+    });
+}
+
 int qsxh_circuit_info(const qsxh_circuit* c, size_t* n_qubits, size_t* n_gates) {
     if (c == nullptr) return fail(QSX_ERR_BAD_ARG, "null circuit");
     if (n_qubits != nullptr) *n_qubits = c->qcir.get_num_qubits();

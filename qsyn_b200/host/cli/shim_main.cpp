@@ -637,5 +637,8 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "Error: %s\n", e.what());
         return 1;
     }
+    // tensors (and their device shards) go first, then the communicators, while the CUDA runtime is still alive
+    sh.tensor_mgr.clear();
+    qsx_shutdown();
     return 0;
 }

@@ -83,6 +83,7 @@ std::optional<StreamGate> lower_to_stream(Operation const& op) {
         g.n_ctrls += cg.get_num_ctrls();
         target = cg.get_target_operation();
     }
+    if (target.is<QCir>()) return std::nullopt;  // (flattened by append_flat, never lowered as one matrix)
     auto t = to_tensor(target);
     if (!t.has_value()) return std::nullopt;
     g.n_targets  = target.get_num_qubits();
@@ -119,25 +120,62 @@ void update_tensor_pin(Qubit2TensorPinMap& qubit2pin, QCirGate const& gate, size
     }
 }
 
+// A gate of the stream with its qubits (controls first).  A (controlled) nested circuit -- the reference contracts
+// to_tensor(inner QCir) as ONE 2^k x 2^k gate tensor (qcir.hpp:181-183, qcir_to_tensor.cpp:147 through operation.hpp) --
+// is FLATTENED into its own gates, each carrying the outer controls: C(AB) = C(A) C(B), same operator, and nothing wider
+// than the widest basic gate ever crosses the ABI.
+struct FlatGate {
+    StreamGate g;
+    QubitIdList qubits;
+};
+
+bool append_flat(Operation const& op, QubitIdList const& qubits, std::vector<FlatGate>& out) {
+    size_t n_ctrls   = 0;
+    Operation target = op;
+    while (target.is<ControlGate>()) {
+        auto const cg = target.get_underlying<ControlGate>();
+        n_ctrls += cg.get_num_ctrls();
+        target = cg.get_target_operation();
+    }
+    if (target.is<QCir>()) {
+        auto const inner = target.get_underlying<QCir>();
+        if (inner.get_num_qubits() + n_ctrls != qubits.size()) return false;
+        for (QCirGate* ig : inner.get_gates()) {
+            QubitIdList mapped(qubits.begin(), qubits.begin() + static_cast<std::ptrdiff_t>(n_ctrls));
+            for (auto q : ig->get_qubits()) mapped.push_back(qubits[n_ctrls + q]);
+            Operation const wrapped = n_ctrls > 0 ? Operation(ControlGate(ig->get_operation(), n_ctrls)) : ig->get_operation();
+            if (!append_flat(wrapped, mapped, out)) return false;
+        }
+        return true;
+    }
+    auto g = lower_to_stream(op);
+    if (!g.has_value() || qubits.size() > QSX_MAX_GATE_QUBITS) return false;
+    out.push_back(FlatGate{std::move(*g), qubits});
+    return true;
+}
+
 int stop_trampoline(void*) { return stop_requested() ? 1 : 0; }
 
 }  // namespace
 
 std::optional<GateStream> to_gate_stream(QCir const& qcir) {
     GateStream gs;
-    gs.gates.reserve(qcir.get_num_gates());
-    gs.matrices.reserve(qcir.get_num_gates());
+    std::vector<FlatGate> flat;
+    flat.reserve(qcir.get_num_gates());
     for (auto const& gate : qcir.get_gates()) {
-        auto g = lower_to_stream(gate->get_operation());
-        if (!g.has_value() || gate->get_num_qubits() > QSX_MAX_GATE_QUBITS) {
+        if (!append_flat(gate->get_operation(), gate->get_qubits(), flat)) {
             spdlog::error("Conversion of Gate {} ({}) to Tensor is not supported yet!!", gate->get_id(), gate->get_operation().get_repr());
             return std::nullopt;
         }
-        gs.matrices.push_back(std::move(g->matrix));
+    }
+    gs.gates.reserve(flat.size());
+    gs.matrices.reserve(flat.size());
+    for (auto& f : flat) {
+        gs.matrices.push_back(std::move(f.g.matrix));
         qsx_gate d{};
-        d.n_ctrls   = static_cast<int32_t>(g->n_ctrls);
-        d.n_targets = static_cast<int32_t>(g->n_targets);
-        for (size_t p = 0; p < gate->get_num_qubits(); ++p) d.qubits[p] = static_cast<int32_t>(gate->get_qubit(p));
+        d.n_ctrls   = static_cast<int32_t>(f.g.n_ctrls);
+        d.n_targets = static_cast<int32_t>(f.g.n_targets);
+        for (size_t p = 0; p < f.qubits.size(); ++p) d.qubits[p] = static_cast<int32_t>(f.qubits[p]);
         d.matrix = gs.matrices.back().data();  // heap storage: stable when the outer vector grows
         gs.gates.push_back(d);
     }
@@ -166,7 +204,7 @@ std::optional<QTensor<double>> to_tensor(QCir const& qcir) try {
     }
 
     bool const tracing = spdlog::get_level() <= spdlog::level::trace;
-    std::vector<StreamGate> lowered;
+    std::vector<FlatGate> lowered;
     std::vector<qsx_gate> stream;
     lowered.reserve(qcir.get_num_gates());
     for (auto const& gate : qcir.get_gates()) {
@@ -175,23 +213,20 @@ std::optional<QTensor<double>> to_tensor(QCir const& qcir) try {
             return std::nullopt;
         }
         spdlog::debug("Gate {} ({})", gate->get_id(), gate->get_operation().get_repr());
-        auto g = lower_to_stream(gate->get_operation());
-        if (!g.has_value() || gate->get_num_qubits() > QSX_MAX_GATE_QUBITS) {
+        if (!append_flat(gate->get_operation(), gate->get_qubits(), lowered)) {
             spdlog::error("Conversion of Gate {} ({}) to Tensor is not supported yet!!", gate->get_id(), gate->get_operation().get_repr());
             return std::nullopt;
         }
-        lowered.push_back(std::move(*g));
         if (tracing) update_tensor_pin(qubit_to_pins, *gate, 2 * n);
     }
-    size_t i = 0;
-    for (auto const& gate : qcir.get_gates()) {
+    stream.reserve(lowered.size());
+    for (auto const& f : lowered) {
         qsx_gate d{};
-        d.n_ctrls   = static_cast<int32_t>(lowered[i].n_ctrls);
-        d.n_targets = static_cast<int32_t>(lowered[i].n_targets);
-        for (size_t p = 0; p < gate->get_num_qubits(); ++p) d.qubits[p] = static_cast<int32_t>(gate->get_qubit(p));
-        d.matrix = lowered[i].matrix.data();
+        d.n_ctrls   = static_cast<int32_t>(f.g.n_ctrls);
+        d.n_targets = static_cast<int32_t>(f.g.n_targets);
+        for (size_t p = 0; p < f.qubits.size(); ++p) d.qubits[p] = static_cast<int32_t>(f.qubits[p]);
+        d.matrix = f.g.matrix.data();
         stream.push_back(d);
-        ++i;
     }
 
     int const rc = unitary.apply(stream, &stop_trampoline, nullptr);

@@ -399,6 +399,9 @@ public:
 
     void set_filename(std::string const& f) { _filename = f; }
     std::string get_filename() const { return _filename; }
+    // additional APIs to make qcir::QCir an qcir::Operation (qcir.hpp:181-183): a circuit can be a gate of another one
+    std::string get_type() const { return "qcir"; }
+    std::string get_repr() const { return _filename; }
     void add_procedures(std::vector<std::string> const& ps) { _procedures.insert(_procedures.end(), ps.begin(), ps.end()); }
     void add_procedure(std::string const& p) { _procedures.emplace_back(p); }
     std::vector<std::string> const& get_procedures() const { return _procedures; }
@@ -435,6 +438,18 @@ private:
     std::string _filename;
     std::vector<std::string> _procedures;
 };
+
+// a circuit used as a gate (qcir.cpp:563-567; is_clifford: every gate is)
+inline Operation adjoint(QCir const& qcir) {
+    auto copy = qcir;
+    copy.adjoint_inplace();
+    return copy;
+}
+inline bool is_clifford(QCir const& qcir) {
+    for (QCirGate* g : qcir.get_gates())
+        if (!is_clifford(g->get_operation())) return false;
+    return true;
+}
 
 // QASM 2.0 reader with the reference's behaviour (qcir_reader.cpp:47-120)
 std::optional<QCir> from_qasm(std::filesystem::path const& filepath);

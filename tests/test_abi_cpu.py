@@ -96,10 +96,12 @@ def test_schedule_preserves_the_unitary(n, g, seed, fuse):
         assert err < 1e-13, err
 
 
-@pytest.mark.parametrize("k", [3, 4, 5])
+@pytest.mark.parametrize("k", [3, 4, 5, 6])
 def test_dense_block_folding_preserves_the_unitary(k):
     """dense_block = k: the whole gate stream becomes dense 2^k x 2^k blocks (host products)."""
     for n, g, seed in [(5, 120, 4), (7, 150, 6), (9, 300, 16)]:
+        if n < k:
+            continue
         qc = _rand_circuit(n, g, seed)  # seed 16 contains cccx / ccswap: wider than a k = 3 / 4 block
         want = O.to_matrix_rowform(qc)
         plan = Q.Plan(n, 2**n, O.gate_stream(qc), Q.PlanOptions(dense_block=k))
@@ -113,6 +115,57 @@ def test_dense_block_folding_preserves_the_unitary(k):
         Q.Plan(5, 32, [], Q.PlanOptions(dense_block=2))
     with pytest.raises(Q.QsxError):
         Q.Plan(4, 16, [], Q.PlanOptions(dense_block=5))
+    with pytest.raises(Q.QsxError):
+        Q.Plan(8, 256, [], Q.PlanOptions(dense_block=7))
+
+
+def _rand_unitary(k, seed):
+    rng = np.random.default_rng(seed)
+    a = rng.standard_normal((2**k, 2**k)) + 1j * rng.standard_normal((2**k, 2**k))
+    q, r = np.linalg.qr(a)
+    return q * (np.diag(r) / np.abs(np.diag(r)))
+
+
+def _circuit_with_dense_gates(n, seed):
+    """random Clifford+T stream with user gates of 3..6 qubits (targets + controls) sprinkled in: what a nested circuit
+    handed over as ONE matrix looks like (reference: to_tensor(QCir) used as a gate, qcir_to_tensor.cpp:147)."""
+    rng = np.random.default_rng(seed)
+    gs = O.gate_stream(O.qcir_from_qasm_text(O.random_clifford_t_qasm(n, 60, seed)))
+    out = []
+    for i, g in enumerate(gs):
+        out.append(g)
+        if i % 12 == 5:
+            k = int(rng.integers(3, min(n, 6) + 1))
+            nc = int(rng.integers(0, k - 2))  # at least 3 targets
+            qs = [int(q) for q in rng.choice(n, k, replace=False)]
+            out.append((nc, qs, _rand_unitary(k - nc, seed * 100 + i)))
+    return out
+
+
+def _oracle_matrix(n, gs):
+    u = np.eye(2**n, dtype=np.complex128)
+    for nc, qs, m in gs:
+        u = O.apply_gate_rows(u, n, O.mat_control(m, nc), qs)
+    return u
+
+
+@pytest.mark.parametrize("n,seed", [(3, 1), (5, 2), (6, 3), (8, 4), (9, 5)])
+def test_dense_user_gates_become_dense_sweeps(n, seed):
+    gs = _circuit_with_dense_gates(n, seed)
+    want = _oracle_matrix(n, gs)
+    for opt in (None, Q.PlanOptions(fuse=0), Q.PlanOptions(dense_block=4 if n >= 4 else 3), Q.PlanOptions(reg_qubits=3, tile_qubits=6)):
+        plan = Q.Plan(n, 2**n, gs, opt)
+        d, st = plan.dump(), plan.stats()
+        n_dense_gates = sum(1 for nc, qs, m in gs if len(qs) - nc >= 3)
+        assert st.n_dense_blocks >= n_dense_gates > 0
+        seen = plan_sim.check_invariants(d)
+        assert len(seen) == st.n_ops
+        got = plan_sim.run_plan_uops(d, np.eye(2**n, dtype=np.complex128))
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-13
+    # too wide for a dense block: refused with the reference's "not supported" status, not a wrong answer
+    with pytest.raises(Q.QsxError) as ei:
+        Q.Plan(9, 512, [(0, list(range(7)), _rand_unitary(7, 1))])
+    assert ei.value.status == "QSX_ERR_UNSUPPORTED"
 
 
 def test_snapping_is_optional_and_small():

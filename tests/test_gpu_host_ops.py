@@ -127,3 +127,10 @@ def test_cli_qcir_equiv_and_tensor_write_read(tmp_path, goldens):
     assert rc == 0, out
     assert out.count("The two circuits are equivalent!!") == 2 and out.count("The two circuits are not equivalent!!") == 1
     assert "qsyn> tensor equiv 0 1 --strict\nEquivalent\n- Global Norm : 1\n- Global Phase: 0\n" in out
+
+
+def test_nested_circuit_gate_through_qc2ts():
+    from tests.test_host_layer import _nested_example
+    outer, want = _nested_example()
+    got = outer.qc2ts().to_numpy()
+    assert np.abs(got - want).max() < 1e-14

@@ -92,12 +92,13 @@ def test_kernel_cache_and_async_mode():
     assert st.jit_launches == st.launches
     assert frob_rel(u.download(), want) < TOL
     mid = abi.jit_stats()
-    assert mid.compiled - before.compiled >= 1 and mid.failed == before.failed
+    made = lambda a, b: (a.compiled + a.disk_hits) - (b.compiled + b.disk_hits)  # compiled here, or found in the on-disk cache
+    assert made(mid, before) >= 1 and mid.failed == before.failed
     plan2 = Q.Plan(n, 2**n, gs, Q.PlanOptions(jit=2))
     u.set_identity()
     st = plan2.run(u)
     after = abi.jit_stats()
-    assert st.jit_launches == st.launches and after.compiled == mid.compiled and after.cache_hits > mid.cache_hits
+    assert st.jit_launches == st.launches and made(after, mid) == 0 and after.cache_hits > mid.cache_hits
     # and the default (jit = 0) leaves small circuits to the interpreter
     st = Q.Unitary(n).apply(gs)
     assert st.jit_launches == 0

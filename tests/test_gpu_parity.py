@@ -296,10 +296,36 @@ def test_inverse_circuit_roundtrip_at_full_size():
     assert np.max(np.abs(band - want)) < 1e-12
 
 
-@pytest.mark.parametrize("k", [3, 4, 5])
+@pytest.mark.parametrize("n,seed", [(3, 1), (5, 2), (6, 3), (8, 4), (9, 5), (11, 6)])
+def test_dense_user_gates_on_the_tensor_pipe(n, seed):
+    """Gates with >= 3 targets (a nested circuit as ONE matrix, reference qcir_to_tensor.cpp:147 used as a gate; controls
+    folded into the block): each is a dense sweep of its own (dense_kernel<3..6>) between interpreted / specialised
+    sweeps -- the reference contracts them like any other gate tensor."""
+    from tests.test_abi_cpu import _circuit_with_dense_gates, _oracle_matrix
+    gs = _circuit_with_dense_gates(n, seed)
+    want = _oracle_matrix(n, gs)
+    for opt in (None, Q.PlanOptions(jit=2), Q.PlanOptions(fuse=0), Q.PlanOptions(dense_block=3)):
+        u = Q.Unitary(n)
+        u.apply(gs, opt)
+        assert frob_rel(u.download(), want) < TOL, (n, seed)
+        u.close()
+    if n >= 6:  # a column shard
+        u = Q.Unitary(n, 0, 2**n // 2, 2**n // 4)
+        u.apply(gs)
+        assert frob_rel(u.download(), want[:, 2**n // 2: 2**n // 2 + 2**n // 4]) < TOL
+    rng = np.random.default_rng(1)
+    wide = np.linalg.qr(rng.standard_normal((128, 128)) + 1j * rng.standard_normal((128, 128)))[0]
+    with pytest.raises(Q.QsxError) as ei:  # wider than the largest dense block: refused, like an unsupported gate in the reference
+        Q.Unitary(9).apply([(0, list(range(7)), wide)])
+    assert ei.value.status == "QSX_ERR_UNSUPPORTED"
+
+
+@pytest.mark.parametrize("k", [3, 4, 5, 6])
 def test_dense_blocks_on_the_tensor_pipe(k):
     """dense_block = k: every sweep is one dense 2^k x 2^k block applied with DMMA (dense_kernel<k>)."""
     for n, g, seed in [(5, 120, 4), (7, 200, 6), (9, 300, 16), (10, 200, 3)]:
+        if n < k:
+            continue
         qc = _rand_circuit(n, g, seed)
         want = O.to_matrix_rowform(qc)
         got = run_device(qc, Q.PlanOptions(dense_block=k))

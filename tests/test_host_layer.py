@@ -122,3 +122,37 @@ def test_tensor_equiv_text_through_the_host_layer(goldens):
     b.adjoint_inplace()
     r, text = a.equiv(b)
     assert text.startswith("Not Equivalent\n- Cosine Similarity: ")
+
+
+def _nested_example():
+    inner = host.Circuit(3)
+    inner.append("h", [0]).append("cx", [0, 2]).append("t", [1]).append("ccx", [2, 0, 1]).append("rz", [2], "pi/3")
+    outer = host.Circuit(6)
+    outer.append("h", [5]).append_circuit(inner, [4, 1, 3]).append("cx", [1, 0]).append_circuit(inner, [5, 2, 0, 3, 1], n_ctrls=2)
+
+    def mat_of(c):
+        u = np.eye(2**c.n_qubits, dtype=complex)
+        for nc, qs, m in c.gate_stream():
+            u = O.apply_gate_rows(u, c.n_qubits, O.mat_control(m, nc), qs)
+        return u
+
+    u_in = mat_of(inner)
+    want = np.eye(64, dtype=complex)
+    want = O.apply_gate_rows(want, 6, O.mat_h(), [5])
+    want = O.apply_gate_rows(want, 6, u_in, [4, 1, 3])  # the reference contracts to_tensor(inner) as ONE gate tensor
+    want = O.apply_gate_rows(want, 6, O.mat_control(O.mat_px(O.Phase(1)), 1), [1, 0])
+    want = O.apply_gate_rows(want, 6, O.mat_control(u_in, 2), [5, 2, 0, 3, 1])
+    return outer, want
+
+
+def test_nested_circuit_gate_is_flattened_into_the_stream():
+    """A QCir is an Operation in the reference (qcir.hpp:181-183); its gate tensor is to_tensor(inner) (qcir_to_tensor.cpp:147).
+    Here the (controlled) nested circuit is flattened: every inner gate carries the outer controls -- the same operator."""
+    outer, want = _nested_example()
+    assert outer.n_gates == 4
+    gs = outer.gate_stream()
+    assert len(gs) == 12 and max(len(qs) for _, qs, _ in gs) == 5  # ccx inside a doubly controlled circuit: 4 controls + 1 target
+    got = np.eye(64, dtype=complex)
+    for nc, qs, m in gs:
+        got = O.apply_gate_rows(got, 6, O.mat_control(m, nc), qs)
+    assert np.abs(got - want).max() < 1e-15
