@@ -1,4 +1,7 @@
 # Builds the B200 tensor-verification engine in-tree.
+# (-l:libstdc++.so.6 is spelled out on every g++ link line: the compiler wrapper of the build image, CXX=/opt/gcc/bin/g++,
+#  finds only libstdc++.a and links it STATICALLY into shared objects; with GCC 13 the stream / locale initialiser lives in
+#  the library, the static copy never runs it, and the first `istream >> double` inside libqsxhost.so crashed)
 #   make            -> qsyn_b200/lib/libqsx.so   (C ABI of include/qsx.h; CUDA sm_100a)
 #   make oracle     -> oracle/_build/*           (CPU checker, test infrastructure only)
 NVCC      ?= /usr/local/cuda/bin/nvcc
@@ -39,7 +42,7 @@ HOSTOBJS  := $(OBJDIR)/host_qcir_io.o $(OBJDIR)/host_qcir_to_tensor.o $(OBJDIR)/
 
 $(LIBHOST): $(HOSTOBJS) $(OBJDIR)/host_qsx_host.o $(LIBQSX)
 	$(CXX) -shared -o $@ $(HOSTOBJS) $(OBJDIR)/host_qsx_host.o \
-	    -L$(LIBDIR) -lqsx -Wl,-rpath,'$$ORIGIN'
+	    -L$(LIBDIR) -lqsx -l:libstdc++.so.6 -lm -Wl,-rpath,'$$ORIGIN'
 
 $(BCAST): $(CSRC)/tools/bcast_probe.cu
 	@mkdir -p bin
@@ -67,7 +70,7 @@ $(OBJDIR)/host_%.o: $(HOST)/cli/%.cpp $(HOSTHDRS)
 $(SHIM): $(HOSTOBJS) $(OBJDIR)/host_shim_main.o $(LIBQSX)
 	@mkdir -p bin
 	$(CXX) -o $@ $(HOSTOBJS) $(OBJDIR)/host_shim_main.o \
-	    -L$(LIBDIR) -lqsx -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
+	    -L$(LIBDIR) -lqsx -l:libstdc++.so.6 -lm -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.hpp) include/qsx.h $(wildcard qsyn_b200/host/util/*.hpp)
 	@mkdir -p $(OBJDIR)

@@ -156,3 +156,30 @@ def test_nested_circuit_gate_is_flattened_into_the_stream():
     for nc, qs, m in gs:
         got = O.apply_gate_rows(got, 6, O.mat_control(m, nc), qs)
     assert np.abs(got - want).max() < 1e-15
+
+
+def test_tensor_read_write_print_on_the_host(tmp_path):
+    """`tensor read` / `tensor write` / `tensor print` of a host tensor need no device (tensor.hpp:326-384, sk.log:19-20)."""
+    src = tmp_path / "m.csv"
+    src.write_text(" 0.126496-0.02764j,  0.169178-0.977043j\n-0.169178-0.977043j,  0.126496+0.02764j\n")
+    t = host.Tensor.read(src)
+    assert t.shape == [2, 2]
+    m = t.to_numpy()
+    assert m[0, 1] == 0.169178 - 0.977043j and m[1, 0] == -0.169178 - 0.977043j
+    assert t.print_string() == "{{ 0.126496-0.02764i ,  0.169178-0.977043i},\n {-0.169178-0.977043i,  0.126496+0.02764i }}"
+    out = tmp_path / "w.csv"
+    t.write(out)
+    assert out.read_text() == " 0.126496-0.02764j,  0.169178-0.977043j\n-0.169178-0.977043j,  0.126496+0.02764j\n"
+    assert abs(t.element(1, 1) - (0.126496 + 0.02764j)) == 0
+    # "j" alone after one number: purely imaginary (tensor.hpp:364-367)
+    src.write_text("2j, 1+0j\n 0+0j, -1j\n")
+    assert host.Tensor.read(src).to_numpy()[0, 0] == 2j
+
+
+def test_host_library_links_the_shared_cxx_runtime():
+    """A static libstdc++ inside libqsxhost.so (what the build image's compiler wrapper produces by default) never runs the
+    stream / locale initialiser of GCC 13 and crashes in the first `istream >> double`: the Makefile must link the .so."""
+    import subprocess
+    for path in (os.path.join(os.path.dirname(Q.lib_path()), "libqsxhost.so"), Q.lib_path()):
+        needed = subprocess.run(["readelf", "-d", path], capture_output=True, text=True).stdout
+        assert "libstdc++.so.6" in needed, path
