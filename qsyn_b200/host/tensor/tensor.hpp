@@ -22,6 +22,7 @@
 #include <complex>
 #include <cstddef>
 #include <format>
+#include <functional>
 #include <fstream>
 #include <initializer_list>
 #include <iostream>
@@ -438,58 +439,133 @@ Tensor<U> direct_sum(Tensor<U> const& t1, Tensor<U> const& t2) {
     return r;
 }
 
-// "{{ a, b},\n { c, d}}" in the style of xtensor's printer
+// "{{ a, b},\n { c, d}}" in the style of xtensor's printer (xio.hpp of xtensor 0.26, not part of the reference tree:
+// the layout below follows its published behaviour; the only sample the reference's tests hold is the 2 x 2 matrix of
+// tests/conversion/sk/ref/sk.log:19-20).  print_options defaults: more than `threshold` = 1000 elements are summarised
+// with `edgeitems` = 3 leading and trailing entries per axis ("..., " inside a row, "...," on a line of its own between
+// rows); a row wraps after floor(line_width = 75 / (cell width + 2)) cells.  A summarised DEVICE matrix only fetches the
+// rows it prints (DeviceUnitary::download_rows), never the whole 2^n x 2^n tensor.
 template <typename U>
 std::ostream& operator<<(std::ostream& os, Tensor<U> const& t) {
     auto const shape = t.shape();
-    auto const data  = t._host_view();
-    std::vector<std::string> cell(data.size());
+    size_t const nd  = shape.size();
+    size_t total     = 1;
+    for (size_t e : shape) total *= e;
+    constexpr size_t kThreshold = 1000, kEdge = 3, kLineWidth = 75;
+    bool const summarise = total > kThreshold;
+    // per axis: the indices that are printed (SIZE_MAX marks the gap)
+    std::vector<std::vector<size_t>> axis_idx(nd);
+    for (size_t a = 0; a < nd; ++a) {
+        if (summarise && shape[a] > 2 * kEdge) {
+            for (size_t i = 0; i < kEdge; ++i) axis_idx[a].push_back(i);
+            axis_idx[a].push_back(SIZE_MAX);
+            for (size_t i = shape[a] - kEdge; i < shape[a]; ++i) axis_idx[a].push_back(i);
+        } else {
+            for (size_t i = 0; i < shape[a]; ++i) axis_idx[a].push_back(i);
+        }
+    }
+    // the elements to print, in print order
+    std::vector<U> vals;
+    {
+        std::vector<size_t> lins;
+        std::vector<size_t> pos(nd, 0);
+        std::function<void(size_t, size_t)> walk = [&](size_t a, size_t lin) {
+            if (a == nd) {
+                lins.push_back(lin);
+                return;
+            }
+            for (size_t i : axis_idx[a])
+                if (i != SIZE_MAX) walk(a + 1, lin * shape[a] + i);
+        };
+        walk(0, 0);
+        bool fetched = false;
+        if constexpr (std::is_same_v<U, std::complex<double>>) {
+            if (summarise && t._dev.resident() && t._dev.as_matrix && nd == 2) {
+                std::vector<U> row(shape[1]);
+                size_t have = SIZE_MAX;
+                for (size_t lin : lins) {
+                    size_t const r = lin / shape[1], c = lin % shape[1];
+                    if (r != have) {
+                        t._dev.unitary.download_rows(r, 1, row.data());
+                        have = r;
+                    }
+                    vals.push_back(row[c]);
+                }
+                fetched = true;
+            }
+        }
+        if (!fetched) {
+            auto const data = t._host_view();
+            for (size_t lin : lins) vals.push_back(data[lin]);
+        }
+    }
+    std::vector<std::string> cell(vals.size());
     size_t width = 0;
     if constexpr (detail::is_complex<U>::value) {
-        std::vector<std::string> re(data.size()), im(data.size());
+        std::vector<std::string> re(vals.size()), im(vals.size());
         size_t wr = 0, wi = 0;
-        for (size_t i = 0; i < data.size(); ++i) {
-            re[i] = detail::trimmed(data[i].real());
+        for (size_t i = 0; i < vals.size(); ++i) {
+            re[i] = detail::trimmed(vals[i].real());
             if (re[i].back() == ' ') re[i].pop_back();
-            std::string m = detail::trimmed(std::abs(data[i].imag()));
+            std::string m = detail::trimmed(std::abs(vals[i].imag()));
             if (m.back() == ' ') m.pop_back();
-            im[i] = std::string(std::signbit(data[i].imag()) && data[i].imag() != 0 ? "-" : "+") + m + "i";
+            im[i] = std::string(std::signbit(vals[i].imag()) && vals[i].imag() != 0 ? "-" : "+") + m + "i";
             wr    = std::max(wr, re[i].size());
             wi    = std::max(wi, im[i].size());
         }
-        for (size_t i = 0; i < data.size(); ++i)
+        for (size_t i = 0; i < vals.size(); ++i)
             cell[i] = std::string(wr - re[i].size(), ' ') + re[i] + im[i] + std::string(wi - im[i].size(), ' ');
+        width = wr + wi;
     } else {
-        for (size_t i = 0; i < data.size(); ++i) {
-            cell[i] = detail::trimmed(static_cast<double>(data[i]));
+        for (size_t i = 0; i < vals.size(); ++i) {
+            cell[i] = detail::trimmed(static_cast<double>(vals[i]));
             width   = std::max(width, cell[i].size());
         }
         for (auto& c : cell) c = std::string(width - c.size(), ' ') + c;
     }
-    if (shape.empty()) return os << (cell.empty() ? "" : cell[0]);
-    size_t const nd = shape.size();
-    std::vector<size_t> idx(nd, 0);
-    for (size_t lin = 0; lin < data.size(); ++lin) {
-        size_t opened = 0;  // number of trailing axes at index 0
-        for (size_t a = nd; a-- > 0 && idx[a] == 0;) ++opened;
-        if (lin == 0) opened = nd;
-        if (lin != 0) {
-            os << ",";
-            if (opened > 0) {
-                os << std::string(opened, '\n') << std::string(nd - opened, ' ');
+    if (nd == 0) return os << (cell.empty() ? "" : cell[0]);
+    size_t const line_lim = kLineWidth / (width + 2);  // cells per line in the innermost axis
+    size_t next           = 0;
+    std::function<void(size_t, size_t)> out = [&](size_t a, size_t blanks) {
+        if (a == nd) {
+            os << cell[next++];
+            return;
+        }
+        bool const inner = a + 1 == nd;
+        std::string const indents(blanks, ' ');
+        size_t on_line = 0;
+        auto const& ix = axis_idx[a];
+        os << '{';
+        for (size_t k = 0; k < ix.size(); ++k) {
+            bool const last = k + 1 == ix.size();
+            if (ix[k] == SIZE_MAX) {
+                if (inner && line_lim != 0 && on_line >= line_lim)
+                    os << " ...,";
+                else if (!inner) {
+                    on_line = 0;
+                    os << "...,\n" << indents;
+                } else {
+                    os << "..., ";
+                }
+                continue;
+            }
+            if (inner && !(line_lim != 0 && on_line < line_lim)) {
+                os << "\n" << indents;
+                on_line = 0;
+            }
+            out(a + 1, blanks + 1);
+            if (last) break;
+            os << ',';
+            ++on_line;
+            if (inner) {
+                if (line_lim != 0 && on_line < line_lim) os << ' ';
             } else {
-                os << " ";
+                os << "\n" << indents;
             }
         }
-        os << std::string(opened, '{') << cell[lin];
-        size_t closed = 0;
-        for (size_t a = nd; a-- > 0;) {
-            if (++idx[a] < shape[a]) break;
-            idx[a] = 0;
-            ++closed;
-        }
-        os << std::string(closed, '}');
-    }
+        os << '}';
+    };
+    out(0, 1);
     return os;
 }
 

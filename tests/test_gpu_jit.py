@@ -47,6 +47,8 @@ def test_specialised_sweeps_equal_the_interpreter(n, g, seed, extra, opts):
     qc = _rand_circuit(n, g, seed, extra=extra)
     gs = O.gate_stream(qc)
     want = O.to_matrix_rowform(qc)
+    opts = dict(opts)
+    opts.setdefault("tile_qubits", 9)  # the default tile depends on the executor (9 specialised, 8 interpreted): same PLAN for both
     interp, st_i = _run(n, gs, jit=-1, **opts)
     spec, st_j = _run(n, gs, jit=2, **opts)
     assert st_i.jit_launches == 0
@@ -65,8 +67,8 @@ def test_specialised_sweeps_on_shards_blocks_and_existing_data():
             outs = []
             for jit in (-1, 2):
                 u = Q.Unitary(n, 0, col0, ncols)
-                u.apply(gs, Q.PlanOptions(jit=jit, l2_block_mib=blk))   # from the lazy identity
-                u.apply(gs2, Q.PlanOptions(jit=jit, l2_block_mib=blk))  # on existing data
+                u.apply(gs, Q.PlanOptions(jit=jit, l2_block_mib=blk, tile_qubits=9))   # from the lazy identity
+                u.apply(gs2, Q.PlanOptions(jit=jit, l2_block_mib=blk, tile_qubits=9))  # on existing data
                 outs.append(u.download())
                 u.close()
             assert np.array_equal(outs[0], outs[1]), (col0, ncols, blk)
@@ -111,7 +113,7 @@ def test_c2_specialised_equals_interpreted_at_full_size():
     outs, sums = [], []
     for jit in (-1, 2):
         u = Q.Unitary(n)
-        st = u.apply(gs, Q.PlanOptions(jit=jit))
+        st = u.apply(gs, Q.PlanOptions(jit=jit, tile_qubits=9))
         assert (st.jit_launches == st.launches) == (jit == 2)
         outs.append(u.download_block(0, 2**n, 1000, 64))
         sums.append(Q.equiv_reduce([u], [u]))
