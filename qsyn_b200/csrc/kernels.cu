@@ -14,6 +14,7 @@
 //   adjoint_inplace   K5: tiled conjugate transpose (tensor.hpp:303-306).
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <type_traits>
 
 #include "kernels.hpp"
@@ -691,18 +692,23 @@ cudaError_t launch_sweep_r(double2* u, int n, uint64_t ncols, uint64_t grid_ncol
 }
 
 // ---------------------------------------------------------------------------------------
-// dense_kernel<K>: one dense 2^K x 2^K complex block on the FP64 tensor pipe (K1f).
+// dense_kernel<K>: one dense 2^K x 2^K complex block on the FP64 tensor pipe (K1f), K = 3..6.
 //
-// A CTA stages a tile of 2^m rows x 8 columns in shared memory (same tiles as sweep_kernel).
-// The block's K row bits are tile bits; for every combination j of the other m-K tile bits the
-// 8 columns give 8 independent complex vectors v of length D = 2^K.  In real form
-// [v'_re; v'_im] = A [v_re; v_im] with A = [[Gr, -Gi], [Gi, Gr]] interleaved per component, so one
-// j is a (2D x 2D) x (2D x 8) real GEMM, computed with mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4):
-//   B fragment (k = lane%4, n = lane/4): component k of column n -> one 8-byte LDS from the tile
-//   A fragment (row = lane/4, k = lane%4): from the padded copy of A in shared memory
-//   C fragment (row = lane/4, n = 2*(lane%4)+{0,1}): written back in place
-// A warp owns whole j's, loads all B fragments of a j into registers before writing, so the
-// update is in place without extra buffering.  Flops: 8 * 2^K per element.
+// A CTA works on tiles of 2^m rows x 8 columns (same tiles as sweep_kernel).  The block's K row bits are tile bits;
+// for every combination j of the other m-K tile bits the 8 columns give 8 independent complex vectors v of length
+// D = 2^K.  In real form [v'_re; v'_im] = A [v_re; v_im] with A = [[Gr, -Gi], [Gi, Gr]] interleaved per component,
+// so one j is a (2D x 2D) x (2D x 8) real GEMM, computed with mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4):
+//   B fragment (k = lane%4, n = lane/4): component k of column n -> one 8-byte LDS from the input tile
+//   A fragment (row = lane/4, k = lane%4): REGISTER resident for the whole launch
+//   C fragment (row = lane/4, n = 2*(lane%4)+{0,1}): written to the output tile
+// Round 1 read every A fragment from shared memory for every DMMA (one LDS per DMMA: ncu showed short_scoreboard on top
+// and 55 % of the DMMA peak).  Now a warp owns a SET of output row blocks for the whole launch and keeps their A
+// fragments in registers (<= 64 doubles): per j it loads the B fragments once and issues RB_W x KB DMMAs on RB_W
+// accumulator chains (each split into 4 partial sums: 2 DMMAs per LDS, 8 independent chains per warp).  Because several
+// warps read the same input vector, the update is out of place (input tile -> output tile in shared memory), and the
+// input tile is double buffered: the cp.async loads of tile i+1 are in flight while tile i is multiplied and stored.
+// Persistent CTAs, two per SM (one at K = 6).
+// Flops: 8 * 2^K per element; bytes: 32 per element.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -710,156 +716,191 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) 
                  : "d"(a), "d"(b));
 }
 
-template <int K>
-__global__ void __launch_bounds__(256, K >= 6 ? 1 : 2)
+template <int K, int RB_W, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS)
     dense_kernel(double2* __restrict__ u, const unsigned char* __restrict__ gprog, int log2_ncols, int log2_ncb,
                  uint32_t n_tiles) {
-    constexpr int D   = 1 << K;        // complex components per vector
-    constexpr int D2  = 2 * D;         // real GEMM size
-    constexpr int LDA = dense_lda(K);  // padded leading dimension of A (doubles)
-    constexpr int KB  = D2 / 4;        // k-blocks
-    constexpr int RB  = D2 / 8;        // row-blocks
+    constexpr int D    = 1 << K;        // complex components per vector
+    constexpr int D2   = 2 * D;         // real GEMM size
+    constexpr int LDA  = dense_lda(K);  // leading dimension of A in the program blob (doubles)
+    constexpr int KB   = D2 / 4;        // k-blocks
+    constexpr int RB   = D2 / 8;        // row-blocks
+    constexpr int SETS = RB / RB_W;     // warps that share one input vector
+    constexpr int NW   = 8;             // warps per CTA
+    static_assert(RB % RB_W == 0 && NW % SETS == 0, "row blocks must split evenly over the warps");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ DevSweep sw;
     __shared__ int32_t block_local[8];
-    __shared__ uint32_t comp_row[D];  // tile-local row offset of component c
+    __shared__ uint32_t comp_row[D];   // tile-local row offset of component c
+    __shared__ uint32_t jrow[64];      // tile-local base row of vector group j (block bits clear)
 
-    // ---- once per (persistent) CTA: header, the real block matrix, row tables ----
     if (threadIdx.x < sizeof(DevSweep) / 16)
         reinterpret_cast<uint4*>(&sw)[threadIdx.x] = __ldg(reinterpret_cast<const uint4*>(gprog) + threadIdx.x);
     if (threadIdx.x < 8) block_local[threadIdx.x] = __ldg(reinterpret_cast<const int32_t*>(gprog + sizeof(DevSweep)) + threadIdx.x);
-    double* const As    = reinterpret_cast<double*>(smem_raw);
-    double2* const tile = reinterpret_cast<double2*>(smem_raw + sizeof(double) * D2 * LDA);
-    {
-        const double* const Ag = reinterpret_cast<const double*>(gprog + sizeof(DevSweep) + 32);
-        for (int i = threadIdx.x; i < D2 * LDA; i += blockDim.x) As[i] = __ldg(Ag + i);
-    }
     __syncthreads();
-    int const m           = sw.m;
-    int const rows        = 1 << m;
-    uint32_t* const growl = reinterpret_cast<uint32_t*>(tile + ((size_t)8 << m));  // tile-local row -> its global tile bits
+    int const m    = sw.m;
+    int const rows = 1 << m;
+    size_t const tile_elems = (size_t)8 << m;
+    double2* const tin0  = reinterpret_cast<double2*>(smem_raw);
+    double2* const tin1  = tin0 + tile_elems;
+    double2* const tout  = tin1 + tile_elems;
+    uint32_t* const growl = reinterpret_cast<uint32_t*>(tout + tile_elems);  // tile-local row -> its global tile bits
     for (int l = threadIdx.x; l < rows; l += blockDim.x) {
         uint32_t g = 0;
         for (int b = 0; b < m; ++b) g |= ((l >> b) & 1u) << sw.sp[b];
         growl[l] = g;
     }
+    uint32_t block_mask = 0;
+    for (int i = 0; i < K; ++i) block_mask |= 1u << block_local[i];
     if (threadIdx.x < D) {
         uint32_t off = 0;
         for (int i = 0; i < K; ++i) off |= ((threadIdx.x >> i) & 1u) << block_local[i];
         comp_row[threadIdx.x] = off;
     }
-    uint32_t block_mask = 0;
-    for (int i = 0; i < K; ++i) block_mask |= 1u << block_local[i];
+    int const n_j = rows >> K;
+    if ((int)threadIdx.x < n_j) {
+        uint32_t base = 0;
+        int jj = threadIdx.x;
+        for (int b = 0; b < m; ++b)
+            if (!((block_mask >> b) & 1u)) {
+                base |= (uint32_t)(jj & 1) << b;
+                jj >>= 1;
+            }
+        jrow[threadIdx.x] = base;
+    }
     __syncthreads();
 
     uint32_t const cw = threadIdx.x & 7u;
-    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int const g = lane >> 2, t = lane & 3;
-    double* const tile_d = reinterpret_cast<double*>(tile);
-    // Column swizzle: a tile row is 8 columns x 16 B = all 32 banks, so the same column of different rows is the same
-    // bank.  The C fragments of one store instruction cover 4 rows (components 4rb .. 4rb+3) x columns {0,2,4,6}: a
-    // 4-way conflict on 16 banks (ncu, round 1: 46 % of the shared-memory wavefronts were conflicts).  XOR-ing the
-    // column with block bit 0 of the row puts components 4rb+{1,3} on the odd columns: every bank is hit exactly twice,
-    // the minimum for 256 bytes.  Loads (16 consecutive doubles of one row per quarter warp) are unaffected.
-    int const swz_bit = block_local[0];
-    auto swz = [&](uint32_t row) { return (row >> swz_bit) & 1u; };
-    // per-lane fragment offsets (in doubles, relative to the j base row), fixed for the whole launch
-    // (the j base row has block bit 0 clear, so the swizzle of a component row is the component's bit 0)
-    uint32_t boff[KB], ooff[RB], ooff2[RB];
+    int const set = warp % SETS, jlane = warp / SETS;   // this warp: row blocks [set * RB_W, ...), vectors jlane, jlane + NW/SETS, ...
+
+    // A fragments of this warp's row blocks: registers for the whole launch
+    double afrag[RB_W][KB];
+    {
+        const double* const Ag = reinterpret_cast<const double*>(gprog + sizeof(DevSweep) + 32);
+#pragma unroll
+        for (int r = 0; r < RB_W; ++r)
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) afrag[r][kb] = __ldg(Ag + (size_t)((set * RB_W + r) * 8 + g) * LDA + 4 * kb + t);
+    }
+    // per-lane fragment offsets in doubles relative to the vector's base row.  Output columns are swizzled with block bit
+    // 0 of the row (= bit 0 of the component): the C fragments of one store instruction cover components 4rb .. 4rb+3 x
+    // columns {0,2,4,6}; unswizzled that is a 4-way bank conflict (a tile row is exactly 32 banks wide).
+    uint32_t boff[KB], ooff[RB_W], ooff2[RB_W];
 #pragma unroll
     for (int kb = 0; kb < KB; ++kb) {
         int const kidx = 4 * kb + t;  // real component index = 2*c + part
-        int const c    = kidx >> 1;
-        boff[kb]       = (((comp_row[c] << 3) + ((uint32_t)g ^ (uint32_t)(c & 1))) << 1) + (kidx & 1);
+        boff[kb]       = (((comp_row[kidx >> 1] << 3) + (uint32_t)g) << 1) + (kidx & 1);
     }
 #pragma unroll
-    for (int rb = 0; rb < RB; ++rb) {
-        int const ridx = rb * 8 + g;  // output real component = 2*c' + part'
+    for (int r = 0; r < RB_W; ++r) {
+        int const ridx = (set * RB_W + r) * 8 + g;  // output real component = 2*c' + part'
         int const c    = ridx >> 1;
-        ooff[rb]       = (((comp_row[c] << 3) + ((uint32_t)(2 * t) ^ (uint32_t)(c & 1))) << 1) + (ridx & 1);
-        ooff2[rb]      = (((comp_row[c] << 3) + ((uint32_t)(2 * t + 1) ^ (uint32_t)(c & 1))) << 1) + (ridx & 1);
+        ooff[r]        = (((comp_row[c] << 3) + ((uint32_t)(2 * t) ^ (uint32_t)(c & 1))) << 1) + (ridx & 1);
+        ooff2[r]       = (((comp_row[c] << 3) + ((uint32_t)(2 * t + 1) ^ (uint32_t)(c & 1))) << 1) + (ridx & 1);
     }
+    int const swz_bit = block_local[0];
 
-    for (uint32_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
-        uint64_t const cb  = tile_id & ((1u << log2_ncb) - 1u);
-        uint32_t const rc  = tile_id >> log2_ncb;
-        uint32_t row_outer = 0;
+    auto tile_origin = [&](uint32_t tile_id, uint32_t& row_outer, uint64_t& col) {
+        uint64_t const cb = tile_id & ((1u << log2_ncb) - 1u);
+        uint32_t const rc = tile_id >> log2_ncb;
+        row_outer         = 0;
         for (int k = 0; k < sw.n_outer; ++k) row_outer |= ((rc >> k) & 1u) << sw.outer[k];
-        uint64_t const col = (cb << 3) + cw;
-
-        // ---- load the tile: 8 columns x 2^m rows, 128 B per row; cp.async keeps every row of the
-        //      thread in flight at once without staging registers ----
+        col = (cb << 3) + cw;
+    };
+    auto load_tile = [&](uint32_t tile_id, double2* dst_tile) {
+        uint32_t row_outer;
+        uint64_t col;
+        tile_origin(tile_id, row_outer, col);
         for (int l = threadIdx.x >> 3; l < rows; l += blockDim.x >> 3) {
             const double2* const src = u + ((size_t)(row_outer | growl[l]) << log2_ncols) + col;
-            uint32_t const dst       = (uint32_t)__cvta_generic_to_shared(tile + (l << 3) + (cw ^ swz((uint32_t)l)));
+            uint32_t const dst       = (uint32_t)__cvta_generic_to_shared(dst_tile + (l << 3) + cw);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
         }
-        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-        __syncthreads();
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
 
-        // ---- GEMM: each warp owns whole j's ----
-        for (int j = warp; j < (rows >> K); j += n_warps) {
-            uint32_t base = 0;  // j deposited into the tile-local bits that are not block bits
-            {
-                int jj = j;
-                for (int b = 0; b < m; ++b)
-                    if (!((block_mask >> b) & 1u)) {
-                        base |= (uint32_t)(jj & 1) << b;
-                        jj >>= 1;
-                    }
-            }
-            double* const jbase = tile_d + ((size_t)base << 4);  // (row * 8 columns) * 2 doubles
+    uint32_t tile_id = blockIdx.x;
+    if (tile_id < n_tiles) load_tile(tile_id, tin0);
+    int buf = 0;
+    for (; tile_id < n_tiles; tile_id += gridDim.x, buf ^= 1) {
+        double2* const tin      = buf ? tin1 : tin0;
+        uint32_t const next_id  = tile_id + gridDim.x;
+        if (next_id < n_tiles) {
+            load_tile(next_id, buf ? tin0 : tin1);  // (its previous contents were consumed two barriers ago)
+            asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        }
+        __syncthreads();  // tile `tile_id` is complete in tin; tout is free (the previous store phase is behind a barrier)
+
+        const double* const tin_d = reinterpret_cast<const double*>(tin);
+        double* const tout_d      = reinterpret_cast<double*>(tout);
+        for (int j = jlane; j < n_j; j += NW / SETS) {
+            uint32_t const base = jrow[j] << 4;  // (row * 8 columns) * 2 doubles
             double bfrag[KB];
 #pragma unroll
-            for (int kb = 0; kb < KB; ++kb) bfrag[kb] = jbase[boff[kb]];
-            double out[RB][2];
+            for (int kb = 0; kb < KB; ++kb) bfrag[kb] = tin_d[base + boff[kb]];
+            // NACC partial sums per row block: DMMA results come back after ~190 cycles while one can be issued every 16,
+            // so a scheduler needs >= 12 independent accumulator chains to stay busy; 4 warps x RB_W = 2 row blocks give 8
+            // (measured 67 % of the DMMA peak at K = 5), 4 partial sums each give 32
+            constexpr int NACC = KB >= 4 ? 4 : KB;
+            double acc[RB_W][NACC][2];
 #pragma unroll
-            for (int rb = 0; rb < RB; ++rb) {
-                double acc[2] = {0.0, 0.0};
-                const double* const arow = As + (size_t)(rb * 8 + g) * LDA + t;
+            for (int r = 0; r < RB_W; ++r)
 #pragma unroll
-                for (int kb = 0; kb < KB; ++kb) dmma_m8n8k4(acc, arow[4 * kb], bfrag[kb]);
-                out[rb][0] = acc[0];
-                out[rb][1] = acc[1];
-            }
-            __syncwarp();  // every lane has read its B fragments of this j
+                for (int a = 0; a < NACC; ++a) acc[r][a][0] = acc[r][a][1] = 0.0;
 #pragma unroll
-            for (int rb = 0; rb < RB; ++rb) {
-                jbase[ooff[rb]]  = out[rb][0];  // column 2t
-                jbase[ooff2[rb]] = out[rb][1];  // column 2t + 1
+            for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                for (int r = 0; r < RB_W; ++r) dmma_m8n8k4(acc[r][kb % NACC], afrag[r][kb], bfrag[kb]);
+#pragma unroll
+            for (int r = 0; r < RB_W; ++r) {
+                double c0 = acc[r][0][0], c1 = acc[r][0][1];
+                if constexpr (NACC == 4) {
+                    c0 = (acc[r][0][0] + acc[r][1][0]) + (acc[r][2][0] + acc[r][3][0]);
+                    c1 = (acc[r][0][1] + acc[r][1][1]) + (acc[r][2][1] + acc[r][3][1]);
+                }
+                tout_d[base + ooff[r]]  = c0;  // column 2t
+                tout_d[base + ooff2[r]] = c1;  // column 2t + 1
             }
         }
         __syncthreads();
 
+        uint32_t row_outer;
+        uint64_t col;
+        tile_origin(tile_id, row_outer, col);
 #pragma unroll 8
         for (int l = threadIdx.x >> 3; l < rows; l += blockDim.x >> 3)
-            __stcg(u + ((size_t)(row_outer | growl[l]) << log2_ncols) + col, tile[(l << 3) + (cw ^ swz((uint32_t)l))]);
-        __syncthreads();  // the tile buffer is reused by the next iteration
+            __stcg(u + ((size_t)(row_outer | growl[l]) << log2_ncols) + col, tout[(l << 3) + (cw ^ (((uint32_t)l >> swz_bit) & 1u))]);
+        // (the next iteration's first barrier separates these reads of tout from its next writes)
     }
 }
 
-template <int K>
+template <int K, int RB_W, int MIN_CTAS>
 cudaError_t launch_dense_k(double2* u, uint64_t ncols, const DevSweep& hs, const unsigned char* prog, cudaStream_t s) {
     int log2_ncols = 0;
     while ((1ull << log2_ncols) < ncols) ++log2_ncols;
     int const log2_ncb     = log2_ncols - 3;
     uint64_t const nblocks = 1ull << (log2_ncb + hs.n_outer);
-    if (log2_ncb < 0 || hs.m > kMaxTileBits || hs.m < K || nblocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-    size_t const smem = sizeof(double) * (2 << K) * dense_lda(K) + ((size_t)16 * 8 << hs.m) + sizeof(uint32_t) * ((size_t)1 << hs.m);
+    if (log2_ncb < 0 || hs.m > 8 || hs.m < K || nblocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    // two input tiles (double buffered), one output tile, the row table
+    size_t const smem = 3 * ((size_t)16 * 8 << hs.m) + sizeof(uint32_t) * ((size_t)1 << hs.m);
     static bool attr_set[64] = {};
     int dev                  = 0;
     if (cudaError_t const rc = cudaGetDevice(&dev); rc != cudaSuccess) return rc;
     if (dev < 64 && !attr_set[dev]) {
-        if (cudaError_t const rc = cudaFuncSetAttribute(dense_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (cudaError_t const rc = cudaFuncSetAttribute(dense_kernel<K, RB_W, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             rc != cudaSuccess)
             return rc;
         attr_set[dev] = true;
     }
-    // persistent CTAs (2 per SM): the 2^(K+1) x 2^(K+1) real matrix is staged once per CTA, not once per tile
+    // persistent CTAs: the A fragments are loaded into registers once per CTA, not once per tile
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    unsigned const grid = (unsigned)std::min<uint64_t>(nblocks, (uint64_t)sms * 2);
-    dense_kernel<K><<<grid, 256, smem, s>>>(u, prog, log2_ncols, log2_ncb, (uint32_t)nblocks);
+    unsigned const grid = (unsigned)std::min<uint64_t>(nblocks, (uint64_t)sms * MIN_CTAS);
+    dense_kernel<K, RB_W, MIN_CTAS><<<grid, 256, smem, s>>>(u, prog, log2_ncols, log2_ncb, (uint32_t)nblocks);
     return cudaGetLastError();
 }
 
@@ -1066,10 +1107,12 @@ cudaError_t launch_sweep(double2* u, int n, uint64_t ncols, uint64_t grid_ncols,
     if (hs.dense_k != 0) {
         if (from_identity || grid_ncols != ncols) return cudaErrorInvalidValue;  // (the runtime materialises the identity first)
         switch (hs.dense_k) {
-            case 3: return launch_dense_k<3>(u, ncols, hs, prog, s);
-            case 4: return launch_dense_k<4>(u, ncols, hs, prog, s);
-            case 5: return launch_dense_k<5>(u, ncols, hs, prog, s);
-            case 6: return launch_dense_k<6>(u, ncols, hs, prog, s);
+            // 2 output row blocks per warp, 2 CTAs per SM (tiles of 2^8 rows): measured against 4 row blocks per warp on one
+            // CTA per SM with 2^9-row tiles: k = 3 / 4 / 5: 97 / 106 / 173 us against 106 / 133 / 194 us at n = 12
+            case 3: return launch_dense_k<3, 2, 2>(u, ncols, hs, prog, s);
+            case 4: return launch_dense_k<4, 2, 2>(u, ncols, hs, prog, s);
+            case 5: return launch_dense_k<5, 2, 2>(u, ncols, hs, prog, s);
+            case 6: return launch_dense_k<6, 2, 1>(u, ncols, hs, prog, s);
             default: return cudaErrorInvalidValue;
         }
     }

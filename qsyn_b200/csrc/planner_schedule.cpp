@@ -13,6 +13,7 @@
 // Locality rule (performance): only the bits in T(g) have to be inside the shared-memory
 // tile (and, for the stage that applies g, in registers); tested bits can be any row bit.
 #include <algorithm>
+#include <cstdlib>
 #include <cassert>
 #include <cmath>
 #include <complex>
@@ -298,8 +299,8 @@ void dense_op_sweep(Plan& plan, int idx) {
     sw.block_matrix = op.mat;
     sw.block_ops    = {idx};
     uint32_t T      = op.tmask();
-    // tile: the block bits plus other row bits for a full CTA (k = 6 keeps 2^8 rows: its matrix alone takes 130 KiB)
-    int const m_want = std::min(cfg.n, std::max(k, k >= 6 ? 8 : 9));
+    // tile: the block bits plus other row bits up to 2^8 rows (three tile buffers of 32 KiB: two CTAs per SM)
+    int const m_want = std::min(cfg.n, std::max(k, 8));
     for (int b = 0; b < cfg.n && popc(T) < m_want; ++b) T |= 1u << b;
     for (int b = 0; b < cfg.n; ++b)
         if ((T >> b) & 1u) sw.tile_bits.push_back(b);
@@ -542,7 +543,7 @@ void schedule_dense(Plan& plan) {
         sw.block_ops = chosen;
         // tile: the block bits plus enough other row bits for a full CTA
         uint32_t T       = S;
-        int const m_want = std::min(cfg.n, std::max(k, std::min(cfg.m_cap, 9)));
+        int const m_want = std::min(cfg.n, std::max(k, 8));  // 2^8-row tiles (launch_dense_k, kernels.cu)
         for (int b = 0; b < cfg.n && popc(T) < m_want; ++b) T |= 1u << b;
         for (int b = 0; b < cfg.n; ++b)
             if ((T >> b) & 1u) sw.tile_bits.push_back(b);
