@@ -704,7 +704,7 @@ cudaError_t launch_sweep_r(double2* u, int n, uint64_t ncols, uint64_t grid_ncol
 // Round 1 read every A fragment from shared memory for every DMMA (one LDS per DMMA: ncu showed short_scoreboard on top
 // and 55 % of the DMMA peak).  Now a warp owns a SET of output row blocks for the whole launch and keeps their A
 // fragments in registers (<= 64 doubles): per j it loads the B fragments once and issues RB_W x KB DMMAs on RB_W
-// accumulator chains (each split into 4 partial sums: 2 DMMAs per LDS, 8 independent chains per warp).  Because several
+// accumulator chains (2 DMMAs per LDS).  Because several
 // warps read the same input vector, the update is out of place (input tile -> output tile in shared memory), and the
 // input tile is double buffered: the cp.async loads of tile i+1 are in flight while tile i is multiplied and stored.
 // Persistent CTAs, two per SM (one at K = 6).
@@ -842,10 +842,14 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
             double bfrag[KB];
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb) bfrag[kb] = tin_d[base + boff[kb]];
-            // NACC partial sums per row block: DMMA results come back after ~190 cycles while one can be issued every 16,
-            // so a scheduler needs >= 12 independent accumulator chains to stay busy; 4 warps x RB_W = 2 row blocks give 8
-            // (measured 67 % of the DMMA peak at K = 5), 4 partial sums each give 32
-            constexpr int NACC = KB >= 4 ? 4 : KB;
+            // One accumulator chain per row block.  Splitting a chain into NACC partial sums (more independent DMMAs in
+            // flight) was measured and is SLOWER: k = 4 / 5 / 6 at n = 12: 104 / 174 / 322 us with 1 chain, 135 / 201 / 338 us
+            // with 2, 136 / 180 / 347 us with 4 -- the final DADDs share the FP64 pipe with the DMMAs, and ncu shows the pipe
+            // itself as the limiter (math_pipe_throttle on top, tensor pipe 67 % active).  -DQSX_DENSE_NACC=2|4 rebuilds it.
+#ifndef QSX_DENSE_NACC
+#define QSX_DENSE_NACC 1
+#endif
+            constexpr int NACC = QSX_DENSE_NACC;
             double acc[RB_W][NACC][2];
 #pragma unroll
             for (int r = 0; r < RB_W; ++r)
@@ -861,6 +865,9 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
                 if constexpr (NACC == 4) {
                     c0 = (acc[r][0][0] + acc[r][1][0]) + (acc[r][2][0] + acc[r][3][0]);
                     c1 = (acc[r][0][1] + acc[r][1][1]) + (acc[r][2][1] + acc[r][3][1]);
+                } else if constexpr (NACC == 2) {
+                    c0 = acc[r][0][0] + acc[r][1][0];
+                    c1 = acc[r][0][1] + acc[r][1][1];
                 }
                 tout_d[base + ooff[r]]  = c0;  // column 2t
                 tout_d[base + ooff2[r]] = c1;  // column 2t + 1
