@@ -563,7 +563,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c4", choices=["c2", "c3", "c4", "c5", "tiny"])
+    ap.add_argument("--workload", default="c4", choices=["c2", "c3", "c4", "c5", "tiny", "rot"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--extras", default="auto", help="comma list of further workloads reported under `extra` (auto: c2, and c5 on 8 GPUs)")
     ap.add_argument("--e2e-steps", type=int, default=10, help="timed end-to-end steps (at most --steps)")

@@ -148,9 +148,20 @@ bool append_flat(Operation const& op, QubitIdList const& qubits, std::vector<Fla
         }
         return true;
     }
-    auto g = lower_to_stream(op);
-    if (!g.has_value() || qubits.size() > QSX_MAX_GATE_QUBITS) return false;
-    out.push_back(FlatGate{std::move(*g), qubits});
+    // A circuit has thousands of gates but a handful of distinct operations (h, t, cx, rz(pi/8), ...): the matrix of an
+    // operation is built once through the QTensor builders and reused.  get_repr() identifies a basic operation completely
+    // (type, phase as an exact rational, number of controls); nested circuits never get here.
+    static thread_local std::unordered_map<std::string, StreamGate> cache;
+    std::string const key = op.get_repr();
+    auto it               = cache.find(key);
+    if (it == cache.end()) {
+        auto g = lower_to_stream(op);
+        if (!g.has_value()) return false;
+        if (cache.size() >= 4096) cache.clear();
+        it = cache.emplace(key, std::move(*g)).first;
+    }
+    if (qubits.size() > QSX_MAX_GATE_QUBITS || it->second.n_ctrls + it->second.n_targets != qubits.size()) return false;
+    out.push_back(FlatGate{it->second, qubits});
     return true;
 }
 

@@ -57,11 +57,13 @@ WORKLOADS = {
     "c4": (15, "clifford_t", 10000, 20261020, "C4: 15-qubit random Clifford+T, 10000 gates (16 GiB unitary)"),
     "c5": (16, "clifford_t", 10000, 20261021, "C5: 16-qubit random Clifford+T, 10000 gates (64 GiB unitary)"),
     "tiny": (8, "clifford_t", 400, 7, "tiny: 8-qubit random Clifford+T, 400 gates (smoke)"),
+    # not a BASELINE config: the dense-rotation circuit the dense k-qubit blocks are compared on
+    "rot": (12, "rotation", 2000, 20261022, "rot: 12-qubit random rx/ry/rz (75 %) + cx circuit, 2000 gates (256 MiB unitary)"),
 }
 
 
 def workload_qasm(name: str) -> tuple[int, str, str]:
     """(n_qubits, description, QASM text of circuit A)."""
     n, gen, g, seed, desc = WORKLOADS[name]
-    text = random_clifford_t_qasm(n, g, seed) if gen == "clifford_t" else qft_qasm(n)
+    text = random_clifford_t_qasm(n, g, seed) if gen == "clifford_t" else random_rotation_qasm(n, g, seed) if gen == "rotation" else qft_qasm(n)
     return n, desc, text
