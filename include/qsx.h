@@ -56,6 +56,9 @@ const char* qsx_last_error(void);
  * Everything it does is otherwise done lazily on first use.  The reference has no counterpart: it is the start-up
  * cost of keeping Tensor storage (tensor.hpp:144) on devices.  qsx_shutdown destroys the communicators. */
 int qsx_init(int n_gpus);
+/* Call before the process exits (the CLI does at `quit`, the Python binding through atexit): waits for the compiler
+ * threads of the specialised sweeps and destroys the NCCL communicators while the CUDA runtime is still alive.  The
+ * library also registers exit hooks of its own as a fallback.  Everything can be used again afterwards. */
 int qsx_shutdown(void);
 /* number of usable CUDA devices (0 on a CPU-only host; never an error) */
 int qsx_device_count(int* count);

@@ -42,6 +42,8 @@ def lib() -> C.CDLL:
                               "there is no Python or CPU fallback for this path")
         _lib = C.CDLL(path)
         _declare(_lib)
+        import atexit
+        atexit.register(_lib.qsx_shutdown)  # compiler threads and communicators go before the interpreter tears down
     return _lib
 
 

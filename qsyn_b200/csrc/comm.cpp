@@ -16,6 +16,7 @@
 #include <string>
 #include <vector>
 
+#include "jit.hpp"
 #include "runtime_internal.hpp"
 
 namespace qsx {
@@ -190,6 +191,7 @@ int qsx_init(int n_gpus) {
 }
 
 int qsx_shutdown(void) {
+    qsx::jit::shutdown();  // no compiler thread may be running when the process tears its libraries down
     std::lock_guard<std::mutex> lk(qsx::g_comm_mu);
     if (qsx::g_nccl.handle != nullptr) {
         for (auto& kv : qsx::g_cliques)

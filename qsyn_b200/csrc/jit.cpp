@@ -87,6 +87,10 @@ std::condition_variable& g_cv_done = *new std::condition_variable;
 auto& g_cache                      = *new std::map<std::pair<uint64_t, uint64_t>, std::unique_ptr<Kernel>>;
 std::deque<Kernel*>& g_queue       = *new std::deque<Kernel*>;
 bool g_pool_started = false;
+bool g_stop         = false;  // set at process exit: no new compilations, wait for the running ones
+int g_active        = 0;      // workers inside the compiler right now
+int g_hook_registrations = 0;
+void stop_pool_at_exit();
 Stats g_stats;
 std::string& g_last_error = *new std::string;
 
@@ -206,7 +210,8 @@ int min_ctas_for(int threads) {
 // version.  QSX_JIT_CACHE=<dir> moves it, QSX_JIT_CACHE=off disables it.  Files are written to a temporary name and
 // renamed, so a reader never sees a partial file.
 std::string const& cache_dir() {
-    static std::string const dir = [] {
+    // (never destroyed: its destructor would run at exit BEFORE the pool's exit hook, under the feet of the workers)
+    static std::string const& dir = *new std::string([] {
         std::string d;
         if (char const* e = std::getenv("QSX_JIT_CACHE")) {
             d = e;
@@ -220,7 +225,7 @@ std::string const& cache_dir() {
         struct stat st {};
         if (::stat(d.c_str(), &st) != 0 || !S_ISDIR(st.st_mode)) return std::string();
         return d;
-    }();
+    }());
     return dir;
 }
 
@@ -317,6 +322,12 @@ void compile_one(Kernel* k) {
     double const dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     {
         std::lock_guard<std::mutex> lk(g_mu);
+        // exit handlers run in reverse order of registration, and the compiler registers destructors of its own lazily
+        // created state DURING the first compilations: the pool's hook is registered again behind them (bounded)
+        if (!from_disk && g_hook_registrations < 64) {
+            ++g_hook_registrations;
+            std::atexit(stop_pool_at_exit);
+        }
         g_stats.compile_seconds += dt;
         if (ok) {
             if (from_disk)
@@ -339,13 +350,29 @@ void worker_main() {
         Kernel* k = nullptr;
         {
             std::unique_lock<std::mutex> lk(g_mu);
-            g_cv_work.wait(lk, [] { return !g_queue.empty(); });
+            g_cv_work.wait(lk, [] { return g_stop || !g_queue.empty(); });
+            if (g_stop) return;
             k = g_queue.front();
             g_queue.pop_front();
             k->state.store(kCompiling, std::memory_order_relaxed);
+            ++g_active;
         }
         compile_one(k);
+        {
+            std::lock_guard<std::mutex> lk(g_mu);
+            --g_active;
+        }
+        g_cv_done.notify_all();
     }
+}
+
+// A process must not run its static destructors (NVRTC has its own) while a compiler thread is still inside
+// nvrtcCompileProgram: `quit` right after converting a 14-qubit circuit crashed exactly there.  At exit the queue is
+// dropped (those sweeps were being interpreted anyway) and the compilations in flight are waited for (< 1 s).
+void stop_pool_at_exit() {
+    if (std::getenv("QSX_JIT_VERBOSE") != nullptr) std::fprintf(stderr, "[qsx jit] exit hook: waiting for %d compilation(s) in flight\n", g_active);
+    shutdown();
+    if (std::getenv("QSX_JIT_VERBOSE") != nullptr) std::fprintf(stderr, "[qsx jit] exit hook: done\n");
 }
 
 // called with g_mu held
@@ -357,6 +384,7 @@ void start_pool_locked() {
     if (n < 1) n = 1;
     if (n > 64) n = 64;
     g_stats.workers = n;
+    std::atexit(stop_pool_at_exit);
     for (int i = 0; i < n; ++i) std::thread(worker_main).detach();  // daemon threads: they only ever wait on the queue
 }
 
@@ -392,7 +420,9 @@ Kernel* request(const unsigned char* blob, size_t size, int R, int threads) {
     std::snprintf(nm, sizeof(nm), "qsx_sweep_%016llx%016llx", (unsigned long long)h0, (unsigned long long)h1);
     k->name = nm;
     std::string err;
-    if (!generate_sweep_source(blob, size, R, k->name, threads, min_ctas_for(threads), k->source, err)) {
+    if (g_stop) {
+        k->state.store(kFailed);
+    } else if (!generate_sweep_source(blob, size, R, k->name, threads, min_ctas_for(threads), k->source, err)) {
         k->state.store(kFailed);
         g_last_error = err;
     } else {
@@ -472,6 +502,20 @@ cudaError_t launch(Kernel* k, double2* u, int log2_ncols, int log2_ncb, uint32_t
         ++g_stats.launches;
     }
     return cudaSuccess;
+}
+
+void shutdown() {
+    std::unique_lock<std::mutex> lk(g_mu);
+    if (!g_pool_started) return;
+    g_stop = true;
+    for (Kernel* k : g_queue) k->state.store(kFailed, std::memory_order_release);
+    g_queue.clear();
+    g_cv_work.notify_all();
+    g_cv_done.notify_all();
+    g_cv_done.wait(lk, [] { return g_active == 0; });
+    // the workers are gone; a later request starts a new pool
+    g_pool_started = false;
+    g_stop         = false;
 }
 
 Stats stats() {

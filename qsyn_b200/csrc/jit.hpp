@@ -33,6 +33,9 @@ bool wait(Kernel* k);
 cudaError_t launch(Kernel* k, double2* u, int log2_ncols, int log2_ncb, uint32_t flags, uint32_t col0, unsigned grid, unsigned threads,
                    size_t smem, cudaStream_t stream);
 
+// process exit: drops the queued compilations and waits for the ones in flight (registered with atexit by the pool)
+void shutdown();
+
 struct Stats {
     uint64_t requested = 0, compiled = 0, failed = 0, hits = 0, launches = 0, disk_hits = 0;
     double compile_seconds = 0;  // summed over the worker threads

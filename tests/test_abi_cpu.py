@@ -196,9 +196,11 @@ def test_plan_rejects_bad_input():
         Q.Plan(3, 8, [(1, [1, 1], h)])
     with pytest.raises(Q.QsxError):
         Q.Plan(3, 6, [(0, [0], h)])  # ncols not a power of two
-    with pytest.raises(Q.QsxError) as ei:
-        Q.Plan(3, 8, [(0, [0, 1, 2], np.eye(8))])
+    with pytest.raises(Q.QsxError) as ei:  # wider than the widest dense block (6 qubits incl. controls)
+        Q.Plan(8, 256, [(1, list(range(7)), _rand_unitary(6, 3))])
     assert ei.value.status == "QSX_ERR_UNSUPPORTED"
+    assert Q.Plan(3, 8, [(0, [0, 1, 2], np.eye(8))]).stats().n_sweeps == 0  # a 3-target identity vanishes like any identity
+    assert Q.Plan(3, 8, [(0, [0, 1, 2], _rand_unitary(3, 4))]).stats().n_dense_blocks == 1
     # identity gates vanish, empty stream is legal (zero gates -> identity, Appendix A.1)
     p = Q.Plan(3, 8, [(0, [0], np.eye(2)), (1, [0, 1], np.eye(2))])
     assert p.stats().n_ops == 0 and p.stats().n_sweeps == 0
