@@ -8,6 +8,9 @@
 //                            qsx_comm_init_rank on every rank: the all-reduce then also spans the ranks
 #include <dlfcn.h>
 #include <nccl.h>
+#include <unistd.h>
+
+#include <cstdio>
 
 #include <cstdlib>
 #include <cstring>
@@ -104,12 +107,31 @@ void register_exit_hook() {
     (void)once;
 }
 
+// NCCL writes its version banner to STDOUT when a communicator is created (with NCCL_DEBUG=VERSION, which GPU images
+// commonly export).  Stdout is the product's text interface -- `tensor equiv` must print exactly what qsyn prints -- so
+// file descriptor 1 points at stderr while NCCL initialises.
+struct StdoutToStderr {
+    int saved = -1;
+    StdoutToStderr() {
+        std::fflush(stdout);
+        saved = dup(1);
+        if (saved >= 0) dup2(2, 1);
+    }
+    ~StdoutToStderr() {
+        if (saved < 0) return;
+        std::fflush(stdout);
+        dup2(saved, 1);
+        close(saved);
+    }
+};
+
 int clique_for(std::vector<int> const& devices, std::vector<ncclComm_t>** out) {
     auto it = g_cliques.find(devices);
     if (it == g_cliques.end()) {
         if (int rc = load_nccl()) return rc;
         register_exit_hook();
         std::vector<ncclComm_t> comms(devices.size(), nullptr);
+        StdoutToStderr quiet;
         QSX_NCCL(g_nccl.CommInitAll(comms.data(), (int)devices.size(), devices.data()));
         it = g_cliques.emplace(devices, std::move(comms)).first;
     }
@@ -225,6 +247,7 @@ int qsx_comm_init_rank(int device, int world, int rank, const void* id, size_t i
     qsx::register_exit_hook();
     ncclUniqueId uid;
     std::memcpy(&uid, id, sizeof(uid));
+    qsx::StdoutToStderr quiet;
     QSX_NCCL(qsx::g_nccl.CommInitRank(&qsx::g_rank_comm, world, uid, rank));
     qsx::g_rank_device = device, qsx::g_rank_world = world;
     return QSX_OK;
