@@ -141,11 +141,6 @@ int clique_for(std::vector<int> const& devices, std::vector<ncclComm_t>** out) {
 
 }  // namespace
 
-bool comm_spans_processes() {
-    std::lock_guard<std::mutex> lk(g_comm_mu);
-    return g_rank_comm != nullptr && g_rank_world > 1;
-}
-
 int comm_allreduce8(DeviceCtx* const* ctx, double* const* out8, int n_devices) {
     std::lock_guard<std::mutex> lk(g_comm_mu);
     if (n_devices < 1) return fail(QSX_ERR_BAD_ARG, "no devices");

@@ -705,6 +705,7 @@ int equiv_impl(const qsx_unitary* const* a, const qsx_unitary* const* b, int n_s
         dev_of[(size_t)k] = (int)d;
         if (++local_pairs[d] > qsx::kMaxLocalShards) return fail(QSX_ERR_BAD_ARG, "too many shard pairs on one device");
     }
+    if (!combine && ctx.size() > 1) return fail(QSX_ERR_BAD_ARG, "qsx_equiv_partial takes one shard pair");
     // lock the devices in ascending id order (no lock-order inversion between concurrent callers)
     std::vector<DeviceCtx*> by_id = ctx;
     std::sort(by_id.begin(), by_id.end(), [](DeviceCtx* x, DeviceCtx* y) { return x->device < y->device; });
@@ -732,7 +733,6 @@ int equiv_impl(const qsx_unitary* const* a, const qsx_unitary* const* b, int n_s
         if (int rc = qsx::comm_allreduce8(ctx.data(), out8.data(), (int)ctx.size())) return rc;
     DeviceCtx* c0 = ctx[0];
     QSX_CUDA(cudaSetDevice(c0->device));
-    if (!combine && ctx.size() > 1) return fail(QSX_ERR_BAD_ARG, "qsx_equiv_partial takes one shard pair");
     QSX_CUDA(cudaMemcpyAsync(c0->host8, out8[0], 8 * sizeof(double), cudaMemcpyDeviceToHost, c0->stream));
     // the other devices' streams carry their half of the collective: drain them too before the scratch is reused
     for (size_t d = ctx.size(); d-- > 0;) {
