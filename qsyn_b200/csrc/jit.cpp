@@ -64,7 +64,8 @@ enum State : int { kQueued = 0, kCompiling = 1, kReady = 2, kFailed = 3 };
 
 struct Kernel {
     uint64_t h0 = 0, h1 = 0;
-    int R = 0, threads = 0;
+    int R = 0, threads = 0, min_ctas = 1;
+    bool persistent = false;
     std::string name, source;
     std::atomic<int> state{kQueued};
     std::vector<char> cubin;
@@ -190,6 +191,8 @@ void hash_program(const unsigned char* p, size_t n, int R, int threads, uint64_t
     }
     h0 = a ^ (uint64_t)n, h1 = b;
 }
+
+constexpr bool kPersistentDefault = false;
 
 int min_ctas_for(int threads) {
     if (char const* e = std::getenv("QSX_JIT_MINCTAS")) {
@@ -403,9 +406,19 @@ bool available(std::string* why) {
     return ok;
 }
 
+// Persistent sweeps (jit_codegen.cpp): QSX_JIT_PERSIST=0/1 overrides the default.
+bool persistent_mode() {
+    static bool const on = [] {
+        char const* e = std::getenv("QSX_JIT_PERSIST");
+        return e != nullptr ? std::atoi(e) != 0 : kPersistentDefault;
+    }();
+    return on;
+}
+
 Kernel* request(const unsigned char* blob, size_t size, int R, int threads) {
     uint64_t h0, h1;
-    hash_program(blob, size, R, threads, h0, h1);
+    bool const persistent = persistent_mode();
+    hash_program(blob, size, R, threads | (persistent ? 1 << 20 : 0), h0, h1);
     std::lock_guard<std::mutex> lk(g_mu);
     if (!available_locked(false)) return nullptr;
     ++g_stats.requested;
@@ -415,14 +428,14 @@ Kernel* request(const unsigned char* blob, size_t size, int R, int threads) {
         return it->second.get();
     }
     auto k     = std::make_unique<Kernel>();
-    k->h0 = h0, k->h1 = h1, k->R = R, k->threads = threads;
+    k->h0 = h0, k->h1 = h1, k->R = R, k->threads = threads, k->min_ctas = min_ctas_for(threads), k->persistent = persistent;
     char nm[64];
     std::snprintf(nm, sizeof(nm), "qsx_sweep_%016llx%016llx", (unsigned long long)h0, (unsigned long long)h1);
     k->name = nm;
     std::string err;
     if (g_stop) {
         k->state.store(kFailed);
-    } else if (!generate_sweep_source(blob, size, R, k->name, threads, min_ctas_for(threads), k->source, err)) {
+    } else if (!generate_sweep_source(blob, size, R, k->name, threads, k->min_ctas, k->persistent, k->source, err)) {
         k->state.store(kFailed);
         g_last_error = err;
     } else {
@@ -435,6 +448,7 @@ Kernel* request(const unsigned char* blob, size_t size, int R, int threads) {
     return raw;
 }
 
+unsigned cta_threads(Kernel* k) { return k != nullptr ? (unsigned)k->threads : 0u; }
 bool ready(Kernel* k) { return k != nullptr && k->state.load(std::memory_order_acquire) == kReady && !k->load_failed; }
 bool failed(Kernel* k) { return k == nullptr || k->state.load(std::memory_order_acquire) == kFailed || k->load_failed; }
 
@@ -473,6 +487,7 @@ cudaError_t launch(Kernel* k, double2* u, int log2_ncols, int log2_ncb, uint32_t
             }
         }
         if (k->load_failed) return cudaErrorNotReady;
+        if (k->persistent) smem = ((size_t)16 << k->R) * (size_t)k->threads;
         if (dev >= 0 && dev < 64 && !k->attr_set[dev] && smem > 48 * 1024) {
             CUdevice cudev = 0;
             CUresult r     = g_drv.CtxGetDevice(&cudev);
@@ -490,7 +505,23 @@ cudaError_t launch(Kernel* k, double2* u, int log2_ncols, int log2_ncb, uint32_t
         return e != nullptr ? (uint32_t)std::max(0, std::atoi(e)) : 0u;
     }();
     uint32_t pf = pf_env;
-    void* args[] = {&u, &log2_ncols, &log2_ncb, &flags, &col0, &pf};
+    if (k->persistent) {
+        static int sms[64] = {};
+        if (dev >= 0 && dev < 64 && sms[dev] == 0) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+        unsigned const wave = (unsigned)((dev >= 0 && dev < 64 && sms[dev] > 0 ? sms[dev] : 148) * k->min_ctas);
+        pf                  = grid;  // tile count
+        grid                = grid < wave ? grid : wave;
+    }
+    uint32_t* ctr = nullptr;
+    if (k->persistent) {  // the tile counter of the dynamic schedule, zeroed in stream order before every launch
+        static uint32_t* ctrs[64] = {};
+        if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+        if (ctrs[dev] == nullptr)
+            if (cudaError_t const e = cudaMalloc(&ctrs[dev], 256); e != cudaSuccess) return e;
+        ctr = ctrs[dev];
+        if (cudaError_t const e = cudaMemsetAsync(ctr, 0, sizeof(uint32_t), stream); e != cudaSuccess) return e;
+    }
+    void* args[] = {&u, &log2_ncols, &log2_ncb, &flags, &col0, &pf, &ctr};
     CUresult const r = g_drv.LaunchKernel(reinterpret_cast<CUfunction>(k->kern), grid, 1, 1, threads, 1, 1, (unsigned)smem, stream, args, nullptr);
     if (r != CUDA_SUCCESS) {
         std::lock_guard<std::mutex> g(g_mu);

@@ -12,8 +12,11 @@ namespace qsx::jit {
 // CUDA C++ source of one sweep program (serialized DevSweep blob) as a kernel
 //   extern "C" __global__ void <kernel_name>(double2* u, int log2_ncols, int log2_ncb, u32 flags, u32 col0, u32 prefetch_distance)
 // with the launch geometry of sweep_kernel<R> (same grid, same CTA size, same dynamic shared memory for the tile).
+// persistent: one wave of CTAs looping over the tiles, next tile's first-stage loads prefetched with cp.async (the last
+// kernel argument is then the tile count, the grid is the resident wave, the shared memory always holds a tile);
+// in: requested, out: whether the generated kernel is (a cluster pair is not).
 bool generate_sweep_source(const unsigned char* blob, size_t size, int R, std::string const& kernel_name, int threads, int min_ctas,
-                           std::string& source, std::string& error);
+                           bool& persistent, std::string& source, std::string& error);
 
 struct Kernel;  // one compiled sweep (cache entry)
 
@@ -26,6 +29,8 @@ bool available(std::string* why);
 Kernel* request(const unsigned char* blob, size_t size, int R, int threads);
 // compiled and loadable?  (false while the compilation is in flight, and forever after a failed one)
 bool ready(Kernel* k);
+// CTA size the kernel was generated for (half of the tile's thread count for a cluster pair)
+unsigned cta_threads(Kernel* k);
 bool failed(Kernel* k);
 // blocks until the compilation of k has finished; returns ready(k)
 bool wait(Kernel* k);

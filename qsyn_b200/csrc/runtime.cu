@@ -182,7 +182,12 @@ void request_jit_kernels(qsx::Plan& pl) {
         if (hs.dense_k != 0) continue;
         int const log2_threads = hs.m - pl.cfg.R + hs.log2w;
         if (log2_threads < 0 || log2_threads > 10) continue;
-        pl.jit_kernels[s] = qsx::jit::request(pl.blob.data() + pl.sweep_offset[s], pl.sweep_size[s], pl.cfg.R, 1 << log2_threads);
+        // QSX_JIT_PAIR=1: a 512-thread tile is specialised as a cluster of two 256-thread CTAs (jit_codegen.cpp).  Off by
+        // default: measured on C4 the pair runs a 2^10-row sweep no faster than one 512-thread CTA (8.95 vs 8.73 ms)
+        char const* const pair_env = std::getenv("QSX_JIT_PAIR");
+        bool const pair            = pair_env != nullptr && std::atoi(pair_env) != 0;
+        int const cta_threads      = pair && log2_threads == 9 ? 256 : (1 << log2_threads);
+        pl.jit_kernels[s]     = qsx::jit::request(pl.blob.data() + pl.sweep_offset[s], pl.sweep_size[s], pl.cfg.R, cta_threads);
     }
 }
 
@@ -494,8 +499,10 @@ int run_sweeps(qsx::Plan& pl, qsx_unitary* u, DeviceCtx* c, unsigned char* dblob
                 qsx::SweepGeometry g;
                 if (qsx::sweep_geometry(u->ncols, block_cols, pl.cfg.R, hs, g)) {
                     uint32_t const fl   = ((s & 1) != 0 ? 1u : 0u) | (from_identity ? 2u : 0u);
-                    cudaError_t const e = qsx::jit::launch(k, u->data + cb0, g.log2_ncols, g.log2_ncb, fl, (uint32_t)(u->col0 + cb0), g.grid,
-                                                           g.threads, g.tile_bytes, c->stream);
+                    bool const pair     = qsx::jit::cta_threads(k) * 2 == g.threads;  // two CTAs per tile, half of the tile each
+                    cudaError_t const e = qsx::jit::launch(k, u->data + cb0, g.log2_ncols, g.log2_ncb, fl, (uint32_t)(u->col0 + cb0),
+                                                           pair ? g.grid * 2 : g.grid, pair ? 256 : g.threads,
+                                                           pair ? g.tile_bytes / 2 : g.tile_bytes, c->stream);
                     if (e == cudaSuccess) {
                         launched = true;
                         ++jit_launches;

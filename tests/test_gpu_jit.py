@@ -39,11 +39,14 @@ def test_jit_is_available_on_the_gpu_box():
                                             (11, 400, 6, True)])
 @pytest.mark.parametrize("opts", [{}, {"reg_qubits": 3, "tile_qubits": 7}, {"reg_qubits": 5, "tile_qubits": 9}, {"snap_tol": -1.0},
                                   {"no_perm_folding": 1}, {"reg_qubits": 2, "tile_qubits": 5, "log2_tile_cols": 2, "max_ops_per_sweep": 40},
-                                  {"tile_qubits": 10, "log2_tile_cols": 2}, {"fuse": 0}],
-                         ids=["default", "R3m7", "R5m9", "nosnap", "noperm", "R2m5w4", "m10w4", "unfused"])
-def test_specialised_sweeps_equal_the_interpreter(n, g, seed, extra, opts):
+                                  {"tile_qubits": 10, "log2_tile_cols": 2}, {"fuse": 0},
+                                  {"tile_qubits": 10}, {"tile_qubits": 9, "reg_qubits": 3}, {"tile_qubits": 10, "no_perm_folding": 1}],
+                         ids=["default", "R3m7", "R5m9", "nosnap", "noperm", "R2m5w4", "m10w4", "unfused", "m10pair", "R3m9pair", "m10pair-noperm"])
+def test_specialised_sweeps_equal_the_interpreter(n, g, seed, extra, opts, request, monkeypatch):
     if opts.get("fuse") == 0 and g > 200:
         pytest.skip("one kernel per gate: covered at the small sizes")
+    if "pair" in request.node.callspec.id:
+        monkeypatch.setenv("QSX_JIT_PAIR", "1")  # 512-thread tiles as clusters of two CTAs (distributed shared memory)
     qc = _rand_circuit(n, g, seed, extra=extra)
     gs = O.gate_stream(qc)
     want = O.to_matrix_rowform(qc)
