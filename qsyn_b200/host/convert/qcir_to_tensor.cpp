@@ -16,6 +16,7 @@
 #include "./qcir_to_tensor.hpp"
 
 #include <complex>
+#include <memory>
 #include <unordered_map>
 
 extern bool stop_requested();
@@ -71,7 +72,7 @@ namespace {
 // 2^k x 2^k block the way QTensor::control does (qtensor.hpp:363-371).
 struct StreamGate {
     size_t n_ctrls = 0;
-    std::vector<double> matrix;  // row-major complex, first target = MSB
+    std::shared_ptr<std::vector<double> const> matrix;  // row-major complex, first target = MSB; shared by every gate of the same operation
     size_t n_targets = 0;
 };
 
@@ -88,11 +89,13 @@ std::optional<StreamGate> lower_to_stream(Operation const& op) {
     if (!t.has_value()) return std::nullopt;
     g.n_targets  = target.get_num_qubits();
     auto const m = t->to_matrix().host_elements();  // rank-2k [o0,i0,..] -> 2^k x 2^k
-    g.matrix.reserve(2 * m.size());
+    std::vector<double> flat;
+    flat.reserve(2 * m.size());
     for (auto const& z : m) {
-        g.matrix.push_back(z.real());
-        g.matrix.push_back(z.imag());
+        flat.push_back(z.real());
+        flat.push_back(z.imag());
     }
+    g.matrix = std::make_shared<std::vector<double> const>(std::move(flat));
     return g;
 }
 
@@ -125,7 +128,7 @@ void update_tensor_pin(Qubit2TensorPinMap& qubit2pin, QCirGate const& gate, size
 // is FLATTENED into its own gates, each carrying the outer controls: C(AB) = C(A) C(B), same operator, and nothing wider
 // than the widest basic gate ever crosses the ABI.
 struct FlatGate {
-    StreamGate g;
+    StreamGate g;  // (the matrix is shared with the per-operation cache below: no copy per gate)
     QubitIdList qubits;
 };
 
@@ -157,7 +160,7 @@ bool append_flat(Operation const& op, QubitIdList const& qubits, std::vector<Fla
     if (it == cache.end()) {
         auto g = lower_to_stream(op);
         if (!g.has_value()) return false;
-        if (cache.size() >= 4096) cache.clear();
+        if (cache.size() >= 4096) cache.clear();  // (matrices still referenced by a gate stream stay alive through it)
         it = cache.emplace(key, std::move(*g)).first;
     }
     if (qubits.size() > QSX_MAX_GATE_QUBITS || it->second.n_ctrls + it->second.n_targets != qubits.size()) return false;
@@ -182,12 +185,12 @@ std::optional<GateStream> to_gate_stream(QCir const& qcir) {
     gs.gates.reserve(flat.size());
     gs.matrices.reserve(flat.size());
     for (auto& f : flat) {
-        gs.matrices.push_back(std::move(f.g.matrix));
         qsx_gate d{};
         d.n_ctrls   = static_cast<int32_t>(f.g.n_ctrls);
         d.n_targets = static_cast<int32_t>(f.g.n_targets);
         for (size_t p = 0; p < f.qubits.size(); ++p) d.qubits[p] = static_cast<int32_t>(f.qubits[p]);
-        d.matrix = gs.matrices.back().data();  // heap storage: stable when the outer vector grows
+        d.matrix = f.g.matrix->data();  // shared storage the stream keeps alive
+        gs.matrices.push_back(std::move(f.g.matrix));
         gs.gates.push_back(d);
     }
     return gs;
@@ -214,7 +217,8 @@ std::optional<QTensor<double>> to_tensor(QCir const& qcir) try {
         spdlog::trace("  - Add Qubit: {} input: {} output: {}", q, 2 * q + 1, 2 * q);
     }
 
-    bool const tracing = spdlog::get_level() <= spdlog::level::trace;
+    bool const tracing   = spdlog::get_level() <= spdlog::level::trace;
+    bool const debugging = spdlog::get_level() <= spdlog::level::debug;
     std::vector<FlatGate> lowered;
     std::vector<qsx_gate> stream;
     lowered.reserve(qcir.get_num_gates());
@@ -223,7 +227,7 @@ std::optional<QTensor<double>> to_tensor(QCir const& qcir) try {
             spdlog::warn("Conversion interrupted.");
             return std::nullopt;
         }
-        spdlog::debug("Gate {} ({})", gate->get_id(), gate->get_operation().get_repr());
+        if (debugging) spdlog::debug("Gate {} ({})", gate->get_id(), gate->get_operation().get_repr());
         if (!append_flat(gate->get_operation(), gate->get_qubits(), lowered)) {
             spdlog::error("Conversion of Gate {} ({}) to Tensor is not supported yet!!", gate->get_id(), gate->get_operation().get_repr());
             return std::nullopt;
@@ -236,7 +240,7 @@ std::optional<QTensor<double>> to_tensor(QCir const& qcir) try {
         d.n_ctrls   = static_cast<int32_t>(f.g.n_ctrls);
         d.n_targets = static_cast<int32_t>(f.g.n_targets);
         for (size_t p = 0; p < f.qubits.size(); ++p) d.qubits[p] = static_cast<int32_t>(f.qubits[p]);
-        d.matrix = f.g.matrix.data();
+        d.matrix = f.g.matrix->data();
         stream.push_back(d);
     }
 

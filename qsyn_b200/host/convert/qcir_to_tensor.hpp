@@ -2,6 +2,8 @@
 // Same declarations as the reference's src/convert/qcir_to_tensor.hpp:21-23.
 #pragma once
 
+#include <memory>
+
 #include "../qcir/qcir.hpp"
 #include "../tensor/qtensor.hpp"
 
@@ -11,10 +13,11 @@ namespace qsyn {
 
 // The ordered gate stream the device consumes (include/qsx.h): one entry per gate of
 // QCir::get_gates(), controls peeled off so that only the 2^t x 2^t TARGET matrix (built with the
-// reference formulas) crosses the ABI.  `gates[i].matrix` points into `matrices[i]`.
+// reference formulas) crosses the ABI.  `gates[i].matrix` points into `*matrices[i]`; gates of the same operation share
+// one matrix.
 struct GateStream {
     std::vector<qsx_gate> gates;
-    std::vector<std::vector<double>> matrices;
+    std::vector<std::shared_ptr<std::vector<double> const>> matrices;
 };
 // nullopt + error log if a gate has no tensor form (qcir_to_tensor.cpp:180-183 of the reference)
 std::optional<GateStream> to_gate_stream(qsyn::qcir::QCir const& qcir);

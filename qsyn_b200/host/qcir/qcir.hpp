@@ -243,7 +243,13 @@ public:
         if (it == _qubits.end()) return std::nullopt;
         return static_cast<size_t>(it - _qubits.begin());
     }
-    static bool qubit_id_is_unique(QubitIdList const& qubits) { return std::set<QubitIdType>(qubits.begin(), qubits.end()).size() == qubits.size(); }
+    static bool qubit_id_is_unique(QubitIdList const& qubits) {
+        if (qubits.size() > 8) return std::set<QubitIdType>(qubits.begin(), qubits.end()).size() == qubits.size();
+        for (size_t i = 1; i < qubits.size(); ++i)
+            for (size_t j = 0; j < i; ++j)
+                if (qubits[i] == qubits[j]) return false;
+        return true;
+    }
 
 private:
     size_t _id;
@@ -410,21 +416,23 @@ private:
     void _update_topological_order() const {
         if (!_dirty) return;
         _gate_list.clear();
-        std::stack<std::pair<bool, QCirGate*>> todo;
-        std::unordered_set<QCirGate*> seen;
+        std::vector<std::pair<bool, QCirGate*>> todo;  // (a stack; gate ids index _gates_by_id, so `seen` is a flat array)
+        std::vector<char> seen(_gates_by_id.size(), 0);
+        _gate_list.reserve(_gates_by_id.size());
         for (auto const& q : _qubits)
-            if (q.get_first_gate() != nullptr) todo.emplace(false, q.get_first_gate());
+            if (q.get_first_gate() != nullptr) todo.emplace_back(false, q.get_first_gate());
         while (!todo.empty()) {
-            auto const [expanded, node] = todo.top();
-            todo.pop();
+            auto const [expanded, node] = todo.back();
+            todo.pop_back();
             if (expanded) {
                 _gate_list.push_back(node);
                 continue;
             }
-            if (!seen.insert(node).second) continue;
-            todo.emplace(true, node);
+            if (seen[node->get_id()]) continue;
+            seen[node->get_id()] = 1;
+            todo.emplace_back(true, node);
             for (auto const& succ : _successors[node->get_id()])
-                if (succ.has_value() && !seen.contains(_gates_by_id[*succ].get())) todo.emplace(false, _gates_by_id[*succ].get());
+                if (succ.has_value() && !seen[*succ]) todo.emplace_back(false, _gates_by_id[*succ].get());
         }
         std::reverse(_gate_list.begin(), _gate_list.end());
         _dirty = false;

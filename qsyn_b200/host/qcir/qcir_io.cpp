@@ -5,6 +5,7 @@
 #include <cctype>
 #include <fstream>
 #include <sstream>
+#include <string_view>
 
 #include "./qcir.hpp"
 
@@ -55,27 +56,46 @@ std::optional<Operation> basic_operation(std::string const& name, std::vector<dv
 }
 
 // token starting at the first non-delimiter at/after pos; returns the position of the delimiter
-// that ends it (npos if it runs to the end, or if there is no token)
-size_t next_token(std::string const& s, std::string& tok, size_t pos = 0, std::string const& delim = " \t\n\v\f\r") {
-    size_t const begin = s.find_first_not_of(delim, pos);
-    if (begin == std::string::npos) {
-        tok.clear();
+// that ends it (npos if it runs to the end, or if there is no token).  Views into `s`: the reader allocates nothing per token.
+constexpr std::string_view kBlank = " \t\n\v\f\r";
+size_t next_token(std::string_view s, std::string_view& tok, size_t pos = 0, std::string_view delim = kBlank) {
+    size_t const begin = pos == std::string_view::npos ? pos : s.find_first_not_of(delim, pos);
+    if (begin == std::string_view::npos) {
+        tok = {};
         return begin;
     }
     size_t const end = s.find_first_of(delim, begin);
-    tok              = s.substr(begin, end == std::string::npos ? end : end - begin);
+    tok              = s.substr(begin, end == std::string_view::npos ? end : end - begin);
     return end;
 }
 
-std::string trim(std::string const& s) {
-    size_t const b = s.find_first_not_of(" \t\n\v\f\r");
-    if (b == std::string::npos) return "";
-    return s.substr(b, s.find_last_not_of(" \t\n\v\f\r") + 1 - b);
+std::string_view trim(std::string_view s) {
+    size_t const b = s.find_first_not_of(kBlank);
+    if (b == std::string_view::npos) return {};
+    return s.substr(b, s.find_last_not_of(kBlank) + 1 - b);
 }
+
+std::optional<Operation> build_operation(std::string str, std::vector<dvlab::Phase> const& params);
 
 }  // namespace
 
 std::optional<Operation> str_to_operation(std::string str, std::vector<dvlab::Phase> const& params) {
+    // A circuit file names a handful of distinct parameter-free gates thousands of times: the (immutable, shared) Operation
+    // of a name is built once per thread.  Parametrised gates are built per call.
+    if (params.empty()) {
+        static thread_local std::unordered_map<std::string, std::optional<Operation>> memo;
+        auto it = memo.find(str);
+        if (it == memo.end()) {
+            if (memo.size() >= 1024) memo.clear();
+            it = memo.emplace(str, build_operation(str, params)).first;
+        }
+        return it->second;
+    }
+    return build_operation(std::move(str), params);
+}
+
+namespace {
+std::optional<Operation> build_operation(std::string str, std::vector<dvlab::Phase> const& params) {
     str                  = lower(std::move(str));
     size_t const n_ctrls = str.find_first_not_of('c');
     if (n_ctrls == std::string::npos) return std::nullopt;  // the reference throws here ("c", "cc", ...)
@@ -84,6 +104,7 @@ std::optional<Operation> str_to_operation(std::string str, std::vector<dvlab::Ph
     if (n_ctrls > 0) return ControlGate(*basic, n_ctrls);
     return basic;
 }
+}  // namespace
 
 std::optional<QCir> from_qasm(std::filesystem::path const& filepath) {
     std::ifstream file{filepath};
@@ -104,46 +125,52 @@ std::optional<QCir> from_qasm_stream(std::istream& file, std::string const& /*na
     size_t const nqubit = std::stoul(word.substr(lb + 1, word.size() - lb - 3));
     QCir qcir{nqubit};
 
-    std::string line;
-    std::getline(file, line);  // rest of the qreg line
-    while (std::getline(file, line)) {
-        line = trim(line.substr(0, line.find("//")));
+    std::string raw;
+    QubitIdList qubit_ids;
+    std::getline(file, raw);  // rest of the qreg line
+    while (std::getline(file, raw)) {
+        std::string_view const line = trim(std::string_view(raw).substr(0, raw.find("//")));
         if (line.empty()) continue;
-        std::string type, phase_str = "0", scratch;
+        std::string_view type, phase_str = "0", scratch;
         size_t const type_end = next_token(line, type);
-        if (next_token(line, scratch, 0, "(") != std::string::npos) {
+        if (next_token(line, scratch, 0, "(") != std::string_view::npos) {
             size_t const stop = next_token(line, type, 0, "(");
             next_token(line, phase_str, stop + 1, ")");
         }
         if (type == "creg" || type == "qreg" || type.empty()) continue;
 
-        QubitIdList qubit_ids;
-        std::string token, id_str;
+        qubit_ids.clear();
+        std::string_view token, id_str;
         size_t pos = next_token(line, token, type_end, ",");
         while (!token.empty()) {
             next_token(token, id_str, next_token(token, id_str, 0, "[") + 1, "]");
             bool const numeric = !id_str.empty() && std::all_of(id_str.begin(), id_str.end(), [](unsigned char c) { return std::isdigit(c); });
-            if (!numeric || std::stoull(id_str) >= nqubit) {
+            size_t id = nqubit;
+            if (numeric && id_str.size() <= 18) {
+                id = 0;
+                for (char ch : id_str) id = 10 * id + static_cast<size_t>(ch - '0');
+            }
+            if (id >= nqubit) {
                 spdlog::error("invalid qubit id on line {}!!", line);
                 return std::nullopt;
             }
-            qubit_ids.emplace_back(std::stoull(id_str));
+            qubit_ids.emplace_back(id);
             pos = next_token(line, token, pos, ",");
         }
         if (!QCirGate::qubit_id_is_unique(qubit_ids)) {
             spdlog::error("duplicate qubit id on line {}!!", line);
             return std::nullopt;
         }
-        if (auto op = str_to_operation(type); op.has_value() && op->get_num_qubits() == qubit_ids.size()) {
+        if (auto op = str_to_operation(std::string(type)); op.has_value() && op->get_num_qubits() == qubit_ids.size()) {
             qcir.append(*op, qubit_ids);
             continue;
         }
-        auto const phase = dvlab::Phase::from_string(phase_str);
+        auto const phase = dvlab::Phase::from_string(std::string(phase_str));
         if (!phase.has_value()) {
             spdlog::error("invalid phase on line {}!!", line);
             return std::nullopt;
         }
-        if (auto op = str_to_operation(type, {*phase}); op.has_value() && op->get_num_qubits() == qubit_ids.size()) {
+        if (auto op = str_to_operation(std::string(type), {*phase}); op.has_value() && op->get_num_qubits() == qubit_ids.size()) {
             qcir.append(*op, qubit_ids);
             continue;
         }

@@ -34,16 +34,34 @@ inline void set_level(level::level_enum lvl) { detail::current_level() = lvl; }
 inline level::level_enum get_level() { return detail::current_level(); }
 
 template <class... Args>
-void trace(std::format_string<Args...> f, Args&&... a) { detail::emit(level::trace, std::format(f, std::forward<Args>(a)...)); }
+void trace(std::format_string<Args...> f, Args&&... a) {
+    if (level::trace < detail::current_level()) return;  // (like spdlog: a disabled level formats nothing)
+    detail::emit(level::trace, std::format(f, std::forward<Args>(a)...));
+}
 template <class... Args>
-void debug(std::format_string<Args...> f, Args&&... a) { detail::emit(level::debug, std::format(f, std::forward<Args>(a)...)); }
+void debug(std::format_string<Args...> f, Args&&... a) {
+    if (level::debug < detail::current_level()) return;  // (like spdlog: a disabled level formats nothing)
+    detail::emit(level::debug, std::format(f, std::forward<Args>(a)...));
+}
 template <class... Args>
-void info(std::format_string<Args...> f, Args&&... a) { detail::emit(level::info, std::format(f, std::forward<Args>(a)...)); }
+void info(std::format_string<Args...> f, Args&&... a) {
+    if (level::info < detail::current_level()) return;  // (like spdlog: a disabled level formats nothing)
+    detail::emit(level::info, std::format(f, std::forward<Args>(a)...));
+}
 template <class... Args>
-void warn(std::format_string<Args...> f, Args&&... a) { detail::emit(level::warn, std::format(f, std::forward<Args>(a)...)); }
+void warn(std::format_string<Args...> f, Args&&... a) {
+    if (level::warn < detail::current_level()) return;  // (like spdlog: a disabled level formats nothing)
+    detail::emit(level::warn, std::format(f, std::forward<Args>(a)...));
+}
 template <class... Args>
-void error(std::format_string<Args...> f, Args&&... a) { detail::emit(level::err, std::format(f, std::forward<Args>(a)...)); }
+void error(std::format_string<Args...> f, Args&&... a) {
+    if (level::err < detail::current_level()) return;  // (like spdlog: a disabled level formats nothing)
+    detail::emit(level::err, std::format(f, std::forward<Args>(a)...));
+}
 template <class... Args>
-void critical(std::format_string<Args...> f, Args&&... a) { detail::emit(level::critical, std::format(f, std::forward<Args>(a)...)); }
+void critical(std::format_string<Args...> f, Args&&... a) {
+    if (level::critical < detail::current_level()) return;  // (like spdlog: a disabled level formats nothing)
+    detail::emit(level::critical, std::format(f, std::forward<Args>(a)...));
+}
 
 }  // namespace spdlog
