@@ -35,10 +35,15 @@ struct DeviceCtx {
     double*      scratch  = nullptr;  // equiv partials of up to kMaxLocalShards shard pairs + 8 outputs
     double*      host8    = nullptr;  // pinned
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
-    // parked shard buffers (pool_alloc / pool_free): size -> pointer
-    std::mutex                   pool_mu;
-    std::multimap<size_t, void*> pool;
-    size_t                       pool_bytes = 0, pool_cap = 0;
+    // parked shard buffers (pool_alloc / pool_free): size -> (pointer, parking sequence number)
+    struct Parked {
+        void*    p;
+        uint64_t seq;
+    };
+    std::mutex                    pool_mu;
+    std::multimap<size_t, Parked> pool;
+    size_t                        pool_bytes = 0, pool_cap = 0;
+    uint64_t                      pool_seq = 0;
 };
 cudaError_t pool_alloc(DeviceCtx* c, void** out, size_t bytes);
 void pool_free(DeviceCtx* c, void* p, size_t bytes);
