@@ -51,6 +51,10 @@ ncclComm_t g_rank_comm   = nullptr;
 int g_rank_device        = -1;
 int g_rank_world         = 1;
 
+}  // namespace
+int comm_world_size() { return g_rank_comm != nullptr ? g_rank_world : 1; }
+namespace {
+
 int load_nccl() {
     if (g_nccl.handle != nullptr) return QSX_OK;
     if (g_nccl_tried) return fail(QSX_ERR_NCCL, g_nccl_why);

@@ -12,7 +12,9 @@
 #include <cuda.h>
 #include <dlfcn.h>
 #include <nvrtc.h>
+#include <sys/resource.h>
 #include <sys/stat.h>
+#include <sys/syscall.h>
 #include <sys/types.h>
 #include <unistd.h>
 
@@ -67,6 +69,7 @@ struct Kernel {
     int R = 0, threads = 0, min_ctas = 1;
     bool persistent = false;
     std::string name, source;
+    std::vector<unsigned char> program;  // copy of the serialized sweep until the worker has generated the source from it
     std::atomic<int> state{kQueued};
     std::vector<char> cubin;
     // loading (first launch)
@@ -275,9 +278,12 @@ void compile_one(Kernel* k) {
     nvrtcProgram prog = nullptr;
     std::string err;
     bool ok = false, from_disk = false;
-    std::string const cpath = cache_path(k);
-    if (read_cached(cpath, k->cubin)) ok = from_disk = true;
-    if (!ok) do {
+    bool generated = generate_sweep_source(k->program.data(), k->program.size(), k->R, k->name, k->threads, k->min_ctas, k->persistent,
+                                           k->source, err);
+    std::vector<unsigned char>().swap(k->program);
+    std::string const cpath = generated ? cache_path(k) : std::string();
+    if (generated && read_cached(cpath, k->cubin)) ok = from_disk = true;
+    if (generated && !ok) do {
         nvrtcResult r = g_nvrtc.CreateProgram(&prog, k->source.c_str(), (k->name + ".cu").c_str(), 0, nullptr, nullptr);
         if (r != NVRTC_SUCCESS) {
             err = std::string("nvrtcCreateProgram: ") + g_nvrtc.GetErrorString(r);
@@ -349,6 +355,9 @@ void compile_one(Kernel* k) {
 }
 
 void worker_main() {
+    // the compilers fill every core; the thread that launches the sweeps (and the driver's own threads) must not queue
+    // behind them: a Linux thread has its own nice value
+    setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), 10);
     for (;;) {
         Kernel* k = nullptr;
         {
@@ -432,13 +441,12 @@ Kernel* request(const unsigned char* blob, size_t size, int R, int threads) {
     char nm[64];
     std::snprintf(nm, sizeof(nm), "qsx_sweep_%016llx%016llx", (unsigned long long)h0, (unsigned long long)h1);
     k->name = nm;
-    std::string err;
     if (g_stop) {
         k->state.store(kFailed);
-    } else if (!generate_sweep_source(blob, size, R, k->name, threads, k->min_ctas, k->persistent, k->source, err)) {
-        k->state.store(kFailed);
-        g_last_error = err;
     } else {
+        // (the source is generated by the worker too: ~1 ms per sweep, which for the ~140 sweeps of a 15-qubit plan would
+        //  otherwise sit on the caller's thread in front of the first launch)
+        k->program.assign(blob, blob + size);
         start_pool_locked();
         g_queue.push_back(k.get());
         g_cv_work.notify_one();

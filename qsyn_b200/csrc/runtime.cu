@@ -187,11 +187,28 @@ void request_jit_kernels(qsx::Plan& pl) {
     if (pl.cfg.jit == 0 || !pl.jit_kernels.empty() || pl.sweeps.empty()) return;
     pl.jit_kernels.assign(pl.sweeps.size(), nullptr);
     if (!qsx::jit::available(nullptr)) return;
-    // every process of a job requests the same kernels: each starts at its own offset, so that together with the
-    // on-disk cache (jit.cpp) the ranks compile different kernels first and pick up each other's results
-    size_t const n_sw = pl.sweeps.size(), start = ((size_t)getpid() * 2654435761u >> 7) % n_sw;
+    // Order of compilation.  The compiler (16 threads: ~20 ms per kernel) is slower than the interpreter it competes with
+    // (~12 ms per sweep at n = 15), so on a cold run a kernel is only useful if it is finished before the executor gets to
+    // its sweep: the queue is filled from the LAST sweep backwards -- the executor and the compiler move towards each other
+    // and everything behind the meeting point runs specialised already in the first conversion (in plan order the
+    // compiler would trail the executor and nothing of the first operand would run compiled).  The processes of a
+    // multi-GPU job request the same kernels: each rotates the order by its share (RANK / WORLD_SIZE of the launcher, else a
+    // hash of the pid), so that together with the on-disk cache (jit.cpp) they compile different kernels first and pick up
+    // each other's results.
+    size_t const n_sw = pl.sweeps.size();
+    size_t start      = 0;
+    {
+        char const* const rk = std::getenv("RANK");
+        char const* const ws = std::getenv("WORLD_SIZE");
+        long const world     = ws != nullptr ? std::atol(ws) : 1;
+        long const rank      = rk != nullptr ? std::atol(rk) : 0;
+        if (world > 1 && rank >= 0 && rank < world)
+            start = (size_t)rank * n_sw / (size_t)world;
+        else if (qsx::comm_world_size() > 1)
+            start = ((size_t)getpid() * 2654435761u >> 7) % n_sw;
+    }
     for (size_t i = 0; i < n_sw; ++i) {
-        size_t const s          = (start + i) % n_sw;
+        size_t const s          = n_sw - 1 - (start + i) % n_sw;
         qsx::DevSweep const& hs = *reinterpret_cast<qsx::DevSweep const*>(pl.blob.data() + pl.sweep_offset[s]);
         if (hs.dense_k != 0) continue;
         int const log2_threads = hs.m - pl.cfg.R + hs.log2w;

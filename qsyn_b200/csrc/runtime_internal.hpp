@@ -65,5 +65,7 @@ int materialize(qsx_unitary* u, DeviceCtx* c);   // writes a lazy identity
 // comm.cpp: all-reduce (SUM) of the 8 doubles at out8[k] (device memory of devices[k], in place) over the devices of
 // this process and, when qsx_comm_init_rank was called, over the ranks of the job; enqueued on each device's stream
 int comm_allreduce8(DeviceCtx* const* ctx, double* const* out8, int n_devices);
+// number of processes of the job (1 unless qsx_comm_init_rank was called)
+int comm_world_size();
 
 }  // namespace qsx
