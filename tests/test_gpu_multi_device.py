@@ -118,9 +118,11 @@ def _run_shim(tmp_path, files, dof_text, n_gpus):
     dof = tmp_path / "case.dof"
     dof.write_text(dof_text)
     env = dict(os.environ, QSX_NUM_GPUS=str(n_gpus))
+    # stdout is the product's text interface; stderr is kept apart (NCCL prints its version banner there when the image
+    # exports NCCL_DEBUG=VERSION -- comm.cpp points fd 1 at fd 2 while a communicator is created)
     r = subprocess.run([SHIM, "--no-version", "--qsynrc-path", "/dev/null", "--verbose", str(dof)], cwd=tmp_path, env=env,
-                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
-    return r.returncode, r.stdout
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    return r.returncode, r.stdout if r.returncode == 0 else r.stdout + r.stderr
 
 
 def _qft_dec_qasm(n):
