@@ -83,6 +83,78 @@ def test_reader_quirks_match_oracle():
         host.Circuit(qasm_text=bad)
 
 
+def test_reader_differential_fuzz_against_the_oracle():
+    """Random QASM text with the dialect's quirks -- blanks and tabs anywhere the reference's tokeniser tolerates them,
+    `//` comments, upper-case names, unknown gates, parametrised gates, c^n prefixes, creg/qreg lines, out-of-range and
+    repeated qubit ids, malformed operands -- through the C++ reader (string-view tokeniser, shared operations) and the
+    oracle's restatement of qcir_reader.cpp:47-120: same accept / reject decision, same gates in the same order."""
+    rng = np.random.default_rng(20261020)
+    names1 = ["h", "x", "y", "z", "s", "sdg", "t", "tdg", "sx", "sxdg", "sy", "ty", "id", "H", "Tdg", "not", "x_1_2"]
+    namesp = ["rz", "rx", "ry", "p", "px", "py", "pz", "RZ"]
+    names2 = ["cx", "cz", "cy", "swap", "ecr", "ch", "cs", "CX", "ct"]
+    namespc = ["crz", "cp", "crx", "ccp"]
+    names3 = ["ccx", "ccz", "cswap", "cch"]
+    phases = ["pi", "pi/2", "-pi/4", "3*pi/8", "0.25", "-1.5707963", "pi*3/7", "2*pi", "0", "1e-3", "pi / 2", "abc", "", "pi/0.5"]
+    n_accept = n_reject = 0
+    for trial in range(400):
+        n = int(rng.integers(1, 7))
+        lines = []
+        expect_gate_lines = 0
+        for _ in range(int(rng.integers(0, 25))):
+            kind = rng.random()
+            sp = lambda: " " * int(rng.integers(0, 3)) + ("\t" if rng.random() < 0.1 else "")  # noqa: E731
+            def q(k):
+                ids = [int(x) for x in rng.choice(max(n, 1), size=min(k, n), replace=False)]
+                while len(ids) < k:
+                    ids.append(int(rng.integers(n)))  # forces a repeated id when the gate needs more qubits than exist
+                if rng.random() < 0.03:
+                    ids[0] = n + int(rng.integers(0, 3))  # out of range
+                sep = "," + (" " if rng.random() < 0.3 else "")
+                return sep.join(f"q[{i}]" for i in ids)
+            if kind < 0.45:
+                line = f"{names1[int(rng.integers(len(names1)))]} {q(1)};"
+            elif kind < 0.60:
+                line = f"{namesp[int(rng.integers(len(namesp)))]}({phases[int(rng.integers(len(phases)))]}) {q(1)};"
+            elif kind < 0.78:
+                line = f"{names2[int(rng.integers(len(names2)))]} {q(2)};"
+            elif kind < 0.84:
+                nm = namespc[int(rng.integers(len(namespc)))]
+                line = f"{nm}({phases[int(rng.integers(len(phases)))]}) {q(3 if nm == 'ccp' else 2)};"
+            elif kind < 0.90:
+                line = f"{names3[int(rng.integers(len(names3)))]} {q(3)};"
+            elif kind < 0.93:
+                line = ["barrier q;", "measure q[0] -> c[0];", "creg c[2];", "foo q[0];", "mcx q[0],q[1];", "u3(0,0,0) q[0];"][int(rng.integers(6))]
+            elif kind < 0.96:
+                line = ["", "   ", "// only a comment", "\t"][int(rng.integers(4))]
+            else:
+                line = ["h q0;", "h q[a];", "h q[];", "h ;", "cx q[0] q[1];", "h q[0]", "h  q [0];", "c q[0];"][int(rng.integers(8))]
+            if rng.random() < 0.2:
+                line = sp() + line
+            if rng.random() < 0.15:
+                line = line + sp() + "// note" + ("//x" if rng.random() < 0.3 else "")
+            lines.append(line)
+        text = "OPENQASM 2.0;\ninclude \"qelib1.inc\";\nqreg q[%d];\n" % n + "\n".join(lines) + ("\n" if rng.random() < 0.8 else "")
+        try:
+            qc = O.qcir_from_qasm_text(text)
+        except Exception:  # the oracle mirrors a throw of the reference (e.g. a name of only 'c's): not a case for the diff
+            continue
+        try:
+            c = host.Circuit(qasm_text=text)
+        except Q.QsxError:
+            c = None
+        assert (c is None) == (qc is None), (text, qc is None)
+        if qc is None:
+            n_reject += 1
+            continue
+        n_accept += 1
+        assert (c.n_qubits, c.n_gates) == (qc.n_qubits, len(qc.gates)), text
+        assert c.gate_reprs() == [(g.gid, g.op.repr()) for g in qc.topological_order()], text
+        for (nc, qs, m), (onc, oqs, om) in zip(c.gate_stream(), O.gate_stream(qc)):
+            assert nc == onc and qs == oqs and np.allclose(m, om, rtol=0, atol=5e-16), text
+        c.close()
+    assert n_accept >= 100 and n_reject >= 30, (n_accept, n_reject)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["benchmark/qft/qft_5.qasm", "benchmark/qasm/qc2ts/toffoli_qiskit.qasm",
                                   "benchmark/SABRE/small/3_17_13.qasm", "benchmark/qft/qft_8crz.qasm"])
