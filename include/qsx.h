@@ -191,6 +191,10 @@ int qsx_jit_get_stats(qsx_jit_stats* stats);
 typedef int (*qsx_stop_fn)(void* arg); /* mirrors `extern bool stop_requested()` (qcir_to_tensor.cpp:20) */
 
 #define QSX_RUN_ASYNC 1u /* do not synchronise at the end (for event timing on qsx_device_stream) */
+/* Do not synchronise at the end when the enqueued sweeps are SHORT (less than 64 GB of HBM traffic, about 12 ms): there is
+ * nothing worth interrupting, and the caller's next host work (parsing and lowering the other operand of a check)
+ * overlaps the device.  A long run is synchronous as without the flag (the stop callback is honoured promptly). */
+#define QSX_RUN_ASYNC_IF_SHORT 2u
 
 typedef struct qsx_run_stats {
     uint64_t launches;   /* kernels launched by this call        */
@@ -215,6 +219,10 @@ int qsx_apply_gates(qsx_unitary* u, const qsx_gate* gates, size_t n_gates, const
  * synchronising call on the device (download, equiv_partial, qsx_device_synchronize). */
 int qsx_apply_gates_async(qsx_unitary* u, const qsx_gate* gates, size_t n_gates, const qsx_plan_options* opt,
                           qsx_run_stats* stats);
+/* The general form: qsx_apply_gates with run flags (QSX_RUN_ASYNC, QSX_RUN_ASYNC_IF_SHORT).  The host layer's
+ * to_tensor(QCir) calls it with QSX_RUN_ASYNC_IF_SHORT and its stop callback. */
+int qsx_apply_gates_ex(qsx_unitary* u, const qsx_gate* gates, size_t n_gates, const qsx_plan_options* opt,
+                       qsx_stop_fn should_stop, void* stop_arg, uint32_t flags, qsx_run_stats* stats);
 
 /* ---- verification: replaces inner_product / cosine_similarity (tensor.hpp:393-403) and
  *      global_scalar_factor / global_norm / global_phase / is_equivalent (qtensor.hpp:383-417) ---- */

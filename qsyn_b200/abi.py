@@ -11,6 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 QSX_MAX_GATE_QUBITS = 16
 QSX_RUN_ASYNC = 1
+QSX_RUN_ASYNC_IF_SHORT = 2
 
 STATUS = {
     0: "QSX_OK", 1: "QSX_ERR_BAD_ARG", 2: "QSX_ERR_OOM", 3: "QSX_ERR_INTERRUPTED", 4: "QSX_ERR_CUDA",
@@ -124,6 +125,8 @@ def _declare(L: C.CDLL) -> None:
         "qsx_apply_gates": [vp, C.POINTER(GateStruct), C.c_size_t, C.POINTER(PlanOptions), STOP_FN, vp,
                             C.POINTER(RunStats)],
         "qsx_apply_gates_async": [vp, C.POINTER(GateStruct), C.c_size_t, C.POINTER(PlanOptions), C.POINTER(RunStats)],
+        "qsx_apply_gates_ex": [vp, C.POINTER(GateStruct), C.c_size_t, C.POINTER(PlanOptions), STOP_FN, vp, C.c_uint32,
+                               C.POINTER(RunStats)],
         "qsx_plan_compile": [vp, i32],
         "qsx_jit_get_stats": [C.POINTER(JitStats)],
         "qsx_init": [i32],
@@ -275,6 +278,15 @@ class Unitary:
         cb = STOP_FN(lambda _arg: int(bool(should_stop()))) if should_stop is not None else C.cast(None, STOP_FN)
         _check(lib().qsx_apply_gates(self._h, arr, n, C.byref(options) if options is not None else None, cb, None,
                                      C.byref(st)))
+        return st
+
+    def apply_ex(self, gates: Iterable[tuple], flags: int, options: PlanOptions | None = None, should_stop=None) -> RunStats:
+        """qsx_apply_gates_ex: apply with run flags (QSX_RUN_ASYNC, QSX_RUN_ASYNC_IF_SHORT) and the stop callback."""
+        arr, keep, n = pack_gates(gates)
+        st = RunStats()
+        cb = STOP_FN(lambda _arg: int(bool(should_stop()))) if should_stop is not None else C.cast(None, STOP_FN)
+        _check(lib().qsx_apply_gates_ex(self._h, arr, n, C.byref(options) if options is not None else None, cb, None, flags,
+                                        C.byref(st)))
         return st
 
     def apply_async(self, gates, options: PlanOptions | None = None) -> RunStats:

@@ -478,7 +478,9 @@ namespace {
 int run_sweeps(qsx::Plan& pl, qsx_unitary* u, DeviceCtx* c, unsigned char* dblob, qsx_stop_fn should_stop,
                void* stop_arg, uint32_t flags, qsx_run_stats* stats) {
     request_jit_kernels(pl);
-    bool const async = (flags & QSX_RUN_ASYNC) != 0;
+    // QSX_RUN_ASYNC_IF_SHORT: under 64 GB of HBM traffic (~12 ms; the amount after which a run with a stop callback drains
+    // the stream for the first time, below) the call returns once the sweeps are enqueued
+    bool const async = (flags & QSX_RUN_ASYNC) != 0 || ((flags & QSX_RUN_ASYNC_IF_SHORT) != 0 && pl.stats.alg_bytes_per_run < 64e9);
     if (!async) QSX_CUDA(cudaEventRecord(c->ev0, c->stream));
     uint64_t launches = 0, jit_launches = 0;
     // Column blocking through the L2 (plan option l2_block_mib): all sweeps run on one block of columns before
@@ -695,7 +697,7 @@ int apply_impl(qsx_unitary* u, const qsx_gate* gates, size_t n_gates, const qsx_
     }
     int const rc = run_plan(plan.get(), u, should_stop, stop_arg, flags, stats);
     if (stats != nullptr) stats->plan_cache_hit = hit ? 1 : 0;
-    if ((flags & QSX_RUN_ASYNC) != 0 && cap == 0) {
+    if ((flags & (QSX_RUN_ASYNC | QSX_RUN_ASYNC_IF_SHORT)) != 0 && cap == 0) {
         // nobody else owns the plan: its programs must outlive the enqueued sweeps
         DeviceCtx* c = nullptr;
         if (get_ctx(u->device, &c) == QSX_OK) cudaStreamSynchronize(c->stream);
@@ -712,6 +714,12 @@ int qsx_apply_gates(qsx_unitary* u, const qsx_gate* gates, size_t n_gates, const
 int qsx_apply_gates_async(qsx_unitary* u, const qsx_gate* gates, size_t n_gates, const qsx_plan_options* opt,
                           qsx_run_stats* stats) {
     return apply_impl(u, gates, n_gates, opt, nullptr, nullptr, QSX_RUN_ASYNC, stats);
+}
+
+int qsx_apply_gates_ex(qsx_unitary* u, const qsx_gate* gates, size_t n_gates, const qsx_plan_options* opt, qsx_stop_fn should_stop,
+                       void* stop_arg, uint32_t flags, qsx_run_stats* stats) {
+    if ((flags & ~(QSX_RUN_ASYNC | QSX_RUN_ASYNC_IF_SHORT)) != 0) return fail(QSX_ERR_BAD_ARG, "unknown run flag");
+    return apply_impl(u, gates, n_gates, opt, should_stop, stop_arg, flags, stats);
 }
 
 // ---- verification -----------------------------------------------------------------------

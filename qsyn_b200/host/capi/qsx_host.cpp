@@ -233,7 +233,7 @@ int qsxh_qc2ts(const qsxh_circuit* c, qsxh_tensor** out) {
         if (c->qcir.get_num_qubits() == 0) return fail(QSX_ERR_BAD_ARG, "QCir is empty!!");
         auto t = qsyn::to_tensor(c->qcir);  // conversion_cmd.cpp:86
         if (!t.has_value()) return fail(QSX_ERR_UNSUPPORTED, "conversion failed (see the log)");
-        *t   = t->to_matrix();              // conversion_cmd.cpp:89
+        *t   = std::move(*t).to_matrix();   // conversion_cmd.cpp:89 (the rvalue form re-tags the device tensor, no clone)
         t->set_filename(c->qcir.get_filename());
         t->add_procedures(c->qcir.get_procedures());
         t->add_procedure("QC2TS");

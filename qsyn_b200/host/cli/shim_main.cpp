@@ -448,7 +448,7 @@ struct Shell {
         spdlog::info("Converting to QCir {} to Tensor {}...", qcir_mgr.focused_id(), tensor_mgr.get_next_id());
         auto tensor = qsyn::to_tensor(*qcir_mgr.get());
         if (tensor.has_value()) {
-            *tensor = tensor->to_matrix();
+            *tensor = std::move(*tensor).to_matrix();  // (rvalue form: the device tensor is re-tagged, not cloned)
             tensor_mgr.add(tensor_mgr.get_next_id());
             tensor_mgr.set(std::make_unique<QTensor<double>>(std::move(tensor.value())));
             tensor_mgr.get()->set_filename(qcir_mgr.get()->get_filename());

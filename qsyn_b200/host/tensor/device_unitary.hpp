@@ -108,7 +108,11 @@ public:
     int apply(std::vector<qsx_gate> const& gates, qsx_stop_fn should_stop = nullptr, void* stop_arg = nullptr) {
         if (_shards.empty()) return QSX_ERR_BAD_ARG;
         if (_shards.size() == 1) {
-            int const rc = qsx_apply_gates(_shards[0], gates.data(), gates.size(), nullptr, should_stop, stop_arg, nullptr);
+            // a short stream (milliseconds of device time) is only enqueued: the caller's next host work -- reading and
+            // lowering the other operand of a check -- overlaps it, and every later use of the tensor is ordered behind it
+            // on the device's stream; a long one is waited for, with the stop callback polled between sweeps
+            int const rc = qsx_apply_gates_ex(_shards[0], gates.data(), gates.size(), nullptr, should_stop, stop_arg,
+                                              QSX_RUN_ASYNC_IF_SHORT, nullptr);
             if (rc == QSX_ERR_OOM) throw std::bad_alloc();
             return rc;
         }

@@ -84,7 +84,8 @@ public:
     std::string get_filename() const { return _filename; }
     std::vector<std::string> const& get_procedures() const { return _procedures; }
 
-    QTensor<T> to_matrix();
+    QTensor<T> to_matrix() &;
+    QTensor<T> to_matrix() &&;  // moves a device-resident tensor instead of cloning it (tensor.hpp)
     QTensor<T> to_matrix(TensorAxisList const& out, TensorAxisList const& in) { return Base::to_matrix(out, in); }
 
     // the device-resident unitary behind this tensor (nullptr for a host tensor)
@@ -230,7 +231,7 @@ QTensor<T> QTensor<T>::control(QTensor<T> const& gate, size_t n_ctrls) {
 
 // rank-2n [o0,i0,...] -> 2^n x 2^n matrix [outputs | inputs] (qtensor.hpp:442-452)
 template <typename T>
-QTensor<T> QTensor<T>::to_matrix() {
+QTensor<T> QTensor<T>::to_matrix() & {
     auto const n_qubits = this->dimension() / 2;
     TensorAxisList out, in;
     for (size_t i = 0; i < n_qubits; ++i) {
@@ -240,6 +241,22 @@ QTensor<T> QTensor<T>::to_matrix() {
     QTensor<T> r    = this->to_matrix(out, in);
     r._filename     = _filename;
     r._procedures   = _procedures;
+    return r;
+}
+
+template <typename T>
+QTensor<T> QTensor<T>::to_matrix() && {
+    auto const n_qubits = this->dimension() / 2;
+    TensorAxisList out, in;
+    for (size_t i = 0; i < n_qubits; ++i) {
+        out.emplace_back(2 * i);
+        in.emplace_back(2 * i + 1);
+    }
+    std::string filename                = std::move(_filename);
+    std::vector<std::string> procedures = std::move(_procedures);
+    QTensor<T> r    = static_cast<Base&&>(*this).to_matrix(out, in);
+    r._filename     = std::move(filename);
+    r._procedures   = std::move(procedures);
     return r;
 }
 

@@ -218,7 +218,10 @@ public:
     template <typename U>
     friend Tensor<U> direct_sum(Tensor<U> const& t1, Tensor<U> const& t2);
 
-    Tensor<DT> to_matrix(TensorAxisList const& row_axes, TensorAxisList const& col_axes);
+    Tensor<DT> to_matrix(TensorAxisList const& row_axes, TensorAxisList const& col_axes) &;
+    // on a temporary (`*t = std::move(*t).to_matrix()`, the conversion_cmd.cpp:89 pattern): a device-resident tensor is
+    // re-tagged and MOVED -- the lvalue form has to clone 16 * 4^n bytes on the device to leave the original intact
+    Tensor<DT> to_matrix(TensorAxisList const& row_axes, TensorAxisList const& col_axes) &&;
 
     void reshape(TensorShape const& shape) {
         _require_host("reshape");
@@ -392,7 +395,26 @@ bool is_partition(Tensor<U> const& t, TensorAxisList const& axes1, TensorAxisLis
 
 // Convert the tensor to a matrix according to the two axis lists (tensor.hpp:266-274)
 template <typename DT>
-Tensor<DT> Tensor<DT>::to_matrix(TensorAxisList const& row_axes, TensorAxisList const& col_axes) {
+Tensor<DT> Tensor<DT>::to_matrix(TensorAxisList const& row_axes, TensorAxisList const& col_axes) && {
+    if constexpr (std::is_same_v<DT, std::complex<double>>) {
+        if (_dev.resident() && is_partition(*this, row_axes, col_axes)) {
+            bool canonical = _dev.as_matrix ? (row_axes == TensorAxisList{0} && col_axes == TensorAxisList{1}) : row_axes.size() == col_axes.size();
+            for (size_t i = 0; !_dev.as_matrix && canonical && i < row_axes.size(); ++i)
+                canonical = row_axes[i] == 2 * i && col_axes[i] == 2 * i + 1;
+            if (canonical) {
+                if (!_dev.as_matrix) {
+                    _dev.as_matrix = true;
+                    reset_axis_history();
+                }
+                return std::move(*this);
+            }
+        }
+    }
+    return static_cast<Tensor<DT>&>(*this).to_matrix(row_axes, col_axes);
+}
+
+template <typename DT>
+Tensor<DT> Tensor<DT>::to_matrix(TensorAxisList const& row_axes, TensorAxisList const& col_axes) & {
     if (!is_partition(*this, row_axes, col_axes)) {
         throw std::invalid_argument("The two axis lists should partition 0~(n-1).");
     }

@@ -134,3 +134,46 @@ def test_nested_circuit_gate_through_qc2ts():
     outer, want = _nested_example()
     got = outer.qc2ts().to_numpy()
     assert np.abs(got - want).max() < 1e-14
+
+
+def test_short_conversions_are_enqueued_long_ones_are_waited_for():
+    """to_tensor(QCir) calls qsx_apply_gates_ex with QSX_RUN_ASYNC_IF_SHORT: a stream of less than 64 GB of HBM traffic is
+    only enqueued (device_ms is not measured, the result is ordered behind it on the device's stream), a longer one is
+    synchronous with the stop callback polled between sweeps.  Either way the values are those of the plain call."""
+    import qsyn_b200 as Q
+    from qsyn_b200 import abi
+
+    n = 11
+    qc = O.qcir_from_qasm_text(O.random_clifford_t_qasm(n, 500, 17))
+    gs = O.gate_stream(qc)
+    ref = Q.Unitary(n)
+    st_ref = ref.apply(gs)
+    assert st_ref.device_ms > 0
+    want = ref.download()
+    polls = []
+    u = Q.Unitary(n)
+    st = u.apply_ex(gs, abi.QSX_RUN_ASYNC_IF_SHORT, should_stop=lambda: polls.append(1) and False)
+    assert st.device_ms == 0 and st.launches == st_ref.launches and len(polls) >= st.launches - 1  # enqueued, callback polled per sweep
+    assert np.array_equal(u.download(), want)
+    # one gate per sweep at n = 12: ~500 passes over (a fraction of) 256 MiB, well over 64 GB -> a long run: synchronous
+    gs12 = O.gate_stream(O.qcir_from_qasm_text(O.random_clifford_t_qasm(12, 500, 18)))
+    ref12, v = Q.Unitary(12), Q.Unitary(12)
+    ref12.apply(gs12)
+    st = v.apply_ex(gs12, abi.QSX_RUN_ASYNC_IF_SHORT, Q.PlanOptions(fuse=0, l2_block_mib=-1))
+    assert st.device_ms > 0 and st.launches >= 400
+    assert np.abs(v.download() - ref12.download()).max() < 1e-12
+    ref12.close(), v.close()
+    # the stop callback still interrupts an enqueue-only run
+    w = Q.Unitary(n)
+    with pytest.raises(Q.QsxError) as ei:
+        w.apply_ex(gs, abi.QSX_RUN_ASYNC_IF_SHORT, should_stop=lambda: True)
+    assert ei.value.status == "QSX_ERR_INTERRUPTED"
+    with pytest.raises(Q.QsxError):
+        w.apply_ex(gs, 64)
+    # through the host layer: two conversions back to back and the check give the text of the synchronous path
+    text = O.random_clifford_t_qasm(n, 500, 17)
+    ca, cb = _circuit(text), _circuit(text + "t q[0];\nx q[0];\nt q[0];\nx q[0];\n")
+    ta, tb = ca.qc2ts(), cb.qc2ts()
+    r, verdict = ta.equiv(tb)
+    assert verdict == "Equivalent\n- Global Norm : 1\n- Global Phase: π/4\n"
+    assert np.array_equal(ta.to_numpy(), want)
