@@ -14,7 +14,8 @@ during construction); the 8 partial sums are combined with ONE ncclAllReduce iss
 
 Default workload: C4 (n = 15, 10 000 Clifford+T gates, 16 GiB unitary): HBM-resident on every GPU count
 (2 GiB per GPU at N = 8).  `extra.c2` repeats the measurement on C2 (256 MiB: L2-assisted, the small end of the
-metric's range) and, on 8 GPUs, `extra.c5` on the north-star target C5 (n = 16, 64 GiB).
+metric's range), `extra.c3` on C3 (QFT-14, 4 GiB, two sweeps per operand) and, on 8 GPUs, `extra.c5` on the north-star
+target C5 (n = 16, 64 GiB).
 
 metric `value` = effective gate-apply throughput: sum over GATES of the algorithmic bytes the
 reference touches for that gate (f * 32 B * 4^n) divided by the device time of
@@ -419,7 +420,7 @@ def run_ours(args):
     c = setup(args)
     out = measure(c, args, args.workload, args.steps, args.warmup, min(args.steps, args.e2e_steps), True)
     extras = [x for x in args.extras.split(",") if x] if args.extras != "auto" else \
-        ([] if args.workload == "c2" else ["c2"]) + (["c5"] if c.world >= 8 and args.workload != "c5" else [])
+        [w for w in ("c2", "c3") if w != args.workload] + (["c5"] if c.world >= 8 and args.workload != "c5" else [])
     extra = {}
     for w in extras:
         few = w in ("c4", "c5")
@@ -625,7 +626,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c4", choices=["c2", "c3", "c4", "c5", "tiny", "rot"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--extras", default="auto", help="comma list of further workloads reported under `extra` (auto: c2, and c5 on 8 GPUs)")
+    ap.add_argument("--extras", default="auto", help="comma list of further workloads reported under `extra` (auto: c2, c3, and c5 on 8 GPUs)")
     ap.add_argument("--e2e-steps", type=int, default=10, help="timed end-to-end steps (at most --steps)")
     ap.add_argument("--cap", type=int, default=0, help="max ops per sweep (0: library default)")
     ap.add_argument("--tile", type=int, default=0, help="tile row bits (0: library default: 9 with specialised sweeps, else 8)")
