@@ -59,6 +59,8 @@ WORKLOADS = {
     "tiny": (8, "clifford_t", 400, 7, "tiny: 8-qubit random Clifford+T, 400 gates (smoke)"),
     # not a BASELINE config: the dense-rotation circuit the dense k-qubit blocks are compared on
     "rot": (12, "rotation", 2000, 20261022, "rot: 12-qubit random rx/ry/rz (75 %) + cx circuit, 2000 gates (256 MiB unitary)"),
+    # parity-only: generic (non-Clifford) 2x2 matrices at a size where rounding has room to accumulate
+    "rot14": (14, "rotation", 6000, 20261023, "rot14: 14-qubit random rx/ry/rz (75 %) + cx circuit, 6000 gates (4 GiB unitary)"),
 }
 
 

@@ -159,7 +159,9 @@ VARIANTS = [
     ("c2", "dense5", {"dense_block": 5}),
     ("c3", "default", {}),
     ("c4", "default", {}),
+    ("c4", "dense5", {"dense_block": 5}),   # BASELINE configs[3] literally: "with k-qubit gate fusion on the FP64 tensor pipe" (822 blocks)
     ("c5", "default", {}),
+    ("rot14", "default", {}),               # not a BASELINE config: 6000 generic rotations, no matrix entry is snapped
 ]
 
 
