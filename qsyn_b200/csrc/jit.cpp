@@ -56,6 +56,7 @@ struct Driver {
     CUresult (*LibraryGetKernel)(CUkernel*, CUlibrary, const char*)                                                           = nullptr;
     CUresult (*KernelSetAttribute)(CUfunction_attribute, int, CUkernel, CUdevice)                                             = nullptr;
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+    CUresult (*LaunchKernelEx)(const CUlaunchConfig*, CUfunction, void**, void**)                                              = nullptr;  // optional
     CUresult (*GetErrorString)(CUresult, const char**)                                                                        = nullptr;
     CUresult (*CtxGetDevice)(CUdevice*)                                                                                       = nullptr;
 };
@@ -152,6 +153,13 @@ bool load_driver(std::string& why) {
     g_drv.LaunchKernel       = reinterpret_cast<decltype(g_drv.LaunchKernel)>(get("cuLaunchKernel"));
     g_drv.GetErrorString     = reinterpret_cast<decltype(g_drv.GetErrorString)>(get("cuGetErrorString"));
     g_drv.CtxGetDevice       = reinterpret_cast<decltype(g_drv.CtxGetDevice)>(get("cuCtxGetDevice"));
+    {
+        // programmatic dependent launch is an optimisation: its absence is not an error
+        bool const was_ok = ok;
+        std::string const was_why = why;
+        g_drv.LaunchKernelEx = reinterpret_cast<decltype(g_drv.LaunchKernelEx)>(get("cuLaunchKernelEx"));
+        ok = was_ok, why = was_why;
+    }
     return ok;
 }
 
@@ -530,7 +538,31 @@ cudaError_t launch(Kernel* k, double2* u, int log2_ncols, int log2_ncb, uint32_t
         if (cudaError_t const e = cudaMemsetAsync(ctr, 0, sizeof(uint32_t), stream); e != cudaSuccess) return e;
     }
     void* args[] = {&u, &log2_ncols, &log2_ncb, &flags, &col0, &pf, &ctr};
-    CUresult const r = g_drv.LaunchKernel(reinterpret_cast<CUfunction>(k->kern), grid, 1, 1, threads, 1, 1, (unsigned)smem, stream, args, nullptr);
+    // Programmatic dependent launch: a generated sweep signals `launch_dependents` when it starts and executes
+    // `griddepcontrol.wait` before its first global access (jit_codegen.cpp), so the NEXT sweep's CTAs are scheduled and run
+    // their index prologue while the last wave of this one drains; the data dependence itself is untouched (the wait returns
+    // when the previous grid has completed and its writes are visible).  Worth ~1-2 us per launch: nothing for a 6 ms sweep,
+    // 10 % for the 15 us sweeps of a 32 MiB shard.  QSX_JIT_PDL=0 launches the plain way.
+    static bool const pdl = [] {
+        char const* e = std::getenv("QSX_JIT_PDL");
+        return e == nullptr || std::atoi(e) != 0;
+    }();
+    CUresult r;
+    if (pdl && g_drv.LaunchKernelEx != nullptr) {
+        CUlaunchAttribute attr{};
+        attr.id                                         = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+        attr.value.programmaticStreamSerializationAllowed = 1;
+        CUlaunchConfig cfg{};
+        cfg.gridDimX = grid, cfg.gridDimY = 1, cfg.gridDimZ = 1;
+        cfg.blockDimX = threads, cfg.blockDimY = 1, cfg.blockDimZ = 1;
+        cfg.sharedMemBytes = (unsigned)smem;
+        cfg.hStream        = stream;
+        cfg.attrs          = &attr;
+        cfg.numAttrs       = 1;
+        r = g_drv.LaunchKernelEx(&cfg, reinterpret_cast<CUfunction>(k->kern), args, nullptr);
+    } else {
+        r = g_drv.LaunchKernel(reinterpret_cast<CUfunction>(k->kern), grid, 1, 1, threads, 1, 1, (unsigned)smem, stream, args, nullptr);
+    }
     if (r != CUDA_SUCCESS) {
         std::lock_guard<std::mutex> g(g_mu);
         g_last_error = "launching " + k->name + ": " + cu_error(r);
