@@ -34,6 +34,24 @@ def test_no_cpu_fallback_when_no_device():
     assert ei.value.status == "QSX_ERR_CUDA" and "no CPU fallback" in str(ei.value)
 
 
+def test_apply_gates_ex_checks_its_arguments_before_touching_a_device():
+    """qsx_apply_gates_ex (the general form to_tensor(QCir) calls): unknown run flags and null handles are QSX_ERR_BAD_ARG
+    on any host; the flag values are those of include/qsx.h."""
+    import ctypes as C
+
+    from qsyn_b200 import abi
+
+    L = Q.lib()
+    assert (abi.QSX_RUN_ASYNC, abi.QSX_RUN_ASYNC_IF_SHORT) == (1, 2)
+    hdr = open(os.path.join(ROOT, "include", "qsx.h")).read()
+    assert "#define QSX_RUN_ASYNC 1u" in hdr and "#define QSX_RUN_ASYNC_IF_SHORT 2u" in hdr
+    null_stop = C.cast(None, abi.STOP_FN)
+    assert L.qsx_apply_gates_ex(None, None, 0, None, null_stop, None, 64, None) != 0
+    assert b"unknown run flag" in L.qsx_last_error()
+    assert L.qsx_apply_gates_ex(None, None, 0, None, null_stop, None, abi.QSX_RUN_ASYNC_IF_SHORT, None) != 0
+    assert b"null unitary" in L.qsx_last_error()
+
+
 def _rand_circuit(n, g, seed, extra=True):
     qc = O.qcir_from_qasm_text(O.random_clifford_t_qasm(n, g, seed))
     if extra:  # sprinkle the rest of the reference gate set
